@@ -1,0 +1,91 @@
+"""ctypes binding of libcoinops.so (the C ABI declared in include/coinops.h).
+
+There is no fallback: if the shared library is missing or a symbol cannot be resolved, importing
+this module raises. Every call checks the return code and raises with ``coin_last_error()``.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcoinops.so")
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY = 0, 1, 2, 3, 4
+F32, F16 = 0, 1
+NMS_PLAIN, NMS_TRICK, NMS_VANILLA, NMS_AUTO = 0, 1, 2, 3
+SCORE_PROBEN, SCORE_AVG, SCORE_MAX = 0, 1, 2
+BOX_SAVG, BOX_AVG, BOX_MAX = 0, 1, 2
+TAG_RCNN, TAG_RPN = 0, 1
+MAX_LEVELS = 8
+ABC_MAX = 1024
+
+
+class CoinLevel(Structure):
+    _fields_ = [("feat_nhwc", c_void_p), ("H", c_int), ("W", c_int), ("spatial_scale", c_float)]
+
+
+P = c_void_p
+_SIGNATURES = {
+    # name: (restype, [argtypes])
+    "coin_last_error": (c_char_p, []),
+    "coin_version": (c_int, []),
+    "coin_nchw_to_nhwc_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, P]),
+    "coin_nhwc_f32_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "coin_roi_align_fwd": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, P]),
+    "coin_roi_align_bwd": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, P]),
+    "coin_roi_pooler_levels": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P]),
+    "coin_apply_deltas": (c_int, [P, P, P, c_int64, c_int, c_float, c_float, c_float, c_float, c_float,
+                                  c_int, c_float, c_float, P]),
+    "coin_get_deltas": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P]),
+    "coin_boxes_clip": (c_int, [P, c_int64, c_float, c_float, P]),
+    "coin_boxes_scale_flip": (c_int, [P, P, c_int64, c_float, c_float, c_int, c_float, c_float, P]),
+    "coin_pairwise_iou": (c_int, [P, c_int64, P, c_int64, P, P]),
+    "coin_matcher": (c_int, [P, c_int64, c_int64, POINTER(c_float), c_int, POINTER(ctypes.c_int8), c_int,
+                             P, P, P, P, P]),
+    "coin_iou_match": (c_int, [P, c_int64, P, c_int64, POINTER(c_float), c_int, POINTER(ctypes.c_int8),
+                               c_int, P, P, P, P, P]),
+    "coin_relabel_roi": (c_int, [P, P, c_int64, c_int64, c_int64, P]),
+    "coin_relabel_rpn": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, P]),
+    "coin_iou_pairs_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "coin_iou_pairs_ge": (c_int, [P, c_int64, P, c_int64, c_float, P, P, c_int64, P, c_size_t, P]),
+    "coin_nms_workspace_bytes": (c_size_t, [c_int64]),
+    "coin_batched_nms": (c_int, [P, P, P, c_int64, c_double, c_int, c_int64, P, P, P, c_size_t, P]),
+    "coin_fusion_nms_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "coin_fusion_nms": (c_int, [P, P, P, c_int64, c_int, c_float, c_int, c_int, c_int, P, P, P, P, P, P, P,
+                                P, c_size_t, P]),
+    "coin_det_postprocess_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "coin_det_postprocess": (c_int, [P, P, c_int64, c_int, c_int, c_float, c_float, c_float, c_double,
+                                     c_int64, c_int64, P, P, P, P, P, P, P, c_size_t, P]),
+    "coin_match_abc_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "coin_match_abc": (c_int, [P, P, P, c_int64, P, P, P, c_int64, c_int, c_float, c_float, c_int64,
+                               P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+}
+
+EXPORTS = tuple(_SIGNATURES.keys())
+
+if not os.path.exists(SO_PATH):
+    raise ImportError(
+        f"{SO_PATH} is missing: build it with `python -m coin_b200.build` (nvcc, sm_100a). "
+        "coin_b200 has no CPU or PyTorch fallback.")
+
+lib = ctypes.CDLL(SO_PATH)
+for _name, (_res, _args) in _SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = the library does not export the declared ABI
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class CoinError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libcoinops error {code}: {message}")
+        self.code = code
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        msg = lib.coin_last_error().decode("utf-8", "replace")
+        if rc == ERR_INVALID:
+            raise ValueError(f"libcoinops: {msg}")
+        raise CoinError(rc, msg)

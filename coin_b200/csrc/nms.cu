@@ -1,0 +1,379 @@
+// nms.cu -- greedy NMS / batched NMS as a sort + 64x64 bit-mask + single-CTA sweep.
+//
+// Replaces torchvision::nms / torchvision.ops.boxes.batched_nms behind detectron2.layers.batched_nms,
+// reached from coin/modeling/roi_heads/fast_rcnn.py:164 (final detections, per class),
+// coin/layers/nms.py:207 ('nms'/'mm' pseudo-label NMS), coin/modeling/meta_arch/clip_rcnn.py:161 and
+// the d2 RPN proposal selection (<- coin/modeling/proposal_generator/rpn.py:113).
+//
+// Semantics follow the CPU oracle (the torchvision CPU kernel): stable descending sort (ties: lower
+// original index first), areas (x2-x1)*(y2-y1), suppress when inter/(a_i+a_j-inter) > thr with the
+// float IoU compared against the DOUBLE threshold (done here by rounding the threshold down to the
+// nearest float, which is equivalent for a strict '>'), keep list in descending-score order.
+// batched variants: TRICK adds idx*(max+1) to the coordinates in fp32 exactly as torchvision does
+// (so near-threshold roundings match), VANILLA restricts suppression to equal classes.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace coin {
+
+constexpr int kSmallSort = 4096;  // single-CTA bitonic sort up to this many boxes
+
+// descending score, ascending index  ->  ascending 64-bit key
+__device__ __forceinline__ uint64_t sort_key(float s, uint32_t idx) {
+    s = s + 0.0f;  // -0.0 -> +0.0 so that signed zeros tie like they do on the CPU
+    uint32_t u = __float_as_uint(s);
+    if (s != s) u = 0x7fc00000u;                       // NaN sorts first, as torch's descending sort
+    u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;        // ascending-orderable
+    return ((uint64_t)(~u) << 32) | idx;
+}
+
+// meta[0] = live box count n (<= n_cap), meta[1] = resolved strategy. Every kernel of the pipeline is
+// launched for the host-known capacity n_cap and reads the live n from `meta`, so a caller can chain
+// NMS behind a device-side compaction without a host synchronisation.
+__device__ __forceinline__ int resolve_n(int n_cap, const int32_t* n_dev) {
+    return n_dev ? min(max(*n_dev, 0), n_cap) : n_cap;
+}
+__device__ __forceinline__ int resolve_strategy(int strategy, int n) {
+    // torchvision CPU rule (boxes.numel() > 4000 -> per-class) behind the d2 wrapper
+    if (strategy == COIN_NMS_AUTO) return (n * 4 > 4000) ? COIN_NMS_VANILLA : COIN_NMS_TRICK;
+    return strategy;
+}
+
+__global__ void make_keys_kernel(const float* __restrict__ scores, int n_cap, const int32_t* __restrict__ n_dev,
+                                 int strategy, uint64_t* __restrict__ keys, int32_t* __restrict__ meta) {
+    const int n = resolve_n(n_cap, n_dev);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { meta[0] = n; meta[1] = resolve_strategy(strategy, n); }
+    if (i < n_cap) keys[i] = i < n ? sort_key(__ldg(scores + i), (uint32_t)i) : ~0ull;
+}
+
+// max over all 4n coordinates (for the coordinate trick); result as orderable int via atomicMax
+__global__ void max_coord_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ meta,
+                                 float* __restrict__ out_max) {
+    const int n = meta[0];
+    if (meta[1] != COIN_NMS_TRICK) return;
+    float m = -INFINITY;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 b = __ldg(boxes + i);
+        m = fmaxf(fmaxf(m, fmaxf(b.x, b.y)), fmaxf(b.z, b.w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) {
+        // float max through integer atomics: order-preserving map for any sign
+        int bits = __float_as_int(m);
+        bits = bits >= 0 ? bits : bits ^ 0x7fffffff;
+        atomicMax(reinterpret_cast<int*>(out_max), bits);
+    }
+}
+
+__device__ __forceinline__ float decode_max(const float* p) {
+    int bits = *reinterpret_cast<const int*>(p);
+    bits = bits >= 0 ? bits : bits ^ 0x7fffffff;
+    return __int_as_float(bits);
+}
+
+// sorted position -> box (with the class offset when strategy == TRICK), class id, original index
+__global__ void gather_sorted_kernel(const uint64_t* __restrict__ keys, const float4* __restrict__ boxes,
+                                     const int64_t* __restrict__ idxs, const int32_t* __restrict__ meta,
+                                     const float* __restrict__ max_coord, float4* __restrict__ sboxes,
+                                     int32_t* __restrict__ scls, int32_t* __restrict__ order) {
+    const int n = meta[0], strategy = meta[1];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t src = (uint32_t)(keys[i] & 0xffffffffu);
+    float4 b = __ldg(boxes + src);
+    const int64_t cls = idxs ? __ldg(idxs + src) : 0;
+    if (strategy == COIN_NMS_TRICK) {
+        const float off = (float)cls * (decode_max(max_coord) + 1.0f);
+        b.x += off; b.y += off; b.z += off; b.w += off;
+    }
+    sboxes[i] = b;
+    scls[i] = (int32_t)cls;
+    order[i] = (int32_t)src;
+}
+
+// Single-CTA path for n <= kSmallSort: key generation, bitonic sort, max-reduce and gather fused.
+__global__ void __launch_bounds__(1024)
+small_sort_gather_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes,
+                         const int64_t* __restrict__ idxs, int n_cap, const int32_t* __restrict__ n_dev,
+                         int strategy_in, float4* __restrict__ sboxes, int32_t* __restrict__ scls,
+                         int32_t* __restrict__ order, int32_t* __restrict__ meta) {
+    extern __shared__ uint64_t skeys[];
+    __shared__ float smax[32];
+    const int n = resolve_n(n_cap, n_dev);
+    const int strategy = resolve_strategy(strategy_in, n);
+    if (threadIdx.x == 0) { meta[0] = n; meta[1] = strategy; }
+    int npow = 1;
+    while (npow < n) npow <<= 1;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+        skeys[i] = i < n ? sort_key(__ldg(scores + i), (uint32_t)i) : ~0ull;
+        if (strategy == COIN_NMS_TRICK && i < n) {
+            const float4 b = __ldg(boxes + i);
+            m = fmaxf(fmaxf(m, fmaxf(b.x, b.y)), fmaxf(b.z, b.w));
+        }
+    }
+    if (strategy == COIN_NMS_TRICK) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const uint64_t a = skeys[i], b = skeys[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { skeys[i] = b; skeys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    float mx = 0.0f;
+    if (strategy == COIN_NMS_TRICK) {
+        mx = smax[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, smax[w]);
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t src = (uint32_t)(skeys[i] & 0xffffffffu);
+        float4 b = __ldg(boxes + src);
+        const int64_t cls = idxs ? __ldg(idxs + src) : 0;
+        if (strategy == COIN_NMS_TRICK) {
+            const float off = (float)cls * (mx + 1.0f);
+            b.x += off; b.y += off; b.z += off; b.w += off;
+        }
+        sboxes[i] = b;
+        scls[i] = (int32_t)cls;
+        order[i] = (int32_t)src;
+    }
+}
+
+// 64 x (4*64) tile of the upper-triangular suppression mask per CTA; row-major [n][colblocks] so
+// that the sweep reads whole rows coalesced. Bits are set only for j > i.
+__global__ void __launch_bounds__(256)
+nms_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ scls,
+                const int32_t* __restrict__ meta, int colblocks, float thr, uint64_t* __restrict__ mask) {
+    const int n = meta[0];
+    const bool same_class_only = meta[1] == COIN_NMS_VANILLA;
+    const int rt = blockIdx.y;                 // row tile
+    const int ct = blockIdx.x * 4 + threadIdx.y;  // col tile of this thread row
+    if (blockIdx.x * 4 + 3 < rt) return;       // whole CTA below the diagonal
+    if (rt * 64 >= n || blockIdx.x * 256 >= n) return;  // beyond the live boxes (capacity launch)
+    __shared__ float4 cb[4][64];
+    __shared__ float ca[4][64];
+    __shared__ int32_t cc[4][64];
+    const int r = threadIdx.x;
+    {
+        const int j = ct * 64 + r;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        int32_t c = -1;
+        if (ct < colblocks && j < n) { b = __ldg(sboxes + j); c = __ldg(scls + j); }
+        cb[threadIdx.y][r] = b;
+        ca[threadIdx.y][r] = box_area(b);
+        cc[threadIdx.y][r] = c;
+    }
+    __syncthreads();
+    const int i = rt * 64 + r;
+    if (i >= n || ct >= colblocks || ct < rt) return;
+    const float4 a = __ldg(sboxes + i);
+    const float area_a = box_area(a);
+    const int32_t cls_a = __ldg(scls + i);
+    const int jn = min(64, n - ct * 64);
+    const int j0 = (ct == rt) ? r + 1 : 0;
+    uint64_t word = 0;
+    for (int j = j0; j < jn; ++j) {
+        const bool cls_ok = !same_class_only || cc[threadIdx.y][j] == cls_a;
+        if (cls_ok && iou_tv(a, area_a, cb[threadIdx.y][j], ca[threadIdx.y][j]) > thr) word |= 1ull << j;
+    }
+    mask[(size_t)i * colblocks + ct] = word;
+}
+
+// Single-CTA sweep over 64-row tiles: the intra-tile dependency chain is resolved by one thread on
+// 64-bit words, the kept rows are then OR-ed into the `removed` bit-vector by all threads.
+__global__ void __launch_bounds__(1024)
+nms_sweep_kernel(const uint64_t* __restrict__ mask, const int32_t* __restrict__ order,
+                 const int32_t* __restrict__ meta, int stride, int64_t max_keep, int64_t* __restrict__ keep,
+                 int32_t* __restrict__ nkeep) {
+    extern __shared__ uint64_t removed[];  // colblocks words
+    const int n = meta[0];
+    const int colblocks = (n + 63) >> 6;   // live column blocks; `stride` is the row pitch of `mask`
+    __shared__ uint64_t diag[2][64];
+    __shared__ uint64_t s_kept;
+    __shared__ int s_krow[64];
+    for (int c = threadIdx.x; c < colblocks; c += blockDim.x) removed[c] = 0;
+    if (threadIdx.x < 64) diag[0][threadIdx.x] = threadIdx.x < n ? mask[(size_t)threadIdx.x * stride] : 0;
+    __syncthreads();
+    int64_t nk = 0;
+    const int64_t limit = max_keep >= 0 ? max_keep : (int64_t)n;
+    for (int t = 0; t < colblocks && nk < limit; ++t) {
+        const int buf = t & 1;
+        const int nr = min(64, n - t * 64);
+        // prefetch next tile's diagonal words (independent of `removed`)
+        uint64_t next_diag = 0;
+        if (threadIdx.x < 64 && t + 1 < colblocks) {
+            const int row = (t + 1) * 64 + threadIdx.x;
+            if (row < n) next_diag = mask[(size_t)row * stride + t + 1];
+        }
+        if (threadIdx.x == 0) {
+            uint64_t cur = removed[t];
+            if (nr < 64) cur |= ~0ull << nr;
+            uint64_t kept = 0;
+#pragma unroll
+            for (int r = 0; r < 64; ++r) {
+                const uint64_t alive = ((cur >> r) & 1ull) ^ 1ull;
+                kept |= alive << r;
+                cur |= alive ? diag[buf][r] : 0ull;
+            }
+            // honour max_keep: drop kept rows beyond the limit
+            int64_t room = limit - nk;
+            if ((int64_t)__popcll(kept) > room) {
+                uint64_t trimmed = 0, k = kept;
+                for (int64_t q = 0; q < room; ++q) { trimmed |= k & (~k + 1); k &= k - 1; }
+                kept = trimmed;
+            }
+            s_kept = kept;
+        }
+        __syncthreads();
+        const uint64_t kept = s_kept;
+        const int nkept = __popcll(kept);
+        if (threadIdx.x < 64 && (kept >> threadIdx.x & 1ull)) {
+            const int pos = __popcll(kept & ((1ull << threadIdx.x) - 1ull));
+            s_krow[pos] = threadIdx.x;
+            keep[nk + pos] = order[t * 64 + threadIdx.x];
+        }
+        if (threadIdx.x < 64) diag[buf ^ 1][threadIdx.x] = next_diag;
+        __syncthreads();
+        const int ncols = colblocks - t - 1;
+        const int items = nkept * ncols;
+        for (int it = threadIdx.x; it < items; it += blockDim.x) {
+            const int q = it / ncols, c = it - q * ncols + t + 1;
+            const uint64_t w = mask[(size_t)(t * 64 + s_krow[q]) * stride + c];
+            if (w) atomicOr(reinterpret_cast<unsigned long long*>(&removed[c]), (unsigned long long)w);
+        }
+        nk += nkept;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nkeep = (int32_t)nk;
+}
+
+struct NmsWs {
+    uint64_t *keys, *keys_alt;
+    void* cub_tmp;
+    size_t cub_bytes;
+    int32_t *order, *scls, *meta;
+    float4* sboxes;
+    float* max_coord;
+    uint64_t* mask;
+    size_t total;
+};
+
+static size_t cub_sort_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<uint64_t> db(nullptr, nullptr);
+    if (cub::DeviceRadixSort::SortKeys(nullptr, bytes, db, (int)n) != cudaSuccess) {
+        cudaGetLastError();
+        bytes = (size_t)n * 16 + (1 << 20);  // conservative when no device can be queried
+    }
+    return bytes;
+}
+
+static NmsWs carve_nms(void* ws, int64_t n) {
+    NmsWs w;
+    Carver c(ws);
+    const int64_t colblocks = ceil_div(n, 64);
+    w.meta = c.take<int32_t>(64);
+    w.max_coord = c.take<float>(64);
+    w.order = c.take<int32_t>((size_t)n);
+    w.scls = c.take<int32_t>((size_t)n);
+    w.sboxes = c.take<float4>((size_t)n);
+    w.keys = w.keys_alt = nullptr;
+    w.cub_tmp = nullptr;
+    w.cub_bytes = 0;
+    if (n > kSmallSort) {
+        w.keys = c.take<uint64_t>((size_t)n);
+        w.keys_alt = c.take<uint64_t>((size_t)n);
+        w.cub_bytes = cub_sort_bytes(n);
+        w.cub_tmp = c.take<char>(w.cub_bytes);
+    }
+    w.mask = c.take<uint64_t>((size_t)n * colblocks);
+    w.total = c.used();
+    return w;
+}
+
+size_t nms_pipeline_workspace_bytes(int64_t n_cap) { return n_cap <= 0 ? 256 : carve_nms(nullptr, n_cap).total + 256; }
+
+// largest float <= t  (so that  iou > result  <=>  (double)iou > t)
+static float round_down_to_float(double t) {
+    float f = (float)t;
+    if ((double)f > t) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+// n_cap: host-known capacity; n_dev: optional device int32 with the live count (<= n_cap).
+int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* idxs, int64_t n_cap,
+                        const int32_t* n_dev, double thr, int strategy, int64_t max_keep, int64_t* keep,
+                        int32_t* nkeep, void* ws, size_t ws_bytes, cudaStream_t s) {
+    NmsWs w = carve_nms(ws, n_cap);
+    if (ws_bytes < w.total) return fail(COIN_ERR_CAPACITY, "nms: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    const int n = (int)n_cap;
+    const int colblocks = (int)ceil_div(n_cap, 64);
+    const float4* b4 = reinterpret_cast<const float4*>(boxes);
+    if (n <= kSmallSort) {
+        int npow = 1;
+        while (npow < n) npow <<= 1;
+        small_sort_gather_kernel<<<1, 1024, npow * sizeof(uint64_t), s>>>(scores, b4, idxs, n, n_dev, strategy, w.sboxes,
+                                                                          w.scls, w.order, w.meta);
+        if (int rc = check_launch("small_sort_gather_kernel")) return rc;
+    } else {
+        make_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(scores, n, n_dev, strategy, w.keys, w.meta);
+        if (int rc = check_launch("make_keys_kernel")) return rc;
+        cub::DoubleBuffer<uint64_t> db(w.keys, w.keys_alt);
+        size_t bytes = w.cub_bytes;
+        cudaError_t e = cub::DeviceRadixSort::SortKeys(w.cub_tmp, bytes, db, n, 0, 64, s);
+        if (e != cudaSuccess) return fail(COIN_ERR_CUDA, "nms: radix sort failed: %s", cudaGetErrorString(e));
+        if (strategy == COIN_NMS_TRICK || strategy == COIN_NMS_AUTO) {
+            cudaMemsetAsync(w.max_coord, 0x80, sizeof(int), s);  // 0x80808080 decodes to ~ -3.4e38
+            max_coord_kernel<<<kNumSMs, 256, 0, s>>>(b4, w.meta, w.max_coord);
+            if (int rc = check_launch("max_coord_kernel")) return rc;
+        }
+        gather_sorted_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(db.Current(), b4, idxs, w.meta, w.max_coord,
+                                                                        w.sboxes, w.scls, w.order);
+        if (int rc = check_launch("gather_sorted_kernel")) return rc;
+    }
+    dim3 grid((unsigned)ceil_div(colblocks, 4), (unsigned)colblocks), block(64, 4);
+    nms_mask_kernel<<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, round_down_to_float(thr), w.mask);
+    if (int rc = check_launch("nms_mask_kernel")) return rc;
+    const size_t smem = (size_t)colblocks * sizeof(uint64_t);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    nms_sweep_kernel<<<1, 1024, smem, s>>>(w.mask, w.order, w.meta, colblocks, max_keep, keep, nkeep);
+    return check_launch("nms_sweep_kernel");
+}
+
+}  // namespace coin
+using namespace coin;
+
+extern "C" size_t coin_nms_workspace_bytes(int64_t n) { return nms_pipeline_workspace_bytes(n); }
+
+extern "C" int coin_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n,
+                                double iou_threshold, int strategy, int64_t max_keep, int64_t* keep,
+                                int32_t* nkeep, void* ws, size_t ws_bytes, coin_stream_t stream) {
+    COIN_REQUIRE(n >= 0 && nkeep, "batched_nms: bad arguments");
+    COIN_REQUIRE(strategy >= COIN_NMS_PLAIN && strategy <= COIN_NMS_AUTO, "batched_nms: bad strategy %d", strategy);
+    COIN_REQUIRE(n < (1ll << 22), "batched_nms: n=%lld exceeds the supported 4M boxes", (long long)n);
+    cudaStream_t s = as_stream(stream);
+    if (n == 0 || max_keep == 0) {
+        cudaMemsetAsync(nkeep, 0, sizeof(int32_t), s);
+        return COIN_OK;
+    }
+    COIN_REQUIRE(boxes && scores && keep && ws, "batched_nms: null pointer");
+    COIN_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "batched_nms: boxes must be 16-byte aligned");
+    if (strategy != COIN_NMS_PLAIN) COIN_REQUIRE(idxs, "batched_nms: idxs is required for a batched strategy");
+    if (strategy == COIN_NMS_PLAIN) idxs = nullptr;
+    return nms_sorted_pipeline(boxes, scores, idxs, n, nullptr, iou_threshold, strategy, max_keep, keep, nkeep, ws,
+                               ws_bytes, s);
+}

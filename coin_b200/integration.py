@@ -1,0 +1,139 @@
+"""Host-side mirror of the COIN functions that sit on the RoI path, running on device tensors.
+
+Same names / argument meaning as the reference so the parity tests read like calls into it:
+    process                          coin/engine/base.py:80-126      (box rescale + flip, field renames)
+    fast_rcnn_inference_single_image coin/modeling/roi_heads/fast_rcnn.py:116-175
+    match_dual_teacher / merge_boxes coin/engine/trainer.py:338-461,480-485
+    delete_duplicate_boxes           coin/utils/util.py:434-457 (device de-dup inside match_abc)
+    label_proposals / label_anchors  the pairwise_iou + Matcher + relabel blocks of
+                                     coin/modeling/roi_heads/clip_roi_heads.py:351-362 and
+                                     coin/modeling/proposal_generator/rpn.py:209-228
+The reference moves the teacher detections to the CPU for the matching (trainer.py:469) and back
+(:457-459); here everything stays on the device and each function is one or a few launches.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+from .layers import Matcher
+from .structures import Boxes, Instances
+
+
+def process(instances: Instances, old_size, new_size, random_flip: str, thresh: Optional[float] = None,
+            keep_name: bool = False) -> Instances:
+    """BASE_Trainer.process: scale boxes from the original image frame into the network-input frame,
+    optionally flip, rename pred_* -> gt_* (one kernel for the box math)."""
+    img_h, img_w = old_size
+    net_h, net_w = new_size
+    if random_flip not in ("no", "horizontal", "vertical"):
+        raise NotImplementedError
+    out = Instances((net_h, net_w))
+    fields = dict(instances.get_fields())
+    name = "pred_boxes" if "pred_boxes" in fields else "gt_boxes"
+    boxes = Boxes(ops.boxes_scale_flip(fields.pop(name).tensor, net_w / img_w, net_h / img_h, random_flip,
+                                       (net_h, net_w)))
+    for k, v in fields.items():
+        out.set(k, v)
+    out.set(name if (keep_name or name == "gt_boxes") else "gt_boxes", boxes)
+    if not keep_name:
+        out.set("gt_classes", out.get("pred_classes"))
+        out.remove("pred_classes")
+    if thresh is not None:
+        return out[instances.scores >= thresh]
+    return out
+
+
+def fast_rcnn_inference_single_image(boxes, scores, image_shape: Tuple[int, int], score_thresh: float,
+                                     nms_thresh: float, topk_per_image: int):
+    """Returns (Instances(pred_boxes, scores, probs, pred_classes), kept RoI indices)."""
+    b, s, p, c, roi = ops.det_postprocess(boxes, scores, image_shape, score_thresh, nms_thresh, topk_per_image)
+    result = Instances(image_shape)
+    result.pred_boxes = Boxes(b)
+    result.scores = s
+    result.probs = p
+    result.pred_classes = c
+    return result, roi
+
+
+def _gather(inst: Instances, idx: torch.Tensor, names) -> dict:
+    return {n: inst.get(n)[idx] for n in names}
+
+
+def match_dual_teacher(online: Instances, offline: Instances, tag: str, iou_threshold: float = 0.5,
+                       weight_for_box_a: float = 1.0, device=None):
+    """CoinTrainer.match_dual_teacher for one image and one tag. ``online`` = cloud detections after
+    process() (fields gt_boxes, gt_classes, scores, probs), ``offline`` = CLIP-detector detections
+    (same fields). Returns (A, B or None, C) Instances with the reference's field names.
+
+    Policy for the reference's non-deterministic choices (random.randint, set iteration order):
+    first element / ascending index; see DESIGN.md."""
+    nc, nd = len(online), len(offline)
+    r = ops.match_abc(online.gt_boxes.tensor, online.gt_classes, online.scores,
+                      offline.gt_boxes.tensor, offline.gt_classes, offline.scores, tag, iou_threshold,
+                      weight_for_box_a)
+    # in the empty-side branches both members of a pair index the same (non-empty) set
+    on_src = offline if nc == 0 else online
+    off_src = online if nd == 0 else offline
+    size = online.image_size
+
+    def pack(on_idx, off_idx, boxes, split_classes):
+        out = Instances(size)
+        out.gt_boxes = Boxes(boxes)
+        if split_classes:
+            out.gt_classes_offline = off_src.gt_classes[off_idx]
+            out.gt_classes_online = on_src.gt_classes[on_idx]
+        else:
+            out.gt_classes = off_src.gt_classes[off_idx]
+        out.gt_scores_online = on_src.scores[on_idx]
+        out.gt_scores_offline = off_src.scores[off_idx]
+        out.gt_probs_online = on_src.probs[on_idx]
+        out.gt_probs_offline = off_src.probs[off_idx]
+        return out
+
+    a = pack(r["a_on"], r["a_off"], r["a_boxes"], False)
+    b = pack(r["b_on"], r["b_off"], r["b_boxes"], True) if tag == "RCNN" else None
+
+    # C rows reference exactly one side (the other index is -1): CLIP-detector rows first
+    c_on, c_off = r["c_on"], r["c_off"]
+    from_off = c_off >= 0
+    n_off = int(from_off.sum().item()) if c_off.numel() else 0
+    off_rows, on_rows = c_off[:n_off], c_on[n_off:]
+    c = Instances(size)
+    fields = ("gt_boxes", "gt_classes", "scores", "probs")
+    parts = []
+    if nd > 0:
+        parts.append({"gt_boxes": offline.gt_boxes.tensor[off_rows], "gt_classes": offline.gt_classes[off_rows],
+                      "scores": offline.scores[off_rows], "probs": offline.probs[off_rows]})
+    if nc > 0:
+        parts.append({"gt_boxes": online.gt_boxes.tensor[on_rows], "gt_classes": online.gt_classes[on_rows],
+                      "scores": online.scores[on_rows], "probs": online.probs[on_rows]})
+    if not parts:
+        parts.append({"gt_boxes": online.gt_boxes.tensor, "gt_classes": online.gt_classes, "scores": online.scores,
+                      "probs": online.probs})
+    cat = {k: torch.cat([p[k] for p in parts], dim=0) for k in fields}
+    c.gt_boxes = Boxes(cat["gt_boxes"])
+    c.gt_classes = cat["gt_classes"]
+    c.gt_scores = cat["scores"]
+    c.gt_probs = cat["probs"]
+    if device is not None:
+        a, c = a.to(device), c.to(device)
+        b = b.to(device) if b is not None else None
+    return a, b, c
+
+
+def label_proposals(matcher: Matcher, a_boxes: Boxes, b_boxes: Boxes, c_boxes: Boxes, proposals: Boxes):
+    """clip_roi_heads.py:351-362: IoU of proposals against A|B|C pseudo boxes, Matcher, and the rule
+    that foreground matches on a private (C) box are ignored. Returns (matched_idxs, matched_labels)."""
+    gt = Boxes.cat([a_boxes, b_boxes, c_boxes])
+    idx, lab = matcher.match_boxes(gt, proposals)
+    la, lb, lc = len(a_boxes), len(b_boxes), len(c_boxes)
+    ops.relabel_roi_(idx, lab, la + lb, la + lb + lc)
+    return idx, lab
+
+
+def label_anchors(matcher: Matcher, a_boxes: Boxes, c_boxes: Boxes, anchors: Boxes):
+    """rpn.py:209-228: returns (gt_labels, matched_idxs, distillation_idxs, distillation_labels)."""
+    gt = Boxes.cat([a_boxes, c_boxes])
+    idx, lab = matcher.match_boxes(gt, anchors)
+    return ops.relabel_rpn_(idx, lab, len(a_boxes), len(c_boxes))

@@ -1,0 +1,377 @@
+"""Functional wrappers: torch CUDA tensors in, torch CUDA tensors out, every call through the C ABI.
+
+Nothing here computes on the host or through torch operators except allocation, dtype casts that
+the reference itself performs (``boxes.float()``, ``deltas.float()``) and narrowing a worst-case
+output buffer to the device-side count. A CPU tensor is an error (no fallback).
+"""
+import ctypes
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_SCALE_CLAMP = math.log(1000.0 / 16)
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
+        raise RuntimeError(f"coin_b200: `{name}` must be a CUDA tensor (there is no CPU fallback)")
+    return t
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    return _cuda(t, name).to(torch.float32).contiguous()
+
+
+def _i64c(t: torch.Tensor, name: str) -> torch.Tensor:
+    return _cuda(t, name).to(torch.int64).contiguous()
+
+
+def _boxes(t: torch.Tensor, name: str) -> torch.Tensor:
+    t = _f32c(t, name)
+    if t.dim() != 2 or t.shape[-1] != 4:
+        if t.numel() == 0:
+            return t.reshape(0, 4)
+        raise ValueError(f"coin_b200: `{name}` must have shape [n, 4], got {tuple(t.shape)}")
+    return t
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return _lib.F32
+    if dt == torch.float16:
+        return _lib.F16
+    raise TypeError(f"coin_b200: unsupported dtype {dt} (fp32 and fp16 are supported)")
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# ROIAlign
+# ------------------------------------------------------------------------------------------------
+def to_nhwc_f32(x: torch.Tensor) -> torch.Tensor:
+    """[N,C,H,W] fp32/fp16 -> fp32 [N,H,W,C] contiguous (the layout the gather kernels read)."""
+    _cuda(x, "input")
+    n, c, h, w = x.shape
+    if x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+        return x.permute(0, 2, 3, 1)  # already channel-last in memory: zero copy
+    x = x.contiguous()
+    out = torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+    check(lib.coin_nchw_to_nhwc_f32(_ptr(x), _dtype_code(x.dtype), _ptr(out), n, c, h, w, _stream()))
+    return out
+
+
+def _levels(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float]):
+    arr = (_lib.CoinLevel * len(feats_nhwc))()
+    for i, (f, s) in enumerate(zip(feats_nhwc, scales)):
+        arr[i].feat_nhwc = f.data_ptr()
+        arr[i].H, arr[i].W = int(f.shape[1]), int(f.shape[2])
+        arr[i].spatial_scale = float(s)
+    return arr
+
+
+def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
+                      roi_level: Optional[torch.Tensor], output_size: Tuple[int, int], sampling_ratio: int,
+                      aligned: bool, out_dtype: torch.dtype) -> torch.Tensor:
+    rois = _f32c(rois, "rois")
+    if rois.dim() != 2 or rois.shape[1] != 5:
+        raise ValueError(f"coin_b200: rois must have shape [K, 5], got {tuple(rois.shape)}")
+    k, c = rois.shape[0], int(feats_nhwc[0].shape[3])
+    ph, pw = output_size
+    out = torch.empty((k, c, ph, pw), dtype=out_dtype, device=rois.device)
+    if roi_level is not None:
+        roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
+    check(lib.coin_roi_align_fwd(_levels(feats_nhwc, scales), len(feats_nhwc), _ptr(rois), _ptr(roi_level), _ptr(out),
+                                 _dtype_code(out_dtype), c, k, ph, pw, int(sampling_ratio), int(bool(aligned)),
+                                 _stream()))
+    return out
+
+
+def roi_align_backward(grad_out: torch.Tensor, shapes: Sequence[Tuple[int, int, int, int]], scales: Sequence[float],
+                       rois: torch.Tensor, roi_level: Optional[torch.Tensor], output_size: Tuple[int, int],
+                       sampling_ratio: int, aligned: bool, out_dtypes: Sequence[torch.dtype]) -> List[torch.Tensor]:
+    """Returns one NCHW gradient per level (shape ``shapes[i]`` = (N,C,H,W), dtype ``out_dtypes[i]``)."""
+    grad_out = _cuda(grad_out, "grad_out").contiguous()
+    rois = _f32c(rois, "rois")
+    k, c = rois.shape[0], shapes[0][1]
+    ph, pw = output_size
+    bufs = [torch.zeros((n, h, w, cc), dtype=torch.float32, device=grad_out.device) for (n, cc, h, w) in shapes]
+    if roi_level is not None:
+        roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
+    check(lib.coin_roi_align_bwd(_levels(bufs, scales), len(bufs), _ptr(rois), _ptr(roi_level), _ptr(grad_out),
+                                 _dtype_code(grad_out.dtype), c, k, ph, pw, int(sampling_ratio), int(bool(aligned)),
+                                 _stream()))
+    outs = []
+    for buf, (n, cc, h, w), dt in zip(bufs, shapes, out_dtypes):
+        g = torch.empty((n, cc, h, w), dtype=dt, device=buf.device)
+        check(lib.coin_nhwc_f32_to_nchw(_ptr(buf), _ptr(g), _dtype_code(dt), n, cc, h, w, _stream()))
+        outs.append(g)
+    return outs
+
+
+def roi_pooler_levels(boxes: torch.Tensor, min_level: int, max_level: int, canonical_box_size: int = 224,
+                      canonical_level: int = 4) -> torch.Tensor:
+    boxes = _boxes(boxes, "boxes")
+    out = torch.empty((boxes.shape[0],), dtype=torch.int32, device=boxes.device)
+    check(lib.coin_roi_pooler_levels(_ptr(boxes), boxes.shape[0], min_level, max_level, canonical_box_size,
+                                     canonical_level, _ptr(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# box codec
+# ------------------------------------------------------------------------------------------------
+def apply_deltas(deltas: torch.Tensor, boxes: torch.Tensor, weights, scale_clamp: float = _SCALE_CLAMP,
+                 clip_to: Optional[Tuple[float, float]] = None) -> torch.Tensor:
+    deltas = _f32c(deltas, "deltas")
+    boxes = _boxes(boxes, "boxes")
+    r = boxes.shape[0]
+    if deltas.dim() != 2 or deltas.shape[0] != r or deltas.shape[1] % 4 != 0:
+        raise ValueError(f"coin_b200: deltas must have shape [R, 4*k] with R={r}, got {tuple(deltas.shape)}")
+    out = torch.empty_like(deltas)
+    wx, wy, ww, wh = (float(v) for v in weights)
+    h, w = clip_to if clip_to is not None else (0.0, 0.0)
+    check(lib.coin_apply_deltas(_ptr(deltas), _ptr(boxes), _ptr(out), r, deltas.shape[1] // 4, wx, wy, ww, wh,
+                                float(scale_clamp), int(clip_to is not None), float(h), float(w), _stream()))
+    return out
+
+
+def get_deltas(src: torch.Tensor, tgt: torch.Tensor, weights, check_valid: bool = True) -> torch.Tensor:
+    src, tgt = _boxes(src, "src_boxes"), _boxes(tgt, "target_boxes")
+    if src.shape != tgt.shape:
+        raise ValueError("coin_b200: src_boxes and target_boxes must have the same shape")
+    out = torch.empty_like(src)
+    flag = torch.zeros((1,), dtype=torch.int32, device=src.device) if check_valid else None
+    wx, wy, ww, wh = (float(v) for v in weights)
+    check(lib.coin_get_deltas(_ptr(src), _ptr(tgt), _ptr(out), src.shape[0], wx, wy, ww, wh, _ptr(flag), _stream()))
+    if check_valid:
+        assert int(flag.item()) == 0, "Input boxes to Box2BoxTransform are not valid!"
+    return out
+
+
+def boxes_clip_(boxes: torch.Tensor, image_size: Tuple[float, float]) -> torch.Tensor:
+    _cuda(boxes, "boxes")
+    if boxes.dtype != torch.float32 or not boxes.is_contiguous():
+        raise ValueError("coin_b200: boxes_clip_ needs a contiguous fp32 tensor (it works in place)")
+    h, w = image_size
+    check(lib.coin_boxes_clip(_ptr(boxes), boxes.numel() // 4, float(h), float(w), _stream()))
+    return boxes
+
+
+def boxes_scale_flip(boxes: torch.Tensor, sx: float, sy: float, flip: str = "no",
+                     net_size: Tuple[float, float] = (0.0, 0.0)) -> torch.Tensor:
+    boxes = _boxes(boxes, "boxes")
+    code = {"no": 0, "horizontal": 1, "vertical": 2}.get(flip)
+    if code is None:
+        raise NotImplementedError(flip)
+    out = torch.empty_like(boxes)
+    net_h, net_w = net_size
+    check(lib.coin_boxes_scale_flip(_ptr(boxes), _ptr(out), boxes.shape[0], float(sx), float(sy), code, float(net_w),
+                                    float(net_h), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# IoU / Matcher
+# ------------------------------------------------------------------------------------------------
+def pairwise_iou(b1: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    b1, b2 = _boxes(b1, "boxes1"), _boxes(b2, "boxes2")
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
+    check(lib.coin_pairwise_iou(_ptr(b1), b1.shape[0], _ptr(b2), b2.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def _matcher_cfg(thresholds: Sequence[float], labels: Sequence[int]):
+    thr = (ctypes.c_float * len(thresholds))(*[float(t) for t in thresholds])
+    lab = (ctypes.c_int8 * len(labels))(*[int(l) for l in labels])
+    return thr, lab
+
+
+def matcher(quality: torch.Tensor, thresholds: Sequence[float], labels: Sequence[int], allow_low_quality: bool,
+            return_vals: bool = False):
+    q = _f32c(quality, "match_quality_matrix")
+    if q.dim() != 2:
+        raise ValueError("coin_b200: match_quality_matrix must be 2-D")
+    n, m = q.shape
+    matches = torch.empty((m,), dtype=torch.int64, device=q.device)
+    mlabels = torch.empty((m,), dtype=torch.int8, device=q.device)
+    vals = torch.empty((m,), dtype=torch.float32, device=q.device) if return_vals else None
+    ws = torch.empty((max(n, 1),), dtype=torch.float32, device=q.device) if allow_low_quality else None
+    thr, lab = _matcher_cfg(thresholds, labels)
+    check(lib.coin_matcher(_ptr(q), n, m, thr, len(thresholds), lab, int(bool(allow_low_quality)), _ptr(matches),
+                           _ptr(mlabels), _ptr(vals), _ptr(ws), _stream()))
+    return (matches, mlabels, vals) if return_vals else (matches, mlabels)
+
+
+def iou_match(gt: torch.Tensor, boxes: torch.Tensor, thresholds: Sequence[float], labels: Sequence[int],
+              allow_low_quality: bool, return_vals: bool = False):
+    """pairwise_iou(gt, boxes) followed by Matcher, without materialising the matrix."""
+    gt, boxes = _boxes(gt, "gt_boxes"), _boxes(boxes, "boxes")
+    n, m = gt.shape[0], boxes.shape[0]
+    matches = torch.empty((m,), dtype=torch.int64, device=boxes.device)
+    mlabels = torch.empty((m,), dtype=torch.int8, device=boxes.device)
+    vals = torch.empty((m,), dtype=torch.float32, device=boxes.device) if return_vals else None
+    ws = torch.empty((max(n, 1),), dtype=torch.float32, device=boxes.device) if allow_low_quality else None
+    thr, lab = _matcher_cfg(thresholds, labels)
+    check(lib.coin_iou_match(_ptr(gt), n, _ptr(boxes), m, thr, len(thresholds), lab, int(bool(allow_low_quality)),
+                             _ptr(matches), _ptr(mlabels), _ptr(vals), _ptr(ws), _stream()))
+    return (matches, mlabels, vals) if return_vals else (matches, mlabels)
+
+
+def relabel_roi_(matches: torch.Tensor, labels: torch.Tensor, c_begin: int, c_end: int) -> torch.Tensor:
+    check(lib.coin_relabel_roi(_ptr(_cuda(matches, "matches")), _ptr(_cuda(labels, "labels")), matches.numel(),
+                               int(c_begin), int(c_end), _stream()))
+    return labels
+
+
+def relabel_rpn_(matches: torch.Tensor, labels: torch.Tensor, len_a: int, len_c: int):
+    didx = torch.empty_like(matches)
+    dlab = torch.empty_like(labels)
+    check(lib.coin_relabel_rpn(_ptr(_cuda(matches, "matches")), _ptr(_cuda(labels, "labels")), matches.numel(),
+                               int(len_a), int(len_c), _ptr(didx), _ptr(dlab), _stream()))
+    return labels, matches, didx, dlab
+
+
+def iou_pairs_ge(b1: torch.Tensor, b2: torch.Tensor, thr: float) -> torch.Tensor:
+    """== (pairwise_iou(b1, b2) >= thr).nonzero(); int64 [P, 2], row-major order."""
+    b1, b2 = _boxes(b1, "boxes1"), _boxes(b2, "boxes2")
+    n, m = b1.shape[0], b2.shape[0]
+    cap = n * m
+    pairs = torch.empty((max(cap, 1), 2), dtype=torch.int64, device=b1.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=b1.device)
+    nbytes = lib.coin_iou_pairs_workspace_bytes(n, m)
+    ws = _workspace(nbytes, b1.device)
+    check(lib.coin_iou_pairs_ge(_ptr(b1), n, _ptr(b2), m, float(thr), _ptr(pairs), _ptr(count), cap, _ptr(ws),
+                                ws.numel(), _stream()))
+    return pairs[: int(count.item())]
+
+
+# ------------------------------------------------------------------------------------------------
+# NMS family
+# ------------------------------------------------------------------------------------------------
+_STRATEGY = {"plain": _lib.NMS_PLAIN, "trick": _lib.NMS_TRICK, "vanilla": _lib.NMS_VANILLA, "auto": _lib.NMS_AUTO}
+
+
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: Optional[torch.Tensor], iou_threshold: float,
+                strategy: str = "auto", max_keep: int = -1) -> torch.Tensor:
+    boxes = _boxes(boxes, "boxes")
+    scores = _f32c(scores, "scores")
+    n = boxes.shape[0]
+    if scores.numel() != n:
+        raise ValueError("coin_b200: boxes and scores disagree in length")
+    if idxs is not None:
+        idxs = _i64c(idxs, "idxs")
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=boxes.device)
+    nkeep = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    ws = _workspace(lib.coin_nms_workspace_bytes(n), boxes.device)
+    check(lib.coin_batched_nms(_ptr(boxes), _ptr(scores), _ptr(idxs), n, float(iou_threshold), _STRATEGY[strategy],
+                               int(max_keep), _ptr(keep), _ptr(nkeep), _ptr(ws), ws.numel(), _stream()))
+    return keep[: int(nkeep.item())]
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float, max_keep: int = -1) -> torch.Tensor:
+    return batched_nms(boxes, scores, None, iou_threshold, "plain", max_keep)
+
+
+_SCORE = {"probEn": _lib.SCORE_PROBEN, "avg": _lib.SCORE_AVG, "max": _lib.SCORE_MAX}
+_BOX = {"s-avg": _lib.BOX_SAVG, "avg": _lib.BOX_AVG, "max": _lib.BOX_MAX}
+
+
+def fusion_nms(boxes: torch.Tensor, probs: torch.Tensor, labels: torch.Tensor, iou_threshold: float,
+               score_method: str, box_method: str, per_class_offset: bool = True):
+    boxes = _boxes(boxes, "boxes")
+    probs = _f32c(probs, "probs")
+    labels = _i64c(labels, "idxs")
+    n, k1 = boxes.shape[0], int(probs.shape[1])
+    dev = boxes.device
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    o_box = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+    o_score = torch.empty((max(n, 1),), dtype=torch.float32, device=dev)
+    o_prob = torch.empty((max(n, 1), k1), dtype=torch.float32, device=dev)
+    o_cls = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    meta = torch.zeros((2,), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.coin_fusion_nms_workspace_bytes(n, k1), dev)
+    check(lib.coin_fusion_nms(_ptr(boxes), _ptr(probs), _ptr(labels), n, k1, float(iou_threshold), _SCORE[score_method],
+                              _BOX[box_method], int(bool(per_class_offset)), _ptr(keep), _ptr(o_box), _ptr(o_score),
+                              _ptr(o_prob), _ptr(o_cls), ctypes.c_void_p(meta.data_ptr()),
+                              ctypes.c_void_p(meta.data_ptr() + 4), _ptr(ws), ws.numel(), _stream()))
+    nk, status = (int(v) for v in meta.tolist())
+    if status & 1:
+        raise AssertionError("fusion_nms: a cluster mixes classes (nms.py:149,157 assert len(final_class)==1)")
+    if status & 2:
+        raise AssertionError("fusion_nms: argmax(prob) != label inside a probEn cluster (nms.py:40)")
+    return keep[:nk], o_box[:nk], o_score[:nk], o_prob[:nk], o_cls[:nk]
+
+
+def det_postprocess(boxes: torch.Tensor, scores: torch.Tensor, image_shape: Tuple[int, int], score_thresh: float,
+                    nms_thresh: float, topk: int, sync: bool = True):
+    """fast_rcnn_inference_single_image. Returns (boxes, scores, probs, classes, roi_index[, count])."""
+    boxes = _f32c(boxes, "boxes")
+    scores = _f32c(scores, "scores")
+    r, k1 = scores.shape
+    kreg = boxes.shape[1] // 4
+    dev = boxes.device
+    cap = int(topk) if topk >= 0 else r * (k1 - 1)
+    cap = max(min(cap, r * (k1 - 1)), 1)
+    o_box = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+    o_score = torch.empty((cap,), dtype=torch.float32, device=dev)
+    o_prob = torch.empty((cap, k1), dtype=torch.float32, device=dev)
+    o_cls = torch.empty((cap,), dtype=torch.int64, device=dev)
+    o_roi = torch.empty((cap,), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.coin_det_postprocess_workspace_bytes(r, k1), dev)
+    h, w = image_shape
+    check(lib.coin_det_postprocess(_ptr(boxes), _ptr(scores), r, k1, kreg, float(h), float(w), float(score_thresh),
+                                   float(nms_thresh), int(topk), cap, _ptr(o_box), _ptr(o_score), _ptr(o_prob),
+                                   _ptr(o_cls), _ptr(o_roi), _ptr(count), _ptr(ws), ws.numel(), _stream()))
+    if not sync:
+        return o_box, o_score, o_prob, o_cls, o_roi, count
+    n = int(count.item())
+    return o_box[:n], o_score[:n], o_prob[:n], o_cls[:n], o_roi[:n]
+
+
+def match_abc(on_boxes, on_classes, on_scores, off_boxes, off_classes, off_scores, tag: str, iou_thr: float,
+              weight_for_box_a: float):
+    """Index form of match_dual_teacher. Returns dict with a_on, a_off, a_boxes, b_*, c_on, c_off."""
+    on_boxes, off_boxes = _boxes(on_boxes, "online boxes"), _boxes(off_boxes, "offline boxes")
+    on_classes, off_classes = _i64c(on_classes, "online classes"), _i64c(off_classes, "offline classes")
+    on_scores, off_scores = _f32c(on_scores, "online scores"), _f32c(off_scores, "offline scores")
+    nc, nd = on_boxes.shape[0], off_boxes.shape[0]
+    dev = on_boxes.device
+    cap = nc * nd + nc + nd
+    i32 = lambda n: torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+    a_on, a_off, b_on, b_off = i32(cap), i32(cap), i32(cap), i32(cap)
+    c_on, c_off = i32(nc + nd), i32(nc + nd)
+    a_box = torch.empty((max(cap, 1), 4), dtype=torch.float32, device=dev)
+    b_box = torch.empty((max(cap, 1), 4), dtype=torch.float32, device=dev)
+    counts = torch.zeros((4,), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.coin_match_abc_workspace_bytes(nc, nd), dev)
+    code = {"RCNN": _lib.TAG_RCNN, "RPN": _lib.TAG_RPN}[tag]
+    check(lib.coin_match_abc(_ptr(on_boxes), _ptr(on_classes), _ptr(on_scores), nc, _ptr(off_boxes), _ptr(off_classes),
+                             _ptr(off_scores), nd, code, float(iou_thr), float(weight_for_box_a), cap, _ptr(a_on),
+                             _ptr(a_off), _ptr(a_box), _ptr(b_on), _ptr(b_off), _ptr(b_box), _ptr(c_on), _ptr(c_off),
+                             _ptr(counts), _ptr(ws), ws.numel(), _stream()))
+    na, nb, ncc, status = (int(v) for v in counts.tolist())
+    if status & 16:
+        raise AssertionError("match_abc: a cloud self-cluster has a single class (util.py:488 assert)")
+    if status & 8:
+        raise AssertionError("match_abc: a duplicate group holds several boxes of the matched class "
+                             "(trainer.py:382 would desynchronise the common lists)")
+    if status & 4:
+        raise RuntimeError("match_abc: pair capacity exceeded")
+    return {"a_on": a_on[:na].long(), "a_off": a_off[:na].long(), "a_boxes": a_box[:na],
+            "b_on": b_on[:nb].long(), "b_off": b_off[:nb].long(), "b_boxes": b_box[:nb],
+            "c_on": c_on[:ncc].long(), "c_off": c_off[:ncc].long()}

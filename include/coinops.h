@@ -1,0 +1,259 @@
+/*
+ * coinops.h -- C ABI of libcoinops.so: the sm_100a RoI / box-decode / IoU-match / NMS path of COIN.
+ *
+ * The reference (Flashkong/COIN) is pure Python; on this path it binds, through detectron2 0.5 and
+ * torchvision 0.10.1, the torch dispatcher operators
+ *     torchvision::roi_align, torchvision::_roi_align_backward, torchvision::nms
+ * and a few dozen ATen elementwise launches per call of pairwise_iou / Matcher / Box2BoxTransform /
+ * Boxes.clip, plus its own Python loops (coin/layers/nms.py, coin/engine/trainer.py:338-485).
+ * Each entry point below names the reference interface it replaces (file:line under the
+ * reference root). INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless its name ends in _host;
+ *   - the caller owns every buffer, including workspaces (query sizes with the *_workspace_bytes
+ *     functions); the library never allocates, frees or retains device memory;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no call synchronises;
+ *   - variable-length results are written into caller-sized worst-case buffers plus a device-side
+ *     int32 count;
+ *   - return value 0 = ok, otherwise a COIN_ERR_* code; coin_last_error() gives the message of the
+ *     last failure on the calling thread. No exception crosses this boundary;
+ *   - boxes are fp32 [n,4] xyxy; indices are int64; Matcher labels are int8 -- as in the reference.
+ */
+#ifndef COINOPS_H_
+#define COINOPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define COIN_OK 0
+#define COIN_ERR_INVALID 1     /* bad shape / null pointer / bad enum            */
+#define COIN_ERR_UNSUPPORTED 2 /* legal in the reference, not supported here     */
+#define COIN_ERR_CUDA 3        /* launch or runtime failure (message has detail) */
+#define COIN_ERR_CAPACITY 4    /* caller buffer / workspace too small            */
+
+#define COIN_F32 0
+#define COIN_F16 1
+
+#define COIN_LAYOUT_NCHW 0
+#define COIN_LAYOUT_NHWC 1
+
+#define COIN_MAX_LEVELS 8
+
+typedef void* coin_stream_t; /* cudaStream_t */
+
+const char* coin_last_error(void);
+int coin_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * ROIAlign / ROIPooler
+ *   replaces: detectron2.layers.ROIAlign.forward -> torchvision::roi_align and its autograd
+ *   backward torchvision::_roi_align_backward, reached from
+ *   coin/modeling/roi_heads/clip_roi_heads.py:51-63,142-147,172-176 (ROIPooler(...)(features, boxes)).
+ * ------------------------------------------------------------------------------------------- */
+
+/* One pyramid level: a feature map in fp32 NHWC ([N,H,W,C]) and its spatial scale. */
+typedef struct {
+    const float* feat_nhwc;
+    int H, W;
+    float spatial_scale;
+} coin_level_t;
+
+/* [N,C,H,W] (fp32 or fp16) -> fp32 [N,H,W,C]. The gather kernels read channel-last fp32. */
+int coin_nchw_to_nhwc_f32(const void* in, int in_dtype, float* out, int N, int C, int H, int W,
+                          coin_stream_t stream);
+/* fp32 [N,H,W,C] -> [N,C,H,W] in out_dtype (used by the backward pass). */
+int coin_nhwc_f32_to_nchw(const float* in, void* out, int out_dtype, int N, int C, int H, int W,
+                          coin_stream_t stream);
+
+/* Forward over `nlevels` maps. rois: [K,5] fp32 (batch, x1, y1, x2, y2) in input-image pixels.
+ * roi_level: int32 [K] level of each RoI, or NULL when nlevels == 1. out: [K,C,PH,PW] out_dtype.
+ * sampling_ratio <= 0 selects the adaptive grid ceil(roi/pooled); aligned = ROIAlignV2. */
+int coin_roi_align_fwd(const coin_level_t* levels_host, int nlevels, const float* rois,
+                       const int32_t* roi_level, void* out, int out_dtype, int C, int K, int PH,
+                       int PW, int sampling_ratio, int aligned, coin_stream_t stream);
+
+/* Backward of the above into per-level fp32 NHWC gradient maps (levels_host[i].feat_nhwc is the
+ * WRITABLE gradient buffer of level i here and must be zeroed by the caller beforehand).
+ * grad_out: [K,C,PH,PW] in grad_dtype. Accumulation uses fp32 atomics. */
+int coin_roi_align_bwd(const coin_level_t* grad_levels_host, int nlevels, const float* rois,
+                       const int32_t* roi_level, const void* grad_out, int grad_dtype, int C, int K,
+                       int PH, int PW, int sampling_ratio, int aligned, coin_stream_t stream);
+
+/* detectron2 ROIPooler level rule: floor(canonical_level + log2(sqrt(area)/canonical_size + 1e-8))
+ * clamped to [min_level, max_level], minus min_level. boxes: [n,4]; out: int32 [n]. */
+int coin_roi_pooler_levels(const float* boxes, int64_t n, int min_level, int max_level,
+                           int canonical_box_size, int canonical_level, int32_t* out_levels,
+                           coin_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Box codec
+ *   replaces: detectron2 Box2BoxTransform.apply_deltas / get_deltas, Boxes.clip, Boxes.scale
+ *   reached from coin/modeling/roi_heads/fast_rcnn.py:145-147,297,619-622,691,729,
+ *   coin/engine/base.py:80-126 (scale + flip), d2 RPN decode (<- proposal_generator/rpn.py:113).
+ * ------------------------------------------------------------------------------------------- */
+
+/* deltas: [R, 4*kreg]; boxes: [R,4]; out: [R, 4*kreg]. If clip != 0 the result is also clamped to
+ * x in [0, clip_w], y in [0, clip_h] (Boxes.clip fused). */
+int coin_apply_deltas(const float* deltas, const float* boxes, float* out, int64_t R, int kreg,
+                      float wx, float wy, float ww, float wh, float scale_clamp, int clip,
+                      float clip_h, float clip_w, coin_stream_t stream);
+
+/* src, tgt: [F,4] -> out [F,4]. *invalid_flag (device int32, caller-zeroed, may be NULL) is set to 1
+ * if any source width is <= 0 (the reference asserts on it). */
+int coin_get_deltas(const float* src, const float* tgt, float* out, int64_t F, float wx, float wy,
+                    float ww, float wh, int32_t* invalid_flag, coin_stream_t stream);
+
+/* In-place Boxes.clip((h, w)). */
+int coin_boxes_clip(float* boxes, int64_t n, float h, float w, coin_stream_t stream);
+
+/* out = flip(scale(in)); flip: 0 none, 1 horizontal (x1' = net_w - x2, x2' = net_w - x1),
+ * 2 vertical. in may equal out. */
+int coin_boxes_scale_flip(const float* in, float* out, int64_t n, float sx, float sy, int flip,
+                          float net_w, float net_h, coin_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * IoU and Matcher
+ *   replaces: detectron2.structures.pairwise_iou and detectron2.modeling.matcher.Matcher, reached
+ *   from coin/engine/trainer.py:364-366,373, coin/utils/util.py:468,
+ *   coin/modeling/roi_heads/clip_roi_heads.py:301-304,311-314,353-356,
+ *   coin/modeling/proposal_generator/rpn.py:159-160,169-170,212-213.
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[i*M + j] = IoU(b1[i], b2[j]) (0 where the intersection is empty). */
+int coin_pairwise_iou(const float* b1, int64_t N, const float* b2, int64_t M, float* out,
+                      coin_stream_t stream);
+
+/* Matcher.__call__ on a materialised [N,M] quality matrix. thresholds_host: the nthr user
+ * thresholds (without the +-inf the Matcher adds); labels_host: nthr+1 labels in {-1,0,1}.
+ * matches: int64 [M]; match_labels: int8 [M]; matched_vals: fp32 [M] or NULL.
+ * row_max_ws: fp32 [N] workspace, required iff allow_low_quality. */
+int coin_matcher(const float* quality, int64_t N, int64_t M, const float* thresholds_host, int nthr,
+                 const int8_t* labels_host, int allow_low_quality, int64_t* matches,
+                 int8_t* match_labels, float* matched_vals, float* row_max_ws, coin_stream_t stream);
+
+/* pairwise_iou + Matcher fused: the [N,M] matrix is never written. gt: [N,4], boxes: [M,4]. */
+int coin_iou_match(const float* gt, int64_t N, const float* boxes, int64_t M,
+                   const float* thresholds_host, int nthr, const int8_t* labels_host,
+                   int allow_low_quality, int64_t* matches, int8_t* match_labels,
+                   float* matched_vals, float* row_max_ws, coin_stream_t stream);
+
+/* Relabelling epilogue of the RoI-head labelling (clip_roi_heads.py:358-362): label -1 where the
+ * match is foreground and fell on a private (C) pseudo box, i.e. index in [c_begin, c_end). */
+int coin_relabel_roi(const int64_t* matches, int8_t* match_labels, int64_t M, int64_t c_begin,
+                     int64_t c_end, coin_stream_t stream);
+
+/* RPN variant (rpn.py:214-228): labels/matches updated in place; distillation outputs written. */
+int coin_relabel_rpn(int64_t* matches, int8_t* labels, int64_t M, int64_t len_a, int64_t len_c,
+                     int64_t* distill_idx, int8_t* distill_labels, coin_stream_t stream);
+
+/* All (i, j) with IoU(b1[i], b2[j]) >= thr in row-major order (== nonzero() of the thresholded
+ * matrix, trainer.py:364-366). pairs: int64 [capacity, 2]; count: device int32 (total found, may
+ * exceed capacity: only the first `capacity` pairs are written). ws: coin_iou_pairs_workspace_bytes. */
+size_t coin_iou_pairs_workspace_bytes(int64_t N, int64_t M);
+int coin_iou_pairs_ge(const float* b1, int64_t N, const float* b2, int64_t M, float thr,
+                      int64_t* pairs, int32_t* count, int64_t capacity, void* ws, size_t ws_bytes,
+                      coin_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NMS
+ *   replaces: torchvision::nms, torchvision.ops.boxes.batched_nms and the detectron2 wrapper
+ *   detectron2.layers.batched_nms, reached from coin/modeling/roi_heads/fast_rcnn.py:164,
+ *   coin/layers/nms.py:207, coin/modeling/meta_arch/clip_rcnn.py:161, d2 find_top_rpn_proposals.
+ * ------------------------------------------------------------------------------------------- */
+
+#define COIN_NMS_PLAIN 0   /* class-agnostic                                               */
+#define COIN_NMS_TRICK 1   /* torchvision coordinate trick: boxes + idx * (max + 1)        */
+#define COIN_NMS_VANILLA 2 /* per-class NMS on the original coordinates                    */
+#define COIN_NMS_AUTO 3    /* the strategy the reference's CPU dependency picks for this n */
+
+size_t coin_nms_workspace_bytes(int64_t n);
+
+/* keep: int64 [n] (kept ORIGINAL indices in descending-score order, ties by lower index);
+ * nkeep: device int32. max_keep < 0 keeps all; otherwise the sweep stops after max_keep boxes
+ * (== keep[:max_keep]). idxs may be NULL for COIN_NMS_PLAIN. iou_threshold is compared as the
+ * torchvision CPU kernel does (float IoU > double threshold). */
+int coin_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n,
+                     double iou_threshold, int strategy, int64_t max_keep, int64_t* keep,
+                     int32_t* nkeep, void* ws, size_t ws_bytes, coin_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Probabilistic-fusion NMS (MyNMS)
+ *   replaces: coin/layers/nms.py:84-238 (mynms.nms with CLOUD.NMS_METHOD in ps/pa/pm/as/aa/am/ms/ma),
+ *   called from coin/modeling/meta_arch/gdino_processor.py:164-182.
+ * ------------------------------------------------------------------------------------------- */
+#define COIN_SCORE_PROBEN 0
+#define COIN_SCORE_AVG 1
+#define COIN_SCORE_MAX 2
+#define COIN_BOX_SAVG 0
+#define COIN_BOX_AVG 1
+#define COIN_BOX_MAX 2
+
+size_t coin_fusion_nms_workspace_bytes(int64_t n, int k1);
+
+/* boxes [n,4], probs [n,k1], labels int64 [n]. per_class_offset != 0 applies the label offset
+ * labels * (max + 1) before the legacy "+1" IoU (nms.py:196-203); 0 restricts clusters to equal
+ * labels instead (the >= 40000 branch, nms.py:222-238). Outputs are sorted by fused score
+ * (descending, ties by sweep order); capacity n rows each. status: device int32, set non-zero when
+ * an assertion of the reference would fire (mixed classes in a cluster, argmax != label for probEn). */
+int coin_fusion_nms(const float* boxes, const float* probs, const int64_t* labels, int64_t n, int k1,
+                    float iou_threshold, int score_method, int box_method, int per_class_offset,
+                    int64_t* keep, float* out_boxes, float* out_scores, float* out_probs,
+                    int64_t* out_classes, int32_t* nkeep, int32_t* status, void* ws, size_t ws_bytes,
+                    coin_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Detection post-processing (filter -> NMS -> top-k)
+ *   replaces: fast_rcnn_inference_single_image, coin/modeling/roi_heads/fast_rcnn.py:116-175.
+ * ------------------------------------------------------------------------------------------- */
+size_t coin_det_postprocess_workspace_bytes(int64_t R, int k1);
+
+/* boxes: [R, 4*kreg] decoded boxes (clipped here); scores: [R,k1] with background last.
+ * Rows holding a non-finite value are dropped first. Candidates = (roi, class) with
+ * score > score_thresh in row-major order; batched NMS (COIN_NMS_AUTO); first topk kept
+ * (topk < 0: all). Outputs have capacity `out_capacity` rows. */
+int coin_det_postprocess(const float* boxes, const float* scores, int64_t R, int k1, int kreg,
+                         float img_h, float img_w, float score_thresh, double nms_thresh,
+                         int64_t topk, int64_t out_capacity, float* out_boxes, float* out_scores,
+                         float* out_probs, int64_t* out_classes, int64_t* out_roi_index,
+                         int32_t* out_count, void* ws, size_t ws_bytes, coin_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Knowledge separation (consistent A / inconsistent B / private C)
+ *   replaces: CoinTrainer.match_dual_teacher, coin/engine/trainer.py:338-461, with
+ *   delete_duplicate_boxes / filter_result / online_boxes_merging (coin/utils/util.py:434-507)
+ *   and merge_boxes (trainer.py:480-485, coin/layers/nms.py:24-31).
+ * ------------------------------------------------------------------------------------------- */
+#define COIN_TAG_RCNN 0
+#define COIN_TAG_RPN 1
+#define COIN_ABC_MAX 1024 /* per-side detection limit of the single-CTA kernel */
+
+/* Row r of the A/B outputs is the pair (on_index[r], off_index[r]) of cloud ("online") and
+ * CLIP-detector ("offline") detections with merged box out_boxes[r]; -1 marks "no such side"
+ * (the empty-side branches, trainer.py:343-361, where both sides are the same detection).
+ * C rows reference exactly one side. All index outputs have capacity cap_pairs = nc*nd + nc + nd
+ * (A, B) and nc + nd (C). counts: device int32 [4] = {nA, nB, nC, status}; status != 0 when an
+ * assertion of the reference would fire. The device resolves the reference's random.randint
+ * picks as "first" and its set iterations as ascending ("determinism policy"). */
+size_t coin_match_abc_workspace_bytes(int64_t nc, int64_t nd);
+int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float* on_scores, int64_t nc,
+                   const float* off_boxes, const int64_t* off_classes, const float* off_scores,
+                   int64_t nd, int tag, float iou_thr, float weight_for_box_a,
+                   int64_t cap_pairs, int32_t* a_on, int32_t* a_off, float* a_boxes, int32_t* b_on,
+                   int32_t* b_off, float* b_boxes, int32_t* c_on, int32_t* c_off, int32_t* counts,
+                   void* ws, size_t ws_bytes, coin_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* COINOPS_H_ */

@@ -1,0 +1,367 @@
+"""CPU restatement of the hot-path arithmetic the COIN reference authors itself.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py). All tensors are CPU tensors.
+
+A detection set is a plain ``dict`` of equally long CPU tensors (the reference uses detectron2
+``Instances``, which cannot be imported here). Field names are the reference's.
+
+Two places of the reference are not functions of their inputs alone:
+  * ``random.randint`` picks (coin/engine/trainer.py:385,387; coin/utils/util.py:450);
+  * iteration order of CPython ``set`` objects (trainer.py:369,391; util.py:471-482).
+Both are exposed as policies: ``choose`` (callable n -> index; default = first, the device policy;
+pass ``random_choice`` for the reference's behaviour) and ``set_order`` ("ascending" = device
+policy, "cpython" = literal ``list(set)`` as the reference executes it).
+"""
+import random
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import d2_ref
+
+DetSet = Dict[str, torch.Tensor]
+
+
+# ------------------------------------------------------------------------------------------------
+# detection-set helpers (stand-ins for detectron2 Instances indexing / cat)
+# ------------------------------------------------------------------------------------------------
+def take(d: DetSet, idx) -> DetSet:
+    if isinstance(idx, int):
+        idx = torch.tensor([idx], dtype=torch.int64)
+    return {k: v[idx] for k, v in d.items()}
+
+
+def cat(sets: List[DetSet]) -> DetSet:
+    return {k: torch.cat([s[k] for s in sets], dim=0) for k in sets[0].keys()}
+
+
+def length(d: DetSet) -> int:
+    return int(next(iter(d.values())).shape[0])
+
+
+def first_choice(n: int) -> int:
+    return 0
+
+
+def random_choice(n: int) -> int:
+    return random.randint(0, n - 1)
+
+
+def _ordered(s: set, set_order: str) -> List[int]:
+    return sorted(s) if set_order == "ascending" else list(s)
+
+
+# ------------------------------------------------------------------------------------------------
+# A13  coin/engine/base.py:80-126  box rescale + flip into the network-input frame
+# ------------------------------------------------------------------------------------------------
+def process_boxes(boxes: torch.Tensor, old_size, new_size, flip: str = "no") -> torch.Tensor:
+    img_h, img_w = old_size
+    net_h, net_w = new_size
+    b = d2_ref.box_scale(boxes.float(), net_w / img_w, net_h / img_h)
+    if flip == "horizontal":
+        f = b.clone()
+        f[:, 0] = net_w - b[:, 2]
+        f[:, 2] = net_w - b[:, 0]
+        b = f
+    elif flip == "vertical":
+        f = b.clone()
+        f[:, 1] = net_h - b[:, 3]
+        f[:, 3] = net_h - b[:, 1]
+        b = f
+    elif flip != "no":
+        raise NotImplementedError(flip)
+    return b
+
+
+# ------------------------------------------------------------------------------------------------
+# A12  coin/layers/nms.py  probabilistic-fusion NMS (MyNMS)
+# ------------------------------------------------------------------------------------------------
+def decode_method(method: str) -> Tuple[Optional[str], Optional[str]]:
+    """nms.py:61-82: two letters -> (score_method, box_method); 'mm' and 'nms' mean plain NMS."""
+    if method == "nms":
+        return None, None
+    assert len(method) == 2
+    sm = {"p": "probEn", "a": "avg", "m": "max"}[method[0]]
+    bm = {"s": "s-avg", "a": "avg", "m": "max"}[method[1]]
+    if sm == "max" and bm == "max":
+        return None, None
+    return sm, bm
+
+
+def _fusion_nms_core(nms_boxes, boxes, probs, labels, thr, score_method, box_method):
+    """nms.py:84-194 on one offset-or-class-restricted set."""
+    n = boxes.shape[0]
+    x1, y1, x2, y2 = nms_boxes.unbind(1)
+    area = (x2 - x1 + 1) * (y2 - y1 + 1)
+    score = probs[torch.arange(n), labels]
+    alive = score.argsort(descending=True)
+    rows = []
+    while alive.numel() > 0:
+        i, rest = alive[0], alive[1:]
+        w = torch.clamp(torch.min(x2[i], x2[rest]) - torch.max(x1[i], x1[rest]) + 1, min=0.0)
+        h = torch.clamp(torch.min(y2[i], y2[rest]) - torch.max(y1[i], y1[rest]) + 1, min=0.0)
+        inter = w * h
+        ovr = inter / (area[i] + area[rest] - inter)
+        hit = ovr > thr
+        members = torch.cat((rest[hit], i.view(1)))  # matched ones first, the pivot last (:130-133)
+        if members.numel() > 1:
+            m_prob, m_score, m_box, m_lab = probs[members], score[members], boxes[members], labels[members]
+            cls = torch.unique(m_lab)
+            assert cls.numel() == 1
+            if score_method == "probEn":
+                assert bool((m_prob.max(1)[1] == m_lab).all())
+                e = torch.exp(torch.log(m_prob).sum(dim=0))
+                f_prob = e / e.sum()
+                f_score = f_prob[cls[0]]
+            elif score_method == "avg":
+                f_prob, f_score = m_prob.mean(dim=0), m_score.mean()
+            else:  # max
+                top = torch.argmax(m_score)
+                f_prob, f_score = m_prob[top], m_score[top]
+            if box_method == "s-avg":
+                wgt = m_score / m_score.sum()
+                f_box = (m_box * wgt[:, None]).sum(dim=0)
+            elif box_method == "avg":
+                f_box = m_box.sum(dim=0) / members.numel()
+            else:
+                f_box = m_box[torch.argmax(m_score)]
+            rows.append((i, f_box, f_score, f_prob, cls[0]))
+        else:
+            rows.append((i, boxes[i], score[i], probs[i], labels[i]))
+        alive = rest[~hit]
+    keep = torch.stack([r[0] for r in rows])
+    o_box = torch.stack([r[1] for r in rows])
+    o_score = torch.stack([r[2] for r in rows])
+    o_prob = torch.stack([r[3] for r in rows])
+    o_cls = torch.stack([r[4] for r in rows])
+    order = o_score.argsort(descending=True)
+    return keep[order], o_box[order], o_score[order], o_prob[order], o_cls[order]
+
+
+def mynms(method: str, boxes, scores, probs, idxs, thr):
+    """MyNMS(method).nms(boxes, scores, probs, idxs, thr)  nms.py:205-238."""
+    sm, bm = decode_method(method)
+    if sm is None:
+        keep = d2_ref.batched_nms(boxes, scores, idxs, thr)
+        return keep, boxes[keep], scores[keep], probs[keep], idxs[keep]
+    assert boxes.shape[-1] == 4
+    if len(boxes) < 40000:
+        boxes = boxes.float()
+        if boxes.numel() == 0:
+            return torch.empty((0,), dtype=torch.int64), boxes, scores, probs, idxs
+        off = idxs.to(boxes) * (boxes.max() + torch.tensor(1).to(boxes))
+        return _fusion_nms_core(boxes + off[:, None], boxes, probs, idxs, thr, sm, bm)
+    kept = torch.zeros_like(scores, dtype=torch.bool)
+    parts = []
+    for cid in torch.unique(idxs).tolist():
+        sel = (idxs == cid).nonzero().view(-1)
+        k, b, s, p, l = _fusion_nms_core(boxes[sel], boxes[sel], probs[sel], idxs[sel], thr, sm, bm)
+        parts.append((b, s, p, l))
+        kept[sel[k]] = True
+    b, s, p, l = (torch.cat([q[i] for q in parts], dim=0) for i in range(4))
+    order = s.argsort(descending=True)
+    return kept.nonzero().view(-1)[order], b[order], s[order], p[order], l[order]
+
+
+def weighted_box_fusion_split(box_a, box_b, score_a, score_b):
+    """nms.py:24-31 (weights first, then multiply, then add)."""
+    s = torch.stack((score_a, score_b), dim=1)
+    w = s / s.sum(dim=1, keepdim=True)
+    return box_a * w[:, 0:1] + box_b * w[:, 1:]
+
+
+# ------------------------------------------------------------------------------------------------
+# A11  coin/modeling/roi_heads/fast_rcnn.py:116-175
+# ------------------------------------------------------------------------------------------------
+def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, nms_thresh, topk):
+    valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
+    if not valid.all():
+        boxes, scores = boxes[valid], scores[valid]
+    probs = scores.clone()
+    scores = scores[:, :-1]
+    kreg = boxes.shape[1] // 4
+    boxes = d2_ref.box_clip(boxes.reshape(-1, 4), image_shape).view(-1, kreg, 4)
+    fmask = scores > score_thresh
+    finds = fmask.nonzero()
+    boxes = boxes[finds[:, 0], 0] if kreg == 1 else boxes[fmask]
+    scores = scores[fmask]
+    probs = probs[finds[:, 0]]
+    keep = d2_ref.batched_nms(boxes, scores, finds[:, 1], nms_thresh)
+    if topk >= 0:
+        keep = keep[:topk]
+    finds = finds[keep]
+    return {"pred_boxes": boxes[keep], "scores": scores[keep], "probs": probs[keep],
+            "pred_classes": finds[:, 1]}, finds[:, 0]
+
+
+# ------------------------------------------------------------------------------------------------
+# A8  relabelling epilogues of the fused IoU+Matcher step
+# ------------------------------------------------------------------------------------------------
+def relabel_roi(matched_idxs, matched_labels, len_a, len_b, len_c):
+    """clip_roi_heads.py:358-362: fg matches that fell on a private (C) box are ignored (-1)."""
+    lab = matched_labels.clone()
+    in_c = (matched_idxs >= len_a + len_b) & (matched_idxs < len_a + len_b + len_c)
+    lab[in_c & ~(matched_labels == 0)] = -1
+    return lab
+
+
+def relabel_rpn(matched_idxs, labels, len_a, len_c):
+    """rpn.py:214-228: returns (gt_labels, matched_idxs, distillation_idxs, distillation_labels)."""
+    idx, lab = matched_idxs.clone(), labels.clone()
+    in_c = (idx >= len_a) & (idx < len_a + len_c)
+    fg_c = in_c & ~(lab == 0)
+    lab[fg_c] = -1
+    dist_idx = matched_idxs - len_a
+    dist_idx[~fg_c] = 0
+    idx[in_c] = 0
+    dist_lab = lab.clone()
+    dist_lab[fg_c] = 1
+    dist_lab[~fg_c] = 0
+    return lab, idx, dist_idx, dist_lab
+
+
+# ------------------------------------------------------------------------------------------------
+# A9  knowledge separation: coin/utils/util.py:434-507 + coin/engine/trainer.py:338-485
+# ------------------------------------------------------------------------------------------------
+def delete_duplicate_boxes(d: DetSet, return_split: bool = False,
+                           choose: Callable[[int], int] = first_choice):
+    """util.py:434-457. Groups rows by the fp32 sum of their 4 coordinates; a group is a duplicate
+    set only when the summed difference to its first row is exactly zero (the reference's weak
+    test, kept as is)."""
+    boxes = d["gt_boxes"]
+    key = boxes.sum(1)
+    uniq = torch.unique(key)
+    member = torch.eq(uniq.unsqueeze(1), key)
+    member = member[member.sum(1) != 1]
+    groups = []
+    for g in range(member.size(0)):
+        rows = member[g]
+        if (boxes[rows] - boxes[rows][0]).sum() == 0:
+            grp = take(d, rows)
+            groups.append(grp if return_split else take(grp, choose(length(grp))))
+        else:
+            member[g][rows.nonzero()[:, 0]] = False
+    singles = take(d, (member.sum(0) == 0).nonzero()[:, 0])
+    if return_split:
+        return singles, groups
+    return cat([singles] + groups)
+
+
+def self_clusters(boxes: torch.Tensor, thresh: float, set_order: str = "ascending") -> List[List[int]]:
+    """util.py:459-482 (filter_result + find_same): index clusters of size != 1 among boxes whose
+    mutual IoU >= thresh, closed transitively by the reference's recursive set union."""
+    adj = d2_ref.pairwise_iou(boxes, boxes) >= thresh
+    sets = [set(adj[i].nonzero()[:, 0].tolist()) for i in range(boxes.shape[0])]
+
+    def absorb(path, i):
+        for j in _ordered(sets[i], set_order):
+            if j != i and j not in path:
+                if sets[j] - sets[i]:
+                    sets[i] = sets[i] | absorb(path + [i], j)
+        return sets[i]
+
+    for i in range(len(sets)):
+        for j in _ordered(sets[i], set_order):
+            if j != i:
+                sets[i] = sets[i] | absorb([i], j)
+        for j in sets[i]:
+            if j != i:
+                sets[j] = set()
+    return [_ordered(s, set_order) for s in sets if len(s) > 1]
+
+
+def online_boxes_merging(online: DetSet, common_off: DetSet, common_on: DetSet,
+                         set_order: str = "ascending"):
+    """util.py:484-507: resolve cloud boxes that overlap each other at IoU >= 0.95 with
+    different classes."""
+    for cluster in self_clusters(online["gt_boxes"], 0.95, set_order):
+        grp = take(online, torch.tensor(cluster, dtype=torch.int64))
+        assert grp["gt_classes"].unique().size(0) != 1
+        hit = torch.eq(grp["gt_boxes"].unsqueeze(1), common_on["gt_boxes"]).sum(-1) == 4
+        touched = torch.unique(hit.nonzero()[:, 1])
+        untouched_mask = torch.ones(length(common_on))
+        untouched_mask[touched] = 0
+        untouched = untouched_mask.nonzero()[:, 0]
+        with_first = hit[0].nonzero()[:, 0]
+        clip_cls = common_off["gt_classes"][with_first].unique()
+        if clip_cls.size(0) == 1:
+            agree = common_on["gt_classes"][touched] == clip_cls
+            if agree.sum() != 0:
+                touched = touched[agree]
+        else:
+            differ = common_on["gt_classes"][touched] != common_off["gt_classes"][touched]
+            touched = touched[differ]
+        common_on = cat([take(common_on, untouched), take(common_on, touched)])
+        common_off = cat([take(common_off, untouched), take(common_off, touched)])
+    return common_off, common_on
+
+
+def match_dual_teacher(online: DetSet, offline: DetSet, tag: str, iou_thr: float = 0.5,
+                       weight_for_box_a: float = 1.0,
+                       choose: Callable[[int], int] = first_choice, set_order: str = "ascending"):
+    """trainer.py:338-461. ``online`` = cloud detections (after process()), ``offline`` =
+    CLIP-detector detections; both with fields gt_boxes, gt_classes, scores, probs.
+    Returns (A, B or None, C) as dicts."""
+    nc, nd = length(online), length(offline)
+    if nc == 0 and nd == 0:
+        com_on, com_off, off_only, on_only = online, offline, [offline], online
+    elif nc == 0:
+        fg = offline["scores"] > 0.8
+        com_on = com_off = take(offline, fg)
+        off_only, on_only = [take(offline, ~fg)], online
+    elif nd == 0:
+        com_on = com_off = online
+        off_only, on_only = [offline], offline
+    else:
+        uniq, dup_groups = delete_duplicate_boxes(offline, return_split=True)
+        pairs = (d2_ref.pairwise_iou(online["gt_boxes"], uniq["gt_boxes"]) >= iou_thr).nonzero()
+        on_parts, off_parts = [take(online, pairs[:, 0])], [take(uniq, pairs[:, 1])]
+        left = set(range(length(uniq))) - set(pairs[:, 1].tolist())
+        off_only = [take(uniq, torch.tensor(_ordered(left, set_order), dtype=torch.int64))]
+        used_on = pairs[:, 0].tolist()
+        for grp in dup_groups:
+            gp = (d2_ref.pairwise_iou(online["gt_boxes"], grp["gt_boxes"]) >= iou_thr).nonzero()
+            if gp.size(0) != 0:
+                i0 = int(gp[0, 0])
+                same = grp["gt_classes"] == online["gt_classes"][i0]
+                on_parts.append(take(online, i0))
+                used_on.append(i0)
+                off_parts.append(take(grp, same) if same.sum() >= 1
+                                 else take(grp, choose(length(grp))))
+            else:
+                off_only.append(take(grp, choose(length(grp))))
+        com_off, com_on = online_boxes_merging(online, cat(off_parts), cat(on_parts), set_order)
+        rest = set(range(nc)) - set(used_on)
+        on_only = take(online, torch.tensor(_ordered(rest, set_order), dtype=torch.int64))
+
+    c = cat(off_only + [on_only])
+    C = {"gt_boxes": c["gt_boxes"], "gt_classes": c["gt_classes"], "gt_scores": c["scores"],
+         "gt_probs": c["probs"]}
+
+    def merged(on_s: DetSet, off_s: DetSet):
+        if weight_for_box_a != 1.0:
+            return weighted_box_fusion_split(on_s["gt_boxes"], off_s["gt_boxes"], on_s["scores"],
+                                             off_s["scores"])
+        return on_s["gt_boxes"]
+
+    def pack(on_s: DetSet, off_s: DetSet, split_classes: bool) -> DetSet:
+        out = {"gt_boxes": merged(on_s, off_s)}
+        if split_classes:
+            out["gt_classes_offline"], out["gt_classes_online"] = off_s["gt_classes"], on_s["gt_classes"]
+        else:
+            out["gt_classes"] = off_s["gt_classes"]
+        out["gt_scores_online"], out["gt_scores_offline"] = on_s["scores"], off_s["scores"]
+        out["gt_probs_online"], out["gt_probs_offline"] = on_s["probs"], off_s["probs"]
+        return delete_duplicate_boxes(out, choose=choose)
+
+    if tag == "RCNN":
+        same = com_off["gt_classes"] == com_on["gt_classes"]
+        A = pack(take(com_on, same), take(com_off, same), False)
+        B = pack(take(com_on, ~same), take(com_off, ~same), True)
+        clash = torch.eq(B["gt_boxes"].unsqueeze(1), A["gt_boxes"]).sum(-1) == 4
+        B = take(B, clash.sum(1) == 0)
+    elif tag == "RPN":
+        A, B = pack(com_on, com_off, False), None
+    else:
+        raise ValueError(tag)
+    return A, B, C
