@@ -29,6 +29,7 @@ _SIGNATURES = {
     # name: (restype, [argtypes])
     "coin_last_error": (c_char_p, []),
     "coin_version": (c_int, []),
+    "coin_launch_count": (ctypes.c_longlong, []),
     "coin_nchw_to_nhwc_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, P]),
     "coin_nhwc_f32_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "coin_roi_align_fwd": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
@@ -67,7 +68,7 @@ EXPORTS = tuple(_SIGNATURES.keys())
 
 if not os.path.exists(SO_PATH):
     raise ImportError(
-        f"{SO_PATH} is missing: build it with `python -m coin_b200.build` (nvcc, sm_100a). "
+        f"{SO_PATH} is missing: build it with `python coin_b200/build.py` (nvcc, sm_100a). "
         "coin_b200 has no CPU or PyTorch fallback.")
 
 lib = ctypes.CDLL(SO_PATH)

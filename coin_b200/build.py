@@ -1,6 +1,6 @@
 """Builds coin_b200/libcoinops.so (sm_100a only) with nvcc. In-tree, no JIT cache.
 
-    python -m coin_b200.build [--force] [--verbose]
+    python coin_b200/build.py [--force] [--verbose]      (or __graft_entry__.build())
 
 -fmad=false: the integer-valued results of this path (match indices, labels, keep lists) are decided
 by float compares; the CPU oracle executes un-fused multiply/add, so the kernels must too.

@@ -16,7 +16,10 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 // thread-local error message (defined in capi.cu)
 int fail(int code, const char* fmt, ...);
 
+void count_launch();  // capi.cu: process-wide counter behind coin_launch_count()
+
 inline int check_launch(const char* what) {
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(COIN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return COIN_OK;

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a) {
     int P = 0;        // common pairs
     int cur = 0;      // which pon/poff buffer is live
     int nC = 0;       // private rows written so far
+    int nC_off = 0;   // ... of which CLIP-detector rows (they come first)
 
     if (on_empty && off_empty) {
         // nothing
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a) {
         for (int p = threadIdx.x; p < min(P, a.cap); p += blockDim.x) a.poff[0][p] = a.pon[0][p];
         nC = compact_append(nd, [&](int j) { return !(a.offs[j] > 0.8f); }, [&](int j) { return j; }, a.c_off, 0, nc + nd, &s_tmp);
         for (int r = threadIdx.x; r < nC; r += blockDim.x) a.c_on[r] = -1;
+        nC_off = nC;
         __syncthreads();
     } else if (off_empty) {
         // trainer.py:356-361: every cloud box is "common" with itself
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a) {
 
         // ---- E. cloud boxes never used in a pair -> private (trainer.py:391)
         const int before = nC;
+        nC_off = nC;
         nC = compact_append(nc, [&](int i) { return !a.on_used[i]; }, [&](int i) { return i; }, a.c_on, nC, nc + nd, &s_tmp);
         for (int r = before + threadIdx.x; r < nC; r += blockDim.x) a.c_off[r] = -1;
         __syncthreads();
@@ -421,6 +424,7 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a) {
         a.counts[0] = nA;
         a.counts[1] = nB;
         a.counts[2] = nC;
+        a.counts[4] = nC_off;
         if (status) atomicOr(&a.counts[3], status);
     }
 }
@@ -464,7 +468,7 @@ extern "C" int coin_match_abc(const float* on_boxes, const int64_t* on_classes, 
     COIN_REQUIRE(nc <= COIN_ABC_MAX && nd <= COIN_ABC_MAX, "match_abc: at most %d detections per side", COIN_ABC_MAX);
     COIN_REQUIRE(tag == COIN_TAG_RCNN || tag == COIN_TAG_RPN, "match_abc: bad tag %d", tag);
     cudaStream_t s = as_stream(stream);
-    cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), s);
+    cudaMemsetAsync(counts, 0, 8 * sizeof(int32_t), s);
     if (nc == 0 && nd == 0) return COIN_OK;
     COIN_REQUIRE(cap_pairs >= nc * nd + nc + nd, "match_abc: cap_pairs must be >= nc*nd + nc + nd");
     COIN_REQUIRE(a_on && a_off && a_boxes && c_on && c_off && ws, "match_abc: null pointer");

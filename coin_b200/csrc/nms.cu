@@ -336,6 +336,7 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
         size_t bytes = w.cub_bytes;
         cudaError_t e = cub::DeviceRadixSort::SortKeys(w.cub_tmp, bytes, db, n, 0, 64, s);
         if (e != cudaSuccess) return fail(COIN_ERR_CUDA, "nms: radix sort failed: %s", cudaGetErrorString(e));
+        count_launch();
         if (strategy == COIN_NMS_TRICK || strategy == COIN_NMS_AUTO) {
             cudaMemsetAsync(w.max_coord, 0x80, sizeof(int), s);  // 0x80808080 decodes to ~ -3.4e38
             max_coord_kernel<<<kNumSMs, 256, 0, s>>>(b4, w.meta, w.max_coord);

@@ -94,11 +94,8 @@ def match_dual_teacher(online: Instances, offline: Instances, tag: str, iou_thre
     a = pack(r["a_on"], r["a_off"], r["a_boxes"], False)
     b = pack(r["b_on"], r["b_off"], r["b_boxes"], True) if tag == "RCNN" else None
 
-    # C rows reference exactly one side (the other index is -1): CLIP-detector rows first
-    c_on, c_off = r["c_on"], r["c_off"]
-    from_off = c_off >= 0
-    n_off = int(from_off.sum().item()) if c_off.numel() else 0
-    off_rows, on_rows = c_off[:n_off], c_on[n_off:]
+    # C rows: CLIP-detector rows first (c_off), then cloud rows (c_on)
+    off_rows, on_rows = r["c_off"], r["c_on"]
     c = Instances(size)
     fields = ("gt_boxes", "gt_classes", "scores", "probs")
     parts = []

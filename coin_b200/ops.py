@@ -266,7 +266,8 @@ _STRATEGY = {"plain": _lib.NMS_PLAIN, "trick": _lib.NMS_TRICK, "vanilla": _lib.N
 
 
 def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: Optional[torch.Tensor], iou_threshold: float,
-                strategy: str = "auto", max_keep: int = -1) -> torch.Tensor:
+                strategy: str = "auto", max_keep: int = -1, sync: bool = True):
+    """sync=False returns (keep buffer of capacity n, device int32 count) without a host round trip."""
     boxes = _boxes(boxes, "boxes")
     scores = _f32c(scores, "scores")
     n = boxes.shape[0]
@@ -279,6 +280,8 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: Optional[torch.
     ws = _workspace(lib.coin_nms_workspace_bytes(n), boxes.device)
     check(lib.coin_batched_nms(_ptr(boxes), _ptr(scores), _ptr(idxs), n, float(iou_threshold), _STRATEGY[strategy],
                                int(max_keep), _ptr(keep), _ptr(nkeep), _ptr(ws), ws.numel(), _stream()))
+    if not sync:
+        return keep, nkeep
     return keep[: int(nkeep.item())]
 
 
@@ -344,8 +347,10 @@ def det_postprocess(boxes: torch.Tensor, scores: torch.Tensor, image_shape: Tupl
 
 
 def match_abc(on_boxes, on_classes, on_scores, off_boxes, off_classes, off_scores, tag: str, iou_thr: float,
-              weight_for_box_a: float):
-    """Index form of match_dual_teacher. Returns dict with a_on, a_off, a_boxes, b_*, c_on, c_off."""
+              weight_for_box_a: float, sync: bool = True):
+    """Index form of match_dual_teacher. Returns dict with a_on, a_off, a_boxes, b_*, c_on, c_off.
+    sync=False returns the un-narrowed buffers plus the device int32 ``counts`` = [nA, nB, nC, status]
+    (narrow later with ``match_abc_narrow`` once the counts have been read back)."""
     on_boxes, off_boxes = _boxes(on_boxes, "online boxes"), _boxes(off_boxes, "offline boxes")
     on_classes, off_classes = _i64c(on_classes, "online classes"), _i64c(off_classes, "offline classes")
     on_scores, off_scores = _f32c(on_scores, "online scores"), _f32c(off_scores, "offline scores")
@@ -357,14 +362,24 @@ def match_abc(on_boxes, on_classes, on_scores, off_boxes, off_classes, off_score
     c_on, c_off = i32(nc + nd), i32(nc + nd)
     a_box = torch.empty((max(cap, 1), 4), dtype=torch.float32, device=dev)
     b_box = torch.empty((max(cap, 1), 4), dtype=torch.float32, device=dev)
-    counts = torch.zeros((4,), dtype=torch.int32, device=dev)
+    counts = torch.zeros((8,), dtype=torch.int32, device=dev)
     ws = _workspace(lib.coin_match_abc_workspace_bytes(nc, nd), dev)
     code = {"RCNN": _lib.TAG_RCNN, "RPN": _lib.TAG_RPN}[tag]
     check(lib.coin_match_abc(_ptr(on_boxes), _ptr(on_classes), _ptr(on_scores), nc, _ptr(off_boxes), _ptr(off_classes),
                              _ptr(off_scores), nd, code, float(iou_thr), float(weight_for_box_a), cap, _ptr(a_on),
                              _ptr(a_off), _ptr(a_box), _ptr(b_on), _ptr(b_off), _ptr(b_box), _ptr(c_on), _ptr(c_off),
                              _ptr(counts), _ptr(ws), ws.numel(), _stream()))
-    na, nb, ncc, status = (int(v) for v in counts.tolist())
+    raw = {"a_on": a_on, "a_off": a_off, "a_boxes": a_box, "b_on": b_on, "b_off": b_off, "b_boxes": b_box,
+           "c_on": c_on, "c_off": c_off, "counts": counts}
+    if not sync:
+        return raw
+    return match_abc_narrow(raw, counts.tolist())
+
+
+def match_abc_narrow(raw, counts):
+    na, nb, ncc, status, nc_off = (int(v) for v in counts[:5])
+    a_on, a_off, a_box, b_on, b_off, b_box, c_on, c_off = (raw[k] for k in (
+        "a_on", "a_off", "a_boxes", "b_on", "b_off", "b_boxes", "c_on", "c_off"))
     if status & 16:
         raise AssertionError("match_abc: a cloud self-cluster has a single class (util.py:488 assert)")
     if status & 8:
@@ -374,4 +389,4 @@ def match_abc(on_boxes, on_classes, on_scores, off_boxes, off_classes, off_score
         raise RuntimeError("match_abc: pair capacity exceeded")
     return {"a_on": a_on[:na].long(), "a_off": a_off[:na].long(), "a_boxes": a_box[:na],
             "b_on": b_on[:nb].long(), "b_off": b_off[:nb].long(), "b_boxes": b_box[:nb],
-            "c_on": c_on[:ncc].long(), "c_off": c_off[:ncc].long()}
+            "c_on": c_on[nc_off:ncc].long(), "c_off": c_off[:nc_off].long()}

@@ -1,0 +1,214 @@
+"""One step of COIN's RoI path over a batch of images, on one GPU.
+
+This is the per-iteration work of ``CoinTrainer.run_step`` (coin/engine/trainer.py:160-218) that
+lies between the backbone and the box-head GEMMs, in the reference's order:
+
+  teacher branch (per image)
+    T1  Box2BoxTransform.apply_deltas + Boxes.clip           fast_rcnn.py:729,145-147
+    T2  score filter -> batched NMS -> top-100                fast_rcnn.py:116-175
+    T3  cloud detections: Boxes.scale (+flip)                 base.py:80-136
+    T4  knowledge separation, tags 'RCNN' and 'RPN'           trainer.py:338-478
+  student branch (per image)
+    S1  RPN proposal NMS (thr 0.7, keep[:post_nms_topk])      d2 find_top_rpn_proposals <- rpn.py:113
+    S2  anchors vs A|C: pairwise_iou + Matcher(low quality)   rpn.py:209-228
+    S3  proposals(+A,B) vs A|B|C: pairwise_iou + Matcher      clip_roi_heads.py:345-362
+  student branch (batch)
+    S4  ROIAlign forward on the sampled RoIs + on the C boxes clip_roi_heads.py:201-203,213-217
+    S5  ROIAlign backward (gradient w.r.t. the res4 map)
+
+Host round trips: two per BATCH (the detection counts after T2, the A/B/C counts after T4), each a
+single small D2H copy; the reference has several per image (trainer.py:469, nonzero()/tolist()).
+Everything else is asynchronous launches of libcoinops kernels on the current stream.
+"""
+from typing import Dict, List
+
+import torch
+
+from . import ops
+from .synth import Shape
+
+ORIG_SCALE = 2048.0 / 1200.0  # Foggy-Cityscapes: 1024x2048 originals, 600x1200 network input
+
+
+def anchors_for(shape: Shape) -> torch.Tensor:
+    """detectron2 DefaultAnchorGenerator for the single stride-16 map (Base-Cloud.yaml:22-24):
+    sizes 32..512 x ratios 0.5,1,2; (H, W, A) flattening. Host-side constant, built once."""
+    import math
+    base = []
+    for s in (32, 64, 128, 256, 512):
+        for r in (0.5, 1.0, 2.0):
+            w = math.sqrt(s * s / r)
+            h = r * w
+            base.append([-w / 2.0, -h / 2.0, w / 2.0, h / 2.0])
+    base = torch.tensor(base, dtype=torch.float32)
+    hf, wf = shape.feat_hw
+    sx = torch.arange(0, wf * shape.stride, step=shape.stride, dtype=torch.float32)
+    sy = torch.arange(0, hf * shape.stride, step=shape.stride, dtype=torch.float32)
+    yy, xx = torch.meshgrid(sy, sx, indexing="ij")
+    shifts = torch.stack((xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)), dim=1)
+    return (shifts.view(-1, 1, 4) + base.view(1, -1, 4)).reshape(-1, 4)
+
+
+class RoIPathStep:
+    BBOX_WEIGHTS = (10.0, 10.0, 5.0, 5.0)   # ROI_BOX_HEAD.BBOX_REG_WEIGHTS (fast_rcnn.py:297)
+    SCORE_THRESH, NMS_THRESH, TOPK = 0.05, 0.5, 100
+    RPN_NMS_THRESH = 0.7
+    MATCH_THRESH = 0.5                      # CLOUD.MATCHER.IOU_THRESHOLDS (config.py:143)
+
+    def __init__(self, shape: Shape, device, weight_for_box_a: float = 1.0, seed: int = 2024):
+        self.shape, self.device, self.w_a = shape, device, weight_for_box_a
+        self.anchors = anchors_for(shape).to(device)
+        hf, wf = shape.feat_hw
+        g = torch.Generator(device="cpu")
+        g.manual_seed(seed + 1)
+        # The box head behind ROIAlign is stood in for by a linear functional <pooled, G>: its gradient
+        # w.r.t. the pooled features is the constant G, resident on the device like a weight.
+        self.head_grad = torch.randn(shape.images * shape.rois, shape.channels, shape.pooled, shape.pooled,
+                                     generator=g).to(device)
+        self._pinned = None
+
+    # -- data movement -------------------------------------------------------------------------
+    def host_inputs(self, batch) -> Dict[str, torch.Tensor]:
+        """Flat dict of the per-step INPUT tensors (pinned host memory) for the end-to-end timing."""
+        flat = {"features": batch["features"]}
+        for i, img in enumerate(batch["images"]):
+            for k in ("teacher_rois", "teacher_deltas", "teacher_probs", "proposals", "rois", "rpn_boxes",
+                      "rpn_scores"):
+                flat[f"{i}.{k}"] = img[k]
+            for side in ("cloud", "clip"):
+                if side == "clip":
+                    continue  # CLIP-detector detections are produced on the device by T2
+                for k, v in img[side].items():
+                    flat[f"{i}.{side}.{k}"] = v * ORIG_SCALE if k == "gt_boxes" else v
+        return {k: v.contiguous().pin_memory() for k, v in flat.items()}
+
+    def h2d(self, pinned: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return {k: v.to(self.device, non_blocking=True) for k, v in pinned.items()}
+
+    def to_device(self, batch):
+        return self.h2d(self.host_inputs(batch))
+
+    @staticmethod
+    def input_bytes(pinned) -> int:
+        return sum(v.numel() * v.element_size() for v in pinned.values())
+
+    # -- the step --------------------------------------------------------------------------------
+    def run(self, d: Dict[str, torch.Tensor], backward: bool = True) -> Dict[str, object]:
+        sh, dev = self.shape, self.device
+        n_img = sh.images
+        img_size = (sh.height, sh.width)
+        k1 = sh.classes + 1
+        nhwc = ops.to_nhwc_f32(d["features"])
+
+        # ---- teacher branch, launches for every image first (no host sync inside the loop)
+        dets, cloud_boxes, rpn = [], [], []
+        for i in range(n_img):
+            dec = ops.apply_deltas(d[f"{i}.teacher_deltas"], d[f"{i}.teacher_rois"], self.BBOX_WEIGHTS,
+                                   clip_to=img_size)                                                    # T1
+            dets.append(ops.det_postprocess(dec, d[f"{i}.teacher_probs"], img_size, self.SCORE_THRESH,
+                                            self.NMS_THRESH, self.TOPK, sync=False))                      # T2
+            cloud_boxes.append(ops.boxes_scale_flip(d[f"{i}.cloud.gt_boxes"], sh.width / (sh.width * ORIG_SCALE),
+                                                    sh.height / (sh.height * ORIG_SCALE), "no", img_size))  # T3
+            rpn.append(ops.batched_nms(d[f"{i}.rpn_boxes"], d[f"{i}.rpn_scores"], None, self.RPN_NMS_THRESH,
+                                       "plain", sh.rpn_post_nms, sync=False))                             # S1
+        counts1 = torch.stack([x[5] for x in dets] + [x[1] for x in rpn]).view(-1).cpu()                 # sync 1
+        n_det = counts1[:n_img].tolist()
+        n_rpn = counts1[n_img:].tolist()
+
+        # ---- knowledge separation (T4): two launches per image
+        raws = []
+        for i in range(n_img):
+            b, s, p, c, _, _ = dets[i]
+            nd = n_det[i]
+            for tag in ("RCNN", "RPN"):
+                raws.append(ops.match_abc(cloud_boxes[i], d[f"{i}.cloud.gt_classes"], d[f"{i}.cloud.scores"],
+                                          b[:nd], c[:nd], s[:nd], tag, self.MATCH_THRESH, self.w_a, sync=False))
+        counts2 = torch.stack([r["counts"] for r in raws]).cpu().tolist()                                 # sync 2
+
+        out: Dict[str, object] = {"dets": [], "abc": [], "roi_labels": [], "rpn_labels": [], "rpn_keep": []}
+        c_rois = []
+        for i in range(n_img):
+            b, s, p, c, roi_idx, _ = dets[i]
+            nd = n_det[i]
+            out["dets"].append({"pred_boxes": b[:nd], "scores": s[:nd], "probs": p[:nd], "pred_classes": c[:nd],
+                                "roi_index": roi_idx[:nd]})
+            out["rpn_keep"].append(rpn[i][0][: n_rpn[i]])
+            cloud = {"gt_boxes": cloud_boxes[i], "gt_classes": d[f"{i}.cloud.gt_classes"],
+                     "scores": d[f"{i}.cloud.scores"], "probs": d[f"{i}.cloud.probs"]}
+            clip = {"gt_boxes": b[:nd], "gt_classes": c[:nd], "scores": s[:nd], "probs": p[:nd]}
+            per_tag = {}
+            for t, tag in enumerate(("RCNN", "RPN")):
+                r = ops.match_abc_narrow(raws[2 * i + t], counts2[2 * i + t])
+                per_tag[tag] = self._pack(r, cloud, clip, tag)
+            out["abc"].append(per_tag)
+
+            a, bb, cc = per_tag["RCNN"]
+            gt = torch.cat((a["gt_boxes"], bb["gt_boxes"], cc["gt_boxes"]))
+            props = torch.cat((d[f"{i}.proposals"], a["gt_boxes"], bb["gt_boxes"]))   # add_ground_truth_to_proposals
+            idx, lab = ops.iou_match(gt, props, [0.5], [0, 1], False)                                      # S3
+            la, lb, lc = a["gt_boxes"].shape[0], bb["gt_boxes"].shape[0], cc["gt_boxes"].shape[0]
+            ops.relabel_roi_(idx, lab, la + lb, la + lb + lc)
+            out["roi_labels"].append((idx, lab))
+
+            a2, _, c2 = per_tag["RPN"]
+            gt2 = torch.cat((a2["gt_boxes"], c2["gt_boxes"]))
+            idx2, lab2 = ops.iou_match(gt2, self.anchors, [0.3, 0.7], [0, -1, 1], True)                    # S2
+            out["rpn_labels"].append(ops.relabel_rpn_(idx2, lab2, a2["gt_boxes"].shape[0], c2["gt_boxes"].shape[0]))
+            cb = cc["gt_boxes"]
+            c_rois.append(torch.cat((torch.full((cb.shape[0], 1), float(i), device=dev), cb), dim=1))
+
+        # ---- ROIAlign forward (S4) and backward (S5)
+        rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
+                          for i in range(n_img)])
+        scale = (1.0 / sh.stride,)
+        size = (sh.pooled, sh.pooled)
+        out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32)
+        out["pooled_c"] = ops.roi_align_forward([nhwc], scale, torch.cat(c_rois), None, size, 0, True, torch.float32)
+        if backward:
+            n, c, h, w = d["features"].shape
+            out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size, 0,
+                                                          True, [torch.float32])[0]
+        out["summary"] = {"dets": n_det, "rpn_keep": n_rpn, "abc": [c2[:3] for c2 in counts2]}
+        return out
+
+    @staticmethod
+    def _pack(r, cloud, clip, tag):
+        """Gather the reference's A / B / C fields (trainer.py:393-455) from the index lists."""
+        def side(on_idx, off_idx, boxes, split):
+            o = {"gt_boxes": boxes}
+            if split:
+                o["gt_classes_offline"], o["gt_classes_online"] = clip["gt_classes"][off_idx], cloud["gt_classes"][on_idx]
+            else:
+                o["gt_classes"] = clip["gt_classes"][off_idx]
+            o["gt_scores_online"], o["gt_scores_offline"] = cloud["scores"][on_idx], clip["scores"][off_idx]
+            o["gt_probs_online"], o["gt_probs_offline"] = cloud["probs"][on_idx], clip["probs"][off_idx]
+            return o
+
+        a = side(r["a_on"], r["a_off"], r["a_boxes"], False)
+        b = side(r["b_on"], r["b_off"], r["b_boxes"], True) if tag == "RCNN" else None
+        off_rows, on_rows = r["c_off"], r["c_on"]
+        c = {"gt_boxes": torch.cat((clip["gt_boxes"][off_rows], cloud["gt_boxes"][on_rows])),
+             "gt_classes": torch.cat((clip["gt_classes"][off_rows], cloud["gt_classes"][on_rows])),
+             "gt_scores": torch.cat((clip["scores"][off_rows], cloud["scores"][on_rows])),
+             "gt_probs": torch.cat((clip["probs"][off_rows], cloud["probs"][on_rows]))}
+        return a, b, c
+
+    # -- results that travel back to the host in the end-to-end measurement ----------------------
+    @staticmethod
+    def result_tensors(out) -> List[torch.Tensor]:
+        res = []
+        for dd in out["dets"]:
+            res += list(dd.values())
+        for per_tag in out["abc"]:
+            for tag in ("RCNN", "RPN"):
+                for part in per_tag[tag]:
+                    if part is not None:
+                        res += list(part.values())
+        for idx, lab in out["roi_labels"]:
+            res += [idx, lab]
+        for tup in out["rpn_labels"]:
+            res += list(tup)
+        res += out["rpn_keep"]
+        if "grad_features" in out:
+            res.append(out["grad_features"])
+        return res

@@ -51,6 +51,9 @@ typedef void* coin_stream_t; /* cudaStream_t */
 
 const char* coin_last_error(void);
 int coin_version(void);
+/* Number of kernels this library has launched in the process so far (bench.py reports the delta
+ * over its timed region as `gpu_launches`; the radix sort of N > 4096 boxes counts as one). */
+long long coin_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * ROIAlign / ROIPooler
@@ -239,8 +242,9 @@ int coin_det_postprocess(const float* boxes, const float* scores, int64_t R, int
  * CLIP-detector ("offline") detections with merged box out_boxes[r]; -1 marks "no such side"
  * (the empty-side branches, trainer.py:343-361, where both sides are the same detection).
  * C rows reference exactly one side. All index outputs have capacity cap_pairs = nc*nd + nc + nd
- * (A, B) and nc + nd (C). counts: device int32 [4] = {nA, nB, nC, status}; status != 0 when an
- * assertion of the reference would fire. The device resolves the reference's random.randint
+ * (A, B) and nc + nd (C). counts: device int32 [8] = {nA, nB, nC, status, nC_off, 0, 0, 0}: C rows
+ * [0, nC_off) are CLIP-detector rows (c_off valid), rows [nC_off, nC) cloud rows (c_on valid);
+ * status != 0 when an assertion of the reference would fire. The device resolves the reference's random.randint
  * picks as "first" and its set iterations as ascending ("determinism policy"). */
 size_t coin_match_abc_workspace_bytes(int64_t nc, int64_t nd);
 int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float* on_scores, int64_t nc,
