@@ -55,6 +55,20 @@ def _dtype_code(dt: torch.dtype) -> int:
     raise TypeError(f"coin_b200: unsupported dtype {dt} (fp32 and fp16 are supported)")
 
 
+def _event_pair(events):
+    if events is None:
+        return None
+    pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    pair[0].record()
+    events.append(pair)
+    return pair
+
+
+def _event_close(pair):
+    if pair is not None:
+        pair[1].record()
+
+
 def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
 
@@ -85,7 +99,8 @@ def _levels(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float]):
 
 def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
                       roi_level: Optional[torch.Tensor], output_size: Tuple[int, int], sampling_ratio: int,
-                      aligned: bool, out_dtype: torch.dtype) -> torch.Tensor:
+                      aligned: bool, out_dtype: torch.dtype, events: Optional[list] = None) -> torch.Tensor:
+    """events: optional list; a (start, end) CUDA-event pair bracketing the kernel launch is appended."""
     rois = _f32c(rois, "rois")
     if rois.dim() != 2 or rois.shape[1] != 5:
         raise ValueError(f"coin_b200: rois must have shape [K, 5], got {tuple(rois.shape)}")
@@ -94,15 +109,18 @@ def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float
     out = torch.empty((k, c, ph, pw), dtype=out_dtype, device=rois.device)
     if roi_level is not None:
         roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
+    pair = _event_pair(events)
     check(lib.coin_roi_align_fwd(_levels(feats_nhwc, scales), len(feats_nhwc), _ptr(rois), _ptr(roi_level), _ptr(out),
                                  _dtype_code(out_dtype), c, k, ph, pw, int(sampling_ratio), int(bool(aligned)),
                                  _stream()))
+    _event_close(pair)
     return out
 
 
 def roi_align_backward(grad_out: torch.Tensor, shapes: Sequence[Tuple[int, int, int, int]], scales: Sequence[float],
                        rois: torch.Tensor, roi_level: Optional[torch.Tensor], output_size: Tuple[int, int],
-                       sampling_ratio: int, aligned: bool, out_dtypes: Sequence[torch.dtype]) -> List[torch.Tensor]:
+                       sampling_ratio: int, aligned: bool, out_dtypes: Sequence[torch.dtype],
+                       events: Optional[list] = None) -> List[torch.Tensor]:
     """Returns one NCHW gradient per level (shape ``shapes[i]`` = (N,C,H,W), dtype ``out_dtypes[i]``)."""
     grad_out = _cuda(grad_out, "grad_out").contiguous()
     rois = _f32c(rois, "rois")
@@ -111,9 +129,11 @@ def roi_align_backward(grad_out: torch.Tensor, shapes: Sequence[Tuple[int, int, 
     bufs = [torch.zeros((n, h, w, cc), dtype=torch.float32, device=grad_out.device) for (n, cc, h, w) in shapes]
     if roi_level is not None:
         roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
+    pair = _event_pair(events)
     check(lib.coin_roi_align_bwd(_levels(bufs, scales), len(bufs), _ptr(rois), _ptr(roi_level), _ptr(grad_out),
                                  _dtype_code(grad_out.dtype), c, k, ph, pw, int(sampling_ratio), int(bool(aligned)),
                                  _stream()))
+    _event_close(pair)
     outs = []
     for buf, (n, cc, h, w), dt in zip(bufs, shapes, out_dtypes):
         g = torch.empty((n, cc, h, w), dtype=dt, device=buf.device)

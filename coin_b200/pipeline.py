@@ -65,7 +65,7 @@ class RoIPathStep:
         # w.r.t. the pooled features is the constant G, resident on the device like a weight.
         self.head_grad = torch.randn(shape.images * shape.rois, shape.channels, shape.pooled, shape.pooled,
                                      generator=g).to(device)
-        self._pinned = None
+        self.kernel_events = None   # bench.py: {"fwd": [], "bwd": []} to time the two dominant kernels live
 
     # -- data movement -------------------------------------------------------------------------
     def host_inputs(self, batch) -> Dict[str, torch.Tensor]:
@@ -162,12 +162,14 @@ class RoIPathStep:
                           for i in range(n_img)])
         scale = (1.0 / sh.stride,)
         size = (sh.pooled, sh.pooled)
-        out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32)
+        ev = self.kernel_events
+        out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
+                                              events=ev["fwd"] if ev else None)
         out["pooled_c"] = ops.roi_align_forward([nhwc], scale, torch.cat(c_rois), None, size, 0, True, torch.float32)
         if backward:
             n, c, h, w = d["features"].shape
             out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size, 0,
-                                                          True, [torch.float32])[0]
+                                                          True, [torch.float32], events=ev["bwd"] if ev else None)[0]
         out["summary"] = {"dets": n_det, "rpn_keep": n_rpn, "abc": [c2[:3] for c2 in counts2]}
         return out
 
