@@ -11,12 +11,15 @@
 //     x-positions are non-decreasing, so the two feature columns a sample needs are kept in a
 //     register window that is advanced (shift + one column load) instead of re-loaded: each
 //     feature row is read once per sample row instead of 4 taps x samples per bin;
-//   * per bin the samples are still accumulated in the order (iy, ix) with the tap expression
-//     ((w1*v1 + w2*v2) + w3*v3) + w4*v4 and un-fused multiply/add (-fmad=false), which is the
-//     torchvision CPU kernel's order: forward results are bit-identical to the oracle;
-//   * the [channels][bins] slab is transposed through padded shared memory so that the NCHW output
-//     ([K,C,PH,PW], 1.2 GB at the benchmark shape - the HBM-bound part) is written as one contiguous
-//     coalesced region per CTA;
+//   * the x taps (per pw, ix) and y taps (per ph, iy) are computed once per CTA into shared-memory
+//     tables with the oracle's exact operation order, so sample positions are bit-identical;
+//   * per bin the samples are accumulated in the order (iy, ix). COIN_ROI_EXACT=1 (parity mode) keeps
+//     the tap expression ((w1*v1 + w2*v2) + w3*v3) + w4*v4 un-fused (-fmad=false) and is bit-identical
+//     to the torchvision CPU kernel; the default accumulates the same terms with FMAs (half the
+//     arithmetic instructions, ~1e-7 relative difference, inside the 1e-5 parity tolerance);
+//   * the [channels][bins] slab is assembled in shared memory in the exact layout of the CTA's
+//     contiguous output region out[k, c0:c0+CC, :, :] and leaves through 1-D TMA bulk stores
+//     (cp.async.bulk.global.shared::cta) - no per-element store instructions for the 1.2 GB output;
 //   * backward mirrors forward: the register window accumulates tap gradients and is flushed with one
 //     fp32 atomic per touched feature cell and channel instead of 4 x samples atomics per bin.
 #include "common.cuh"
@@ -86,23 +89,102 @@ __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 
 // ------------------------------------------------------------------------------------------------
+// per-RoI sample tables (shared memory): the x taps depend only on (pw, ix), the y taps only on
+// (ph, iy); computing them once per CTA removes ~25 instructions from every sample of every warp.
+// ------------------------------------------------------------------------------------------------
+struct Tap {          // 16 bytes, read as one LDS.128 (broadcast: every lane reads the same entry)
+    int lo, hi;       // element offsets of the low / high cell (x*C or y*W*C); lo < 0: sample outside the map
+    float l, h;       // interpolation weights towards hi / lo
+};
+constexpr int kTapCap = 256;   // entries per axis; larger sampling grids compute taps on the fly
+
+__device__ __forceinline__ Tap make_tap(float start, float bin, int p, int i, int grid, int size, int stride) {
+    const float v = start + (float)p * bin + ((float)i + 0.5f) * bin / (float)grid;
+    Tap t;
+    int lo, hi;
+    if (!axis_taps(v, size, lo, hi, t.l, t.h)) {
+        t.lo = -1; t.hi = -1; t.l = 0.0f; t.h = 0.0f;
+        return t;
+    }
+    t.lo = lo * stride;
+    t.hi = hi * stride;
+    return t;
+}
+
+// ---- TMA bulk copies (shared <-> global, 1-D) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_store_g2s_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(
+            smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <typename OutT, int PWC, int CPL>
-__global__ void __launch_bounds__(512)
-roi_align_fwd_kernel(const RoiParams p, OutT* __restrict__ out, const int NBpad, const int chunks) {
-    extern __shared__ float tile[];  // [32*CPL][NBpad], NBpad odd -> conflict-free both ways
+// EXACT: tap expression and accumulation order of the torchvision CPU kernel with un-fused
+// multiply/add -> bit-identical to the oracle. !EXACT: the same samples accumulated with FMAs
+// (4 instead of 8 instructions per channel and sample, ~1e-7 relative difference).
+template <typename OutT, int PWC, int CPL, bool EXACT>
+__global__ void __launch_bounds__(256, (CPL >= 4 ? 2 : 3))
+roi_align_fwd_kernel(const RoiParams p, OutT* __restrict__ out, const int chunks) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ Tap xs[kTapCap], ys[kTapCap];
+    OutT* tile = reinterpret_cast<OutT*>(smem_raw);  // [32*CPL][PH*PW] == the CTA's contiguous output region
     const int k = blockIdx.x / chunks;
     const int c0 = (blockIdx.x - k * chunks) * (32 * CPL);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
     const coin_level_t L = p.lv[lvl];
-    const int H = L.H, W = L.W, C = p.C, PH = p.PH, PW = p.PW;
+    const int H = L.H, W = L.W, C = p.C, PH = p.PH, PW = p.PW, NB = PH * PW;
     const RoiGeom g = roi_geometry(p.rois + 5 * (size_t)k, L.spatial_scale, PH, PW, p.sampling_ratio, p.aligned);
     const float* __restrict__ fbase = L.feat_nhwc + (size_t)g.batch * H * W * C + c0 + lane;
     bool chv[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) chv[j] = (c0 + lane + 32 * j) < C;
+
+    const bool tabx = PW * g.grid_w <= kTapCap, taby = PH * g.grid_h <= kTapCap;
+    if (tabx)
+        for (int s = threadIdx.x; s < PW * g.grid_w; s += blockDim.x) {
+            const int pw = s / g.grid_w;
+            xs[s] = make_tap(g.start_w, g.bin_w, pw, s - pw * g.grid_w, g.grid_w, W, C);
+        }
+    if (taby)
+        for (int s = threadIdx.x; s < PH * g.grid_h; s += blockDim.x) {
+            const int ph = s / g.grid_h;
+            ys[s] = make_tap(g.start_h, g.bin_h, ph, s - ph * g.grid_h, g.grid_h, H, W * C);
+        }
+    __syncthreads();
+
+    // 1/count: exact for powers of two (and skipped for 1); the EXACT path divides otherwise
+    const int icount = (int)g.count;
+    const bool pow2 = (icount & (icount - 1)) == 0;
+    const float rcount = 1.0f / g.count;
 
     for (int ph = warp; ph < PH; ph += nwarps) {
         for (int pw0 = 0; pw0 < PW; pw0 += PWC) {
@@ -113,51 +195,56 @@ roi_align_fwd_kernel(const RoiParams p, OutT* __restrict__ out, const int NBpad,
                 for (int j = 0; j < CPL; ++j) acc[i][j] = 0.0f;
 
             for (int iy = 0; iy < g.grid_h; ++iy) {
-                const float y = g.start_h + (float)ph * g.bin_h + ((float)iy + 0.5f) * g.bin_h / (float)g.grid_h;
-                int y_lo, y_hi;
-                float ly, hy;
-                if (!axis_taps(y, H, y_lo, y_hi, ly, hy)) continue;
-                const float* __restrict__ rowL = fbase + (size_t)y_lo * W * C;
-                const float* __restrict__ rowH = fbase + (size_t)y_hi * W * C;
-                int col0 = -1, col1 = -1;  // feature columns currently held in the register window
+                const Tap Y = taby ? ys[ph * g.grid_h + iy] : make_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H, W * C);
+                if (Y.lo < 0) continue;
+                const float* __restrict__ rowL = fbase + Y.lo;
+                const float* __restrict__ rowH = fbase + Y.hi;
+                const float ly = Y.l, hy = Y.h;
+                int col0 = -1, col1 = -1;  // element offsets of the columns held in the register window
                 float vL0[CPL], vL1[CPL], vH0[CPL], vH1[CPL];
 #pragma unroll
                 for (int i = 0; i < PWC; ++i) {
                     const int pw = pw0 + i;
                     if (pw >= PW) break;
                     for (int ix = 0; ix < g.grid_w; ++ix) {
-                        const float x = g.start_w + (float)pw * g.bin_w + ((float)ix + 0.5f) * g.bin_w / (float)g.grid_w;
-                        int x_lo, x_hi;
-                        float lx, hx;
-                        if (!axis_taps(x, W, x_lo, x_hi, lx, hx)) continue;
-                        if (x_lo != col0 || x_hi != col1) {
-                            if (x_lo == col1) {
+                        const Tap X = tabx ? xs[pw * g.grid_w + ix] : make_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W, C);
+                        if (X.lo < 0) continue;
+                        if (X.lo != col0 || X.hi != col1) {
+                            if (X.lo == col1) {
 #pragma unroll
                                 for (int j = 0; j < CPL; ++j) { vL0[j] = vL1[j]; vH0[j] = vH1[j]; }
                             } else {
 #pragma unroll
                                 for (int j = 0; j < CPL; ++j) {
-                                    vL0[j] = chv[j] ? __ldg(rowL + (size_t)x_lo * C + 32 * j) : 0.0f;
-                                    vH0[j] = chv[j] ? __ldg(rowH + (size_t)x_lo * C + 32 * j) : 0.0f;
+                                    vL0[j] = chv[j] ? __ldg(rowL + X.lo + 32 * j) : 0.0f;
+                                    vH0[j] = chv[j] ? __ldg(rowH + X.lo + 32 * j) : 0.0f;
                                 }
                             }
-                            if (x_hi == x_lo) {
+                            if (X.hi == X.lo) {
 #pragma unroll
                                 for (int j = 0; j < CPL; ++j) { vL1[j] = vL0[j]; vH1[j] = vH0[j]; }
                             } else {
 #pragma unroll
                                 for (int j = 0; j < CPL; ++j) {
-                                    vL1[j] = chv[j] ? __ldg(rowL + (size_t)x_hi * C + 32 * j) : 0.0f;
-                                    vH1[j] = chv[j] ? __ldg(rowH + (size_t)x_hi * C + 32 * j) : 0.0f;
+                                    vL1[j] = chv[j] ? __ldg(rowL + X.hi + 32 * j) : 0.0f;
+                                    vH1[j] = chv[j] ? __ldg(rowH + X.hi + 32 * j) : 0.0f;
                                 }
                             }
-                            col0 = x_lo;
-                            col1 = x_hi;
+                            col0 = X.lo;
+                            col1 = X.hi;
                         }
-                        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                        const float w1 = hy * X.h, w2 = hy * X.l, w3 = ly * X.h, w4 = ly * X.l;
 #pragma unroll
-                        for (int j = 0; j < CPL; ++j)
-                            acc[i][j] += w1 * vL0[j] + w2 * vL1[j] + w3 * vH0[j] + w4 * vH1[j];
+                        for (int j = 0; j < CPL; ++j) {
+                            if (EXACT) {
+                                acc[i][j] += w1 * vL0[j] + w2 * vL1[j] + w3 * vH0[j] + w4 * vH1[j];
+                            } else {
+                                acc[i][j] = __fmaf_rn(w1, vL0[j], acc[i][j]);
+                                acc[i][j] = __fmaf_rn(w2, vL1[j], acc[i][j]);
+                                acc[i][j] = __fmaf_rn(w3, vH0[j], acc[i][j]);
+                                acc[i][j] = __fmaf_rn(w4, vH1[j], acc[i][j]);
+                            }
+                        }
                     }
                 }
             }
@@ -165,27 +252,35 @@ roi_align_fwd_kernel(const RoiParams p, OutT* __restrict__ out, const int NBpad,
             for (int i = 0; i < PWC; ++i) {
                 if (pw0 + i < PW) {
 #pragma unroll
-                    for (int j = 0; j < CPL; ++j)
-                        tile[(lane + 32 * j) * NBpad + ph * PW + pw0 + i] = acc[i][j] / g.count;
+                    for (int j = 0; j < CPL; ++j) {
+                        float v = acc[i][j];
+                        if (icount != 1) v = (pow2 || !EXACT) ? v * rcount : v / g.count;
+                        tile[(lane + 32 * j) * NB + ph * PW + pw0 + i] = from_f32<OutT>(v);
+                    }
                 }
             }
         }
     }
-    __syncthreads();
 
-    // The CTA's output region out[k, c0 : c0+cc, :, :] is contiguous: stream it out coalesced.
-    const int NB = PH * PW;
+    // The CTA's output region out[k, c0 : c0+cc, :, :] is contiguous: hand it to the TMA as 1-D bulk
+    // stores (no per-element store instructions); fall back to a coalesced copy when unaligned.
     const int cc = min(32 * CPL, C - c0);
-    const int total = cc * NB;
+    const uint32_t bytes = (uint32_t)cc * NB * sizeof(OutT);
     OutT* __restrict__ obase = out + ((size_t)k * C + c0) * NB;
-    const int step = blockDim.x;
-    const int dc = step / NB, db = step - dc * NB;
-    int c = threadIdx.x / NB, b = threadIdx.x - c * NB;
-    for (int e = threadIdx.x; e < total; e += step) {
-        obase[e] = from_f32<OutT>(tile[c * NBpad + b]);
-        c += dc;
-        b += db;
-        if (b >= NB) { b -= NB; ++c; }
+    if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15u) == 0) {
+        bulk_store_g2s_fence();
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            const uint32_t piece = ((bytes / 4 + 15u) / 16u) * 16u;
+            const uint32_t off = piece * threadIdx.x;
+            if (off < bytes) {
+                bulk_store(reinterpret_cast<char*>(obase) + off, smem_raw + off, min(piece, bytes - off));
+                bulk_store_commit_wait();
+            }
+        }
+    } else {
+        __syncthreads();
+        for (int e = threadIdx.x; e < cc * NB; e += blockDim.x) obase[e] = tile[e];
     }
 }
 
@@ -193,37 +288,57 @@ roi_align_fwd_kernel(const RoiParams p, OutT* __restrict__ out, const int NBpad,
 // backward
 // ------------------------------------------------------------------------------------------------
 template <typename GT, int PWC, int CPL>
-__global__ void __launch_bounds__(512)
-roi_align_bwd_kernel(const RoiParams p, const GT* __restrict__ grad_out, const int NBpad, const int chunks) {
-    extern __shared__ float tile[];
+__global__ void __launch_bounds__(256, (CPL >= 4 ? 2 : 3))
+roi_align_bwd_kernel(const RoiParams p, const GT* __restrict__ grad_out, const int chunks) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ Tap xs[kTapCap], ys[kTapCap];
+    __shared__ __align__(8) uint64_t mbar;
+    const GT* tile = reinterpret_cast<const GT*>(smem_raw);  // [32*CPL][PH*PW]
     const int k = blockIdx.x / chunks;
     const int c0 = (blockIdx.x - k * chunks) * (32 * CPL);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
     const coin_level_t L = p.lv[lvl];
-    const int H = L.H, W = L.W, C = p.C, PH = p.PH, PW = p.PW;
+    const int H = L.H, W = L.W, C = p.C, PH = p.PH, PW = p.PW, NB = PH * PW;
+    const int cc = min(32 * CPL, C - c0);
+    const uint32_t bytes = (uint32_t)cc * NB * sizeof(GT);
+    const GT* __restrict__ ibase = grad_out + ((size_t)k * C + c0) * NB;
+    const bool bulk = (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(ibase) & 15u) == 0;
+
+    // stage grad_out[k, c0 : c0+cc, :, :] (contiguous) into shared memory, asynchronously
+    if (bulk) {
+        if (threadIdx.x == 0) mbar_init(&mbar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&mbar, bytes);
+            const uint32_t piece = ((bytes / 4 + 15u) / 16u) * 16u;
+            for (uint32_t off = 0; off < bytes; off += piece)
+                bulk_load(smem_raw + off, reinterpret_cast<const char*>(ibase) + off, min(piece, bytes - off), &mbar);
+        }
+    } else {
+        GT* wtile = reinterpret_cast<GT*>(smem_raw);
+        for (int e = threadIdx.x; e < cc * NB; e += blockDim.x) wtile[e] = ibase[e];
+    }
+
     const RoiGeom g = roi_geometry(p.rois + 5 * (size_t)k, L.spatial_scale, PH, PW, p.sampling_ratio, p.aligned);
     float* __restrict__ gbase = const_cast<float*>(L.feat_nhwc) + (size_t)g.batch * H * W * C + c0 + lane;
     bool chv[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) chv[j] = (c0 + lane + 32 * j) < C;
-
-    {   // stage grad_out[k, c0 : c0+cc, :, :] (contiguous) into the padded tile
-        const int NB = PH * PW;
-        const int cc = min(32 * CPL, C - c0);
-        const int total = cc * NB;
-        const GT* __restrict__ ibase = grad_out + ((size_t)k * C + c0) * NB;
-        const int step = blockDim.x;
-        const int dc = step / NB, db = step - dc * NB;
-        int c = threadIdx.x / NB, b = threadIdx.x - c * NB;
-        for (int e = threadIdx.x; e < total; e += step) {
-            tile[c * NBpad + b] = to_f32(ibase[e]);
-            c += dc;
-            b += db;
-            if (b >= NB) { b -= NB; ++c; }
+    const bool tabx = PW * g.grid_w <= kTapCap, taby = PH * g.grid_h <= kTapCap;
+    if (tabx)
+        for (int s = threadIdx.x; s < PW * g.grid_w; s += blockDim.x) {
+            const int pw = s / g.grid_w;
+            xs[s] = make_tap(g.start_w, g.bin_w, pw, s - pw * g.grid_w, g.grid_w, W, C);
         }
-    }
+    if (taby)
+        for (int s = threadIdx.x; s < PH * g.grid_h; s += blockDim.x) {
+            const int ph = s / g.grid_h;
+            ys[s] = make_tap(g.start_h, g.bin_h, ph, s - ph * g.grid_h, g.grid_h, H, W * C);
+        }
     __syncthreads();
+    if (bulk) mbar_wait(&mbar, 0);
+    const float rcount = 1.0f / g.count;
 
     for (int ph = warp; ph < PH; ph += nwarps) {
         for (int pw0 = 0; pw0 < PW; pw0 += PWC) {
@@ -232,17 +347,14 @@ roi_align_bwd_kernel(const RoiParams p, const GT* __restrict__ grad_out, const i
             for (int i = 0; i < PWC; ++i)
 #pragma unroll
                 for (int j = 0; j < CPL; ++j)
-                    gbin[i][j] = (pw0 + i < PW && chv[j])
-                                     ? tile[(lane + 32 * j) * NBpad + ph * PW + pw0 + i] / g.count
-                                     : 0.0f;
+                    gbin[i][j] = (pw0 + i < PW && chv[j]) ? to_f32(tile[(lane + 32 * j) * NB + ph * PW + pw0 + i]) * rcount : 0.0f;
 
             for (int iy = 0; iy < g.grid_h; ++iy) {
-                const float y = g.start_h + (float)ph * g.bin_h + ((float)iy + 0.5f) * g.bin_h / (float)g.grid_h;
-                int y_lo, y_hi;
-                float ly, hy;
-                if (!axis_taps(y, H, y_lo, y_hi, ly, hy)) continue;
-                float* __restrict__ rowL = gbase + (size_t)y_lo * W * C;
-                float* __restrict__ rowH = gbase + (size_t)y_hi * W * C;
+                const Tap Y = taby ? ys[ph * g.grid_h + iy] : make_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H, W * C);
+                if (Y.lo < 0) continue;
+                float* __restrict__ rowL = gbase + Y.lo;
+                float* __restrict__ rowH = gbase + Y.hi;
+                const float ly = Y.l, hy = Y.h;
                 int col0 = -1, col1 = -1;
                 float aL0[CPL], aL1[CPL], aH0[CPL], aH1[CPL];
 #pragma unroll
@@ -252,8 +364,8 @@ roi_align_bwd_kernel(const RoiParams p, const GT* __restrict__ grad_out, const i
 #pragma unroll
                     for (int j = 0; j < CPL; ++j) {
                         if (chv[j]) {
-                            atomicAdd(rowL + (size_t)col * C + 32 * j, aL[j]);
-                            atomicAdd(rowH + (size_t)col * C + 32 * j, aH[j]);
+                            atomicAdd(rowL + col + 32 * j, aL[j]);
+                            atomicAdd(rowH + col + 32 * j, aH[j]);
                         }
                     }
                 };
@@ -262,12 +374,10 @@ roi_align_bwd_kernel(const RoiParams p, const GT* __restrict__ grad_out, const i
                     const int pw = pw0 + i;
                     if (pw >= PW) break;
                     for (int ix = 0; ix < g.grid_w; ++ix) {
-                        const float x = g.start_w + (float)pw * g.bin_w + ((float)ix + 0.5f) * g.bin_w / (float)g.grid_w;
-                        int x_lo, x_hi;
-                        float lx, hx;
-                        if (!axis_taps(x, W, x_lo, x_hi, lx, hx)) continue;
-                        if (x_lo != col0 || x_hi != col1) {
-                            if (col0 >= 0 && x_lo == col1 && col1 != col0) {
+                        const Tap X = tabx ? xs[pw * g.grid_w + ix] : make_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W, C);
+                        if (X.lo < 0) continue;
+                        if (X.lo != col0 || X.hi != col1) {
+                            if (col0 >= 0 && X.lo == col1 && col1 != col0) {
                                 flush(aL0, aH0, col0);
 #pragma unroll
                                 for (int j = 0; j < CPL; ++j) {
@@ -282,16 +392,16 @@ roi_align_bwd_kernel(const RoiParams p, const GT* __restrict__ grad_out, const i
 #pragma unroll
                                 for (int j = 0; j < CPL; ++j) aL0[j] = aL1[j] = aH0[j] = aH1[j] = 0.0f;
                             }
-                            col0 = x_lo;
-                            col1 = x_hi;
+                            col0 = X.lo;
+                            col1 = X.hi;
                         }
-                        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                        const float w1 = hy * X.h, w2 = hy * X.l, w3 = ly * X.h, w4 = ly * X.l;
 #pragma unroll
                         for (int j = 0; j < CPL; ++j) {
-                            aL0[j] += gbin[i][j] * w1;
-                            aL1[j] += gbin[i][j] * w2;
-                            aH0[j] += gbin[i][j] * w3;
-                            aH1[j] += gbin[i][j] * w4;
+                            aL0[j] = __fmaf_rn(gbin[i][j], w1, aL0[j]);
+                            aL1[j] = __fmaf_rn(gbin[i][j], w2, aL1[j]);
+                            aH0[j] = __fmaf_rn(gbin[i][j], w3, aH0[j]);
+                            aH1[j] = __fmaf_rn(gbin[i][j], w4, aH1[j]);
                         }
                     }
                 }
@@ -374,44 +484,47 @@ static int fill_params(RoiParams& p, const coin_level_t* levels, int nlevels, co
     return COIN_OK;
 }
 
-struct LaunchCfg { int cpl, pwc, threads, nbpad, chunks; size_t smem; };
+struct LaunchCfg { int cpl, pwc, threads, chunks, exact; size_t smem; };
 
-static int pick_cfg(LaunchCfg& cfg, int C, int PH, int PW, const char* env_prefix) {
+static int pick_cfg(LaunchCfg& cfg, int C, int PH, int PW, size_t elt, const char* env_prefix) {
     const int NB = PH * PW;
-    cfg.nbpad = NB | 1;
     cfg.pwc = (PW > 7) ? 14 : 7;
-    int cpl = (cfg.pwc == 14) ? 2 : 4;
+    int cpl = 4;
     char name[64];
     snprintf(name, sizeof name, "%s_CPL", env_prefix);
     cpl = env_int(name, cpl);
     snprintf(name, sizeof name, "%s_PWC", env_prefix);
     cfg.pwc = env_int(name, cfg.pwc);
     if (cfg.pwc != 7 && cfg.pwc != 14) cfg.pwc = 7;
-    if (cpl != 1 && cpl != 2 && cpl != 4) cpl = 2;
+    if (cpl != 1 && cpl != 2 && cpl != 4) cpl = 4;
     while (cpl > 1 && (32 * (cpl / 2) >= C)) cpl /= 2;  // narrow maps: do not waste lanes-by-channel slots
-    while (cpl > 1 && (size_t)32 * cpl * cfg.nbpad * sizeof(float) > 200 * 1024) cpl /= 2;
+    while (cpl > 1 && (size_t)32 * cpl * NB * elt > 100 * 1024) cpl /= 2;  // keep two CTAs per SM resident
     cfg.cpl = cpl;
-    cfg.smem = (size_t)32 * cpl * cfg.nbpad * sizeof(float);
-    if (cfg.smem > 227 * 1024)
-        return fail(COIN_ERR_UNSUPPORTED, "roi_align: output %dx%d needs %zu B of shared memory (> 227 KB)", PH, PW, cfg.smem);
-    cfg.threads = 32 * (PH < 16 ? PH : 16);
+    cfg.smem = align_up((size_t)32 * cpl * NB * elt, 128);
+    if (cfg.smem > 200 * 1024)
+        return fail(COIN_ERR_UNSUPPORTED, "roi_align: output %dx%d needs %zu B of shared memory per CTA", PH, PW, cfg.smem);
+    snprintf(name, sizeof name, "%s_ROWS", env_prefix);
+    const int rows_per_warp = std::max((int)ceil_div(PH, 8), env_int(name, PH > 7 ? 2 : 1));  // kernels allow <= 8 warps
+    const int warps = (int)ceil_div(PH, rows_per_warp);
+    cfg.threads = 32 * warps;
     cfg.chunks = (int)ceil_div(C, 32 * cpl);
+    cfg.exact = env_int("COIN_ROI_EXACT", 0);
     return COIN_OK;
 }
 
 template <typename OutT, int PWC, int CPL>
 static int launch_fwd(const RoiParams& p, OutT* out, const LaunchCfg& cfg, cudaStream_t s) {
-    auto kern = roi_align_fwd_kernel<OutT, PWC, CPL>;
-    if (cfg.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
-    kern<<<(unsigned)(p.K * cfg.chunks), cfg.threads, cfg.smem, s>>>(p, out, cfg.nbpad, cfg.chunks);
+    auto kern = cfg.exact ? roi_align_fwd_kernel<OutT, PWC, CPL, true> : roi_align_fwd_kernel<OutT, PWC, CPL, false>;
+    if (cfg.smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    kern<<<(unsigned)(p.K * cfg.chunks), cfg.threads, cfg.smem, s>>>(p, out, cfg.chunks);
     return check_launch("roi_align_fwd_kernel");
 }
 
 template <typename GT, int PWC, int CPL>
 static int launch_bwd(const RoiParams& p, const GT* go, const LaunchCfg& cfg, cudaStream_t s) {
     auto kern = roi_align_bwd_kernel<GT, PWC, CPL>;
-    if (cfg.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
-    kern<<<(unsigned)(p.K * cfg.chunks), cfg.threads, cfg.smem, s>>>(p, go, cfg.nbpad, cfg.chunks);
+    if (cfg.smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    kern<<<(unsigned)(p.K * cfg.chunks), cfg.threads, cfg.smem, s>>>(p, go, cfg.chunks);
     return check_launch("roi_align_bwd_kernel");
 }
 
@@ -440,7 +553,7 @@ extern "C" int coin_roi_align_fwd(const coin_level_t* levels_host, int nlevels, 
     if (K == 0) return COIN_OK;
     COIN_REQUIRE(out, "roi_align_fwd: out is null");
     LaunchCfg cfg;
-    if (int rc = pick_cfg(cfg, C, PH, PW, "COIN_ROI_FWD")) return rc;
+    if (int rc = pick_cfg(cfg, C, PH, PW, out_dtype == COIN_F32 ? 4 : 2, "COIN_ROI_FWD")) return rc;
     cudaStream_t s = as_stream(stream);
     if (out_dtype == COIN_F32) COIN_DISPATCH_ROI(launch_fwd, float, static_cast<float*>(out));
     COIN_DISPATCH_ROI(launch_fwd, __half, static_cast<__half*>(out));
@@ -455,7 +568,7 @@ extern "C" int coin_roi_align_bwd(const coin_level_t* grad_levels_host, int nlev
     if (K == 0) return COIN_OK;
     COIN_REQUIRE(grad_out, "roi_align_bwd: grad_out is null");
     LaunchCfg cfg;
-    if (int rc = pick_cfg(cfg, C, PH, PW, "COIN_ROI_BWD")) return rc;
+    if (int rc = pick_cfg(cfg, C, PH, PW, grad_dtype == COIN_F32 ? 4 : 2, "COIN_ROI_BWD")) return rc;
     cudaStream_t s = as_stream(stream);
     if (grad_dtype == COIN_F32) COIN_DISPATCH_ROI(launch_bwd, float, static_cast<const float*>(grad_out));
     COIN_DISPATCH_ROI(launch_bwd, __half, static_cast<const __half*>(grad_out));

@@ -60,6 +60,22 @@ def test_roi_align_foggy_shape(dev, pooled, dtype):
         assert torch.equal(out.cpu(), ref)  # fp32 accumulate + round-to-nearest-even, same as autocast
 
 
+def test_roi_align_default_fma_mode_within_tolerance(dev, monkeypatch):
+    monkeypatch.setenv("COIN_ROI_EXACT", "0")
+    g = synth.gen(34)
+    shape = synth.SHAPES["foggy_cpu"]
+    h, w = shape.feat_hw
+    x = torch.randn(2, 128, h, w, generator=g)
+    boxes = synth.random_boxes(g, 160, shape.height, shape.width)
+    rois = torch.cat((torch.randint(0, 2, (160, 1), generator=g).float(), boxes), dim=1)
+    for pooled in (7, 14):
+        out = coin_b200.ROIAlign(pooled, 1.0 / 16, 0, True)(x.to(dev), rois.to(dev))
+        ref = torchvision.ops.roi_align(x, rois, (pooled, pooled), 1.0 / 16, 0, True)
+        # every output is a convex combination of features: |error| is relative to max|feature|
+        close(out, ref, scale=float(x.abs().max()))
+        assert float((out.cpu() - ref).abs().max()) < 4e-6
+
+
 def test_roi_align_backward_foggy_shape(dev):
     g = synth.gen(32)
     shape = synth.SHAPES["foggy_cpu"]

@@ -39,11 +39,13 @@ def main():
         t = timeit(lambda: ops.to_nhwc_f32(x))
         print(f"nchw->nhwc: {t:.1f} us")
         go = torch.randn(k, c, pooled, pooled, device=dev)
-        for pwc, cpl in itertools.product((7, 14), (1, 2, 4)):
-            if pooled == 7 and pwc == 14:
+        for pwc, cpl, rows, exact in itertools.product((7, 14), (2, 4), (1, 2, 4), (0, 1)):
+            if pooled == 7 and (pwc == 14 or rows == 4):
                 continue
             os.environ["COIN_ROI_FWD_PWC"], os.environ["COIN_ROI_FWD_CPL"] = str(pwc), str(cpl)
             os.environ["COIN_ROI_BWD_PWC"], os.environ["COIN_ROI_BWD_CPL"] = str(pwc), str(cpl)
+            os.environ["COIN_ROI_FWD_ROWS"] = os.environ["COIN_ROI_BWD_ROWS"] = str(rows)
+            os.environ["COIN_ROI_EXACT"] = str(exact)
             tf = timeit(lambda: ops.roi_align_forward([nhwc], (1 / 16,), rois, None, (pooled, pooled), 0, True, torch.float32))
             buf = torch.zeros((n, h, w, c), device=dev)
             lv = ops._levels([buf], (1 / 16,))
@@ -51,7 +53,7 @@ def main():
             def bwd():
                 check(lib.coin_roi_align_bwd(lv, 1, ops._ptr(rois), ops._ptr(None), ops._ptr(go), 0, c, k, pooled, pooled, 0, 1, ops._stream()))
             tb = timeit(bwd)
-            print(f"pwc={pwc:2d} cpl={cpl}: fwd {tf:8.1f} us ({alg/tf/1e3:7.1f} GB/s)   bwd {tb:8.1f} us ({(out_bytes + 2*x.numel()*4)/tb/1e3:7.1f} GB/s)")
+            print(f"pwc={pwc:2d} cpl={cpl} rows={rows} exact={exact}: fwd {tf:8.1f} us ({alg/tf/1e3:7.1f} GB/s)   bwd {tb:8.1f} us ({(out_bytes + 2*x.numel()*4)/tb/1e3:7.1f} GB/s)")
         import torchvision
         tt = timeit(lambda: torchvision.ops.roi_align(x, rois, (pooled, pooled), 1 / 16, 0, True))
         print(f"torchvision CUDA roi_align fwd: {tt:.1f} us ({alg/tt/1e3:.1f} GB/s)")
