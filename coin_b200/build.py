@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcoinops.so")
-SOURCES = ["capi.cu", "roi_align.cu", "box_codec.cu", "iou_match.cu", "nms.cu", "fusion_nms.cu",
+SOURCES = ["capi.cu", "roi_align.cu", "roi_align_sep.cu", "box_codec.cu", "iou_match.cu", "nms.cu", "fusion_nms.cu",
            "det_postprocess.cu", "match_abc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -37,7 +37,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "coinops.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "roi_common.cuh"), os.path.join(HERE, "..", "include", "coinops.h")]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     env = dict(os.environ)

@@ -22,94 +22,9 @@
 //     (cp.async.bulk.global.shared::cta) - no per-element store instructions for the 1.2 GB output;
 //   * backward mirrors forward: the register window accumulates tap gradients and is flushed with one
 //     fp32 atomic per touched feature cell and channel instead of 4 x samples atomics per bin.
-#include "common.cuh"
+#include "roi_common.cuh"
 
 namespace coin {
-
-struct RoiParams {
-    coin_level_t lv[COIN_MAX_LEVELS];
-    const float* rois;
-    const int32_t* roi_level;
-    int C, K, PH, PW, sampling_ratio, aligned;
-};
-
-struct RoiGeom {
-    float start_w, start_h, bin_w, bin_h, count;
-    int grid_h, grid_w, batch;
-};
-
-// Same operation order as oracle/scalar_ref.c::roi_geometry (and the torchvision kernels).
-__device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ roi, float scale, int PH,
-                                                int PW, int sampling_ratio, int aligned) {
-    RoiGeom g;
-    g.batch = (int)__ldg(roi);
-    const float offset = aligned ? 0.5f : 0.0f;
-    g.start_w = __ldg(roi + 1) * scale - offset;
-    g.start_h = __ldg(roi + 2) * scale - offset;
-    const float end_w = __ldg(roi + 3) * scale - offset;
-    const float end_h = __ldg(roi + 4) * scale - offset;
-    float roi_w = end_w - g.start_w;
-    float roi_h = end_h - g.start_h;
-    if (!aligned) {
-        roi_w = fmaxf(roi_w, 1.0f);
-        roi_h = fmaxf(roi_h, 1.0f);
-    }
-    g.bin_h = roi_h / (float)PH;
-    g.bin_w = roi_w / (float)PW;
-    g.grid_h = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(roi_h / (float)PH);
-    g.grid_w = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(roi_w / (float)PW);
-    const int cnt = g.grid_h * g.grid_w;
-    g.count = (float)(cnt > 1 ? cnt : 1);
-    return g;
-}
-
-// One coordinate of a bilinear sample: returns false when the sample lies outside [-1, size].
-__device__ __forceinline__ bool axis_taps(float v, int size, int& lo, int& hi, float& l, float& h) {
-    if (v < -1.0f || v > (float)size) return false;
-    if (v <= 0.0f) v = 0.0f;
-    lo = (int)v;
-    if (lo >= size - 1) {
-        hi = lo = size - 1;
-        v = (float)lo;
-    } else {
-        hi = lo + 1;
-    }
-    l = v - (float)lo;
-    h = 1.0f - l;
-    return true;
-}
-
-template <typename T>
-__device__ __forceinline__ T from_f32(float v);
-template <>
-__device__ __forceinline__ float from_f32<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
-__device__ __forceinline__ float to_f32(float v) { return v; }
-__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
-
-// ------------------------------------------------------------------------------------------------
-// per-RoI sample tables (shared memory): the x taps depend only on (pw, ix), the y taps only on
-// (ph, iy); computing them once per CTA removes ~25 instructions from every sample of every warp.
-// ------------------------------------------------------------------------------------------------
-struct Tap {          // 16 bytes, read as one LDS.128 (broadcast: every lane reads the same entry)
-    int lo, hi;       // element offsets of the low / high cell (x*C or y*W*C); lo < 0: sample outside the map
-    float l, h;       // interpolation weights towards hi / lo
-};
-constexpr int kTapCap = 256;   // entries per axis; larger sampling grids compute taps on the fly
-
-__device__ __forceinline__ Tap make_tap(float start, float bin, int p, int i, int grid, int size, int stride) {
-    const float v = start + (float)p * bin + ((float)i + 0.5f) * bin / (float)grid;
-    Tap t;
-    int lo, hi;
-    if (!axis_taps(v, size, lo, hi, t.l, t.h)) {
-        t.lo = -1; t.hi = -1; t.l = 0.0f; t.h = 0.0f;
-        return t;
-    }
-    t.lo = lo * stride;
-    t.hi = hi * stride;
-    return t;
-}
 
 // ---- TMA bulk copies (shared <-> global, 1-D) ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -508,7 +423,7 @@ static int pick_cfg(LaunchCfg& cfg, int C, int PH, int PW, size_t elt, const cha
     const int warps = (int)ceil_div(PH, rows_per_warp);
     cfg.threads = 32 * warps;
     cfg.chunks = (int)ceil_div(C, 32 * cpl);
-    cfg.exact = env_int("COIN_ROI_EXACT", 0);
+    cfg.exact = env_int("COIN_ROI_EXACT", 0) == 1;
     return COIN_OK;
 }
 
@@ -552,6 +467,9 @@ extern "C" int coin_roi_align_fwd(const coin_level_t* levels_host, int nlevels, 
     COIN_REQUIRE(out_dtype == COIN_F32 || out_dtype == COIN_F16, "roi_align_fwd: bad out_dtype %d", out_dtype);
     if (K == 0) return COIN_OK;
     COIN_REQUIRE(out, "roi_align_fwd: out is null");
+    // COIN_ROI_EXACT: 0 (default) separable fast kernel; 1 bit-exact parity kernel; 2 the parity kernel's FMA variant
+    const int mode = env_int("COIN_ROI_EXACT", 0);
+    if (mode == 0) return launch_roi_align_fwd_sep(p, out, out_dtype, as_stream(stream));
     LaunchCfg cfg;
     if (int rc = pick_cfg(cfg, C, PH, PW, out_dtype == COIN_F32 ? 4 : 2, "COIN_ROI_FWD")) return rc;
     cudaStream_t s = as_stream(stream);

@@ -1,0 +1,353 @@
+// roi_align_sep.cu -- separable ROIAlign forward for sm_100a (the default, non-parity-mode kernel).
+//
+// Replaces torchvision::roi_align as reached from coin/modeling/roi_heads/clip_roi_heads.py:51-63,
+// 142-147,172-176 (ROIPooler -> ROIAlign). Same sample positions, bilinear weights, validity rule and
+// 1/count scaling as the torchvision kernel; the summation is re-associated (see below), so results
+// agree to ~1e-7 relative instead of bit for bit. COIN_ROI_EXACT=1 selects the bit-exact kernel of
+// roi_align.cu instead.
+//
+// ROIAlign is a separable linear map per RoI and channel:
+//     out[ph,pw] = 1/count * sum_{iy,ix} bilinear(F, y(ph,iy), x(pw,ix))
+//                = 1/count * sum_ix ( hx * T[ph][xlo] + lx * T[ph][xhi] ),
+//     T[ph][x]   = sum_iy ( hy * F[ylo][x] + ly * F[yhi][x] )            (valid samples only;
+// a sample is valid iff its y is valid and its x is valid, so validity factorises too).
+//
+// One warp owns a "unit" = a group of output rows x a chunk of output columns x a 32*CPL-channel slab:
+//   phase 1 (lane = channel): T for the unit's rows and feature columns, from fp32 NHWC global memory.
+//           Every load is a coalesced 128-byte line; the iterations over feature columns are
+//           independent, so a warp keeps 2*U*CPL loads in flight (the v2 kernel stalled on one
+//           dependent L2 round trip per sample). T goes to a per-warp shared-memory buffer with an odd
+//           pitch.
+//   phase 2 (lane = output bin): each lane holds the <= 4 column weights of its bin in registers and
+//           walks the channels: <= 4 conflict-free LDS + FMA per output, and the warp's store covers
+//           nrows*PW consecutive floats of out[k, c, :, :] -- coalesced without staging the output
+//           tile in shared memory.
+// Both phases are warp-local (no CTA barrier after the tap tables are built). A CTA loops over
+// several channel slabs of the same RoI so the tables are built once per 256 channels.
+#include <climits>
+
+#include "roi_common.cuh"
+
+namespace coin {
+
+constexpr int kSepTap = 128;     // tap-table entries per axis (PW*grid_w and PH*grid_h must fit)
+constexpr int kSepCells = 32;    // T cells (row x feature column) per unit
+constexpr int kSepChunks = 16;   // max column chunks per RoI
+constexpr int kSepU = 4;         // feature columns in flight per phase-1 iteration
+
+struct SepChunk { int pa, nb, ca, ncol; };  // bins [pa, pa+nb) need feature columns [ca, ca+ncol)
+
+struct XTap { int lo, hi; float l, h; };    // cell indices (not offsets); lo < 0: sample outside the map
+
+__device__ __forceinline__ XTap make_xtap(float start, float bin, int p, int i, int grid, int size) {
+    const float v = start + (float)p * bin + ((float)i + 0.5f) * bin / (float)grid;
+    XTap t;
+    if (!axis_taps(v, size, t.lo, t.hi, t.l, t.h)) { t.lo = -1; t.hi = -1; t.l = 0.0f; t.h = 0.0f; }
+    return t;
+}
+
+// CS: channel stride of the NHWC map in elements when known at compile time (0 = use p.C); PHT/PWT: the
+// output size when known at compile time (0 = use p.PH / p.PW). Compile-time strides turn the address
+// arithmetic of the two inner loops into immediate offsets.
+template <typename OutT, int CPL, int CS, int PHT, int PWT>
+__global__ void __launch_bounds__(256, 3)
+roi_align_fwd_sep_kernel(const RoiParams p, OutT* __restrict__ out, const int cgroups, const int slabs) {
+    constexpr int CC = 32 * CPL, P = CC + 1;
+    extern __shared__ float tsm[];                 // [nwarps][kSepCells][P]
+    __shared__ XTap xs[kSepTap];
+    __shared__ Tap ys[kSepTap];
+    __shared__ int blo[kSepTap], bhi[kSepTap];
+    __shared__ SepChunk chunks[kSepChunks];
+    __shared__ int s_nchunks, s_rows, s_mode;      // mode 0: separable, 1: direct, 2: all zero
+
+    const int k = blockIdx.x / cgroups;
+    const int cg0 = (blockIdx.x - k * cgroups) * (CC * slabs);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
+    const coin_level_t L = p.lv[lvl];
+    const int H = L.H, W = L.W;
+    const int C = CS ? CS : p.C, PH = PHT ? PHT : p.PH, PW = PWT ? PWT : p.PW, NB = PH * PW;
+    const RoiGeom g = roi_geometry(p.rois + 5 * (size_t)k, L.spatial_scale, PH, PW, p.sampling_ratio, p.aligned);
+    const float* __restrict__ fimg = L.feat_nhwc + (size_t)g.batch * H * W * C;
+    const float rcount = 1.0f / g.count;
+    const int nslab = min(slabs, (int)((C - cg0 + CC - 1) / CC));
+    OutT* __restrict__ oroi = out + (size_t)k * C * NB;
+
+    const bool empty = g.grid_h <= 0 || g.grid_w <= 0;
+    const bool tables = !empty && PW <= kSepTap && PH <= kSepTap && (long long)PW * g.grid_w <= kSepTap &&
+                        (long long)PH * g.grid_h <= kSepTap;
+    if (tables) {
+        for (int s = threadIdx.x; s < PW * g.grid_w; s += blockDim.x) {
+            const int pw = s / g.grid_w;
+            xs[s] = make_xtap(g.start_w, g.bin_w, pw, s - pw * g.grid_w, g.grid_w, W);
+        }
+        for (int s = threadIdx.x; s < PH * g.grid_h; s += blockDim.x) {
+            const int ph = s / g.grid_h;
+            ys[s] = make_tap(g.start_h, g.bin_h, ph, s - ph * g.grid_h, g.grid_h, H, W * C);
+        }
+    }
+    __syncthreads();
+    if (tables) {
+        for (int pw = threadIdx.x; pw < PW; pw += blockDim.x) {   // feature-column span of every bin
+            int lo = INT_MAX, hi = -1;
+            for (int ix = 0; ix < g.grid_w; ++ix) {
+                const XTap X = xs[pw * g.grid_w + ix];
+                if (X.lo >= 0) { lo = min(lo, X.lo); hi = max(hi, X.hi); }
+            }
+            blo[pw] = lo; bhi[pw] = hi;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int mode = empty ? 2 : (tables ? 0 : 1), n = 0, maxcol = 1, maxnb = 1;
+        bool any = false;
+        if (mode == 0) {
+            int pa = 0;
+            while (pa < PW) {          // greedy chunks: <= kSepCells columns and <= 32 bins each
+                int lo = INT_MAX, hi = -1, pb = pa;
+                while (pb < PW && pb - pa < 32) {
+                    const int nlo = min(lo, blo[pb]), nhi = max(hi, bhi[pb]);
+                    if (nhi >= 0 && nhi - nlo + 1 > kSepCells) break;
+                    lo = nlo; hi = nhi; ++pb;
+                }
+                if (pb == pa || n == kSepChunks) { mode = 1; break; }   // a single bin wider than the buffer
+                SepChunk c;
+                c.pa = pa; c.nb = pb - pa; c.ca = hi < 0 ? 0 : lo; c.ncol = hi < 0 ? 0 : hi - lo + 1;
+                chunks[n++] = c;
+                any |= hi >= 0;
+                maxcol = max(maxcol, c.ncol); maxnb = max(maxnb, c.nb);
+                pa = pb;
+            }
+            if (mode == 0 && !any) mode = 2;   // every x sample lies outside the map
+        }
+        s_mode = mode; s_nchunks = n;
+        s_rows = max(1, min(min(kSepCells / maxcol, 32 / maxnb), PH));
+    }
+    __syncthreads();
+    const int mode = s_mode;
+
+    if (mode == 2) {   // no sample inside the map: the RoI pools to zeros
+        for (int sl = 0; sl < nslab; ++sl) {
+            const int c0 = cg0 + sl * CC, cc = min(CC, C - c0);
+            OutT* o = oroi + (size_t)c0 * NB;
+            for (int e = threadIdx.x; e < cc * NB; e += blockDim.x) o[e] = from_f32<OutT>(0.0f);
+        }
+        return;
+    }
+    if (mode == 1) {   // exotic geometry (sampling grids beyond the tables): direct 4-tap evaluation
+        for (int sl = 0; sl < nslab; ++sl) {
+            const int c0 = cg0 + sl * CC;
+            for (int b = warp; b < NB; b += nwarps) {
+                const int ph = b / PW, pw = b - ph * PW;
+                float acc[CPL];
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) acc[j] = 0.0f;
+                for (int iy = 0; iy < g.grid_h; ++iy) {
+                    const Tap Y = make_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H, W * C);
+                    if (Y.lo < 0) continue;
+                    for (int ix = 0; ix < g.grid_w; ++ix) {
+                        const Tap X = make_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W, C);
+                        if (X.lo < 0) continue;
+                        const float w1 = Y.h * X.h, w2 = Y.h * X.l, w3 = Y.l * X.h, w4 = Y.l * X.l;
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) {
+                            const int c = c0 + lane + 32 * j;
+                            if (c < C) {
+                                const float* f = fimg + c;
+                                acc[j] += w1 * __ldg(f + Y.lo + X.lo) + w2 * __ldg(f + Y.lo + X.hi) +
+                                          w3 * __ldg(f + Y.hi + X.lo) + w4 * __ldg(f + Y.hi + X.hi);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    const int c = c0 + lane + 32 * j;
+                    if (c < C) oroi[(size_t)c * NB + b] = from_f32<OutT>(acc[j] * rcount);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- separable path ---------------------------------------------------------------------
+    const int nchunks = s_nchunks, rows = s_rows;
+    const int nrg = (PH + rows - 1) / rows, nunits = nrg * nchunks;
+    float* __restrict__ Tw = tsm + (size_t)warp * kSepCells * P;
+    const int gh = g.grid_h, gw = g.grid_w;
+
+    for (int item = warp; item < nunits * nslab; item += nwarps) {
+        const int sl = item / nunits, unit = item - sl * nunits;
+        const int rg = unit / nchunks;
+        const SepChunk ch = chunks[unit - rg * nchunks];
+        const int ph0 = rg * rows, nr = min(rows, PH - ph0);
+        const int c0 = cg0 + sl * CC, cc = min(CC, C - c0);
+        bool chv[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) chv[j] = lane + 32 * j < cc;
+        const float* __restrict__ fb = fimg + c0 + lane + (size_t)ch.ca * C;
+
+        // phase 1: T[row][col][channel] for the unit (lane = channel); kSepU independent columns per step
+        for (int r = 0; r < nr; ++r) {
+            const Tap* __restrict__ yt = ys + (ph0 + r) * gh;
+            float* __restrict__ trow = Tw + r * ch.ncol * P + lane;
+            for (int col0 = 0; col0 < ch.ncol; col0 += kSepU) {
+                float t[kSepU][CPL];
+                bool cv[kSepU];
+#pragma unroll
+                for (int u = 0; u < kSepU; ++u) {
+                    cv[u] = col0 + u < ch.ncol;
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) t[u][j] = 0.0f;
+                }
+                for (int iy = 0; iy < gh; ++iy) {
+                    const Tap Y = yt[iy];
+                    if (Y.lo < 0) continue;                       // warp-uniform
+                    const float* __restrict__ rl = fb + Y.lo + (size_t)col0 * C;
+                    const float* __restrict__ rh = fb + Y.hi + (size_t)col0 * C;
+                    float a[kSepU][CPL], b[kSepU][CPL];
+#pragma unroll
+                    for (int u = 0; u < kSepU; ++u)
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) {
+                            a[u][j] = (cv[u] && chv[j]) ? __ldg(rl + u * C + 32 * j) : 0.0f;
+                            b[u][j] = (cv[u] && chv[j]) ? __ldg(rh + u * C + 32 * j) : 0.0f;
+                        }
+#pragma unroll
+                    for (int u = 0; u < kSepU; ++u)
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j)
+                            t[u][j] = __fmaf_rn(Y.l, b[u][j], __fmaf_rn(Y.h, a[u][j], t[u][j]));
+                }
+#pragma unroll
+                for (int u = 0; u < kSepU; ++u)
+                    if (cv[u]) {
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) trow[(col0 + u) * P + 32 * j] = t[u][j];
+                    }
+            }
+        }
+        __syncwarp();
+
+        // phase 2: lane = output bin (row lr, column ch.pa + pwl) of the unit
+        const bool active = lane < nr * ch.nb;
+        const int lr = active ? lane / ch.nb : 0;
+        const int pwl = active ? lane - lr * ch.nb : 0;
+        float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
+        int first = -1, span = 0;
+        if (active) {
+            const XTap* xt = xs + (ch.pa + pwl) * gw;
+            for (int ix = 0; ix < gw; ++ix) {
+                const XTap X = xt[ix];
+                if (X.lo < 0) continue;
+                if (first < 0) first = X.lo;
+                const int d = X.lo - first, e = X.hi - first;
+                if (d < 0) span = 99;
+                span = max(span, e + 1);
+                w0 += (d == 0 ? X.h : 0.0f) + (e == 0 ? X.l : 0.0f);
+                w1 += (d == 1 ? X.h : 0.0f) + (e == 1 ? X.l : 0.0f);
+                w2 += (d == 2 ? X.h : 0.0f) + (e == 2 ? X.l : 0.0f);
+                w3 += (d == 3 ? X.h : 0.0f) + (e == 3 ? X.l : 0.0f);
+            }
+        }
+        const int maxspan = __reduce_max_sync(0xffffffffu, span);
+        const int cb = first < 0 ? 0 : first - ch.ca;            // first column of the bin inside the chunk
+        const float* __restrict__ tb = Tw + (lr * ch.ncol + cb) * P;
+        OutT* __restrict__ ob = oroi + (size_t)c0 * NB + (ph0 + lr) * PW + ch.pa + pwl;
+        if (maxspan <= 4) {
+            // column offsets clamped into the chunk; a zero weight never multiplies (0 * inf would be NaN)
+            const int lim = max(ch.ncol - 1 - cb, 0);
+            const float* __restrict__ t1 = tb + min(1, lim) * P;
+            const float* __restrict__ t2 = tb + min(2, lim) * P;
+            const float* __restrict__ t3 = tb + min(3, lim) * P;
+            w0 *= rcount; w1 *= rcount; w2 *= rcount; w3 *= rcount;
+            const bool u0 = w0 != 0.0f, u1 = w1 != 0.0f, u2 = w2 != 0.0f, u3 = w3 != 0.0f;
+            if (active) {
+                int c = 0;
+                if (maxspan <= 2) {
+                    for (; c + 8 <= cc; c += 8) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float acc = u0 ? w0 * tb[c + q] : 0.0f;
+                            if (u1) acc = __fmaf_rn(w1, t1[c + q], acc);
+                            ob[(size_t)(c + q) * NB] = from_f32<OutT>(acc);
+                        }
+                    }
+                } else {
+                    for (; c + 4 <= cc; c += 4) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float acc = u0 ? w0 * tb[c + q] : 0.0f;
+                            if (u1) acc = __fmaf_rn(w1, t1[c + q], acc);
+                            if (u2) acc = __fmaf_rn(w2, t2[c + q], acc);
+                            if (u3) acc = __fmaf_rn(w3, t3[c + q], acc);
+                            ob[(size_t)(c + q) * NB] = from_f32<OutT>(acc);
+                        }
+                    }
+                }
+                for (; c < cc; ++c) {
+                    float acc = u0 ? w0 * tb[c] : 0.0f;
+                    if (u1) acc = __fmaf_rn(w1, t1[c], acc);
+                    if (u2) acc = __fmaf_rn(w2, t2[c], acc);
+                    if (u3) acc = __fmaf_rn(w3, t3[c], acc);
+                    ob[(size_t)c * NB] = from_f32<OutT>(acc);
+                }
+            }
+        } else if (active) {   // wide bins (fixed sampling_ratio with large RoIs): per-sample evaluation
+            const XTap* xt = xs + (ch.pa + pwl) * gw;
+            const float* __restrict__ trow = Tw + (lr * ch.ncol - ch.ca) * P;
+            for (int c = 0; c < cc; ++c) {
+                float acc = 0.0f;
+                for (int ix = 0; ix < gw; ++ix) {
+                    const XTap X = xt[ix];
+                    if (X.lo >= 0) acc = __fmaf_rn(X.l, trow[X.hi * P + c], __fmaf_rn(X.h, trow[X.lo * P + c], acc));
+                }
+                ob[(size_t)c * NB] = from_f32<OutT>(acc * rcount);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <typename OutT, int CPL, int CS, int PHT, int PWT>
+static int launch_sep(const RoiParams& p, OutT* out, int warps, int slabs, cudaStream_t s) {
+    constexpr int CC = 32 * CPL;
+    auto kern = roi_align_fwd_sep_kernel<OutT, CPL, CS, PHT, PWT>;
+    const size_t smem = (size_t)warps * kSepCells * (CC + 1) * sizeof(float);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int cgroups = (int)ceil_div(p.C, CC * slabs);
+    kern<<<(unsigned)(p.K * cgroups), 32 * warps, smem, s>>>(p, out, cgroups, slabs);
+    return check_launch("roi_align_fwd_sep_kernel");
+}
+
+static int sep_env(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <typename OutT>
+static int dispatch_sep(const RoiParams& p, OutT* out, int cpl, int warps, int slabs, cudaStream_t s) {
+    if (cpl == 1) return launch_sep<OutT, 1, 0, 0, 0>(p, out, warps, slabs, s);
+    const bool spec = sep_env("COIN_ROI_SEP_GENERIC", 0) == 0;
+    if (spec && p.C == 1024 && p.PH == 14 && p.PW == 14) return launch_sep<OutT, 2, 1024, 14, 14>(p, out, warps, slabs, s);
+    if (spec && p.C == 1024 && p.PH == 7 && p.PW == 7) return launch_sep<OutT, 2, 1024, 7, 7>(p, out, warps, slabs, s);
+    if (spec && p.C == 256 && p.PH == 7 && p.PW == 7) return launch_sep<OutT, 2, 256, 7, 7>(p, out, warps, slabs, s);
+    return launch_sep<OutT, 2, 0, 0, 0>(p, out, warps, slabs, s);
+}
+
+int launch_roi_align_fwd_sep(const RoiParams& p, void* out, int out_dtype, cudaStream_t s) {
+    int cpl = sep_env("COIN_ROI_SEP_CPL", 2);
+    if (cpl != 1 && cpl != 2) cpl = 2;
+    if (p.C <= 32) cpl = 1;
+    const int cc = 32 * cpl;
+    // one warp per unit of the common case (two 14-bin rows per unit, or four 7-bin rows)
+    const int rows = std::max(1, std::min(32 / std::min(p.PW, 32), p.PH));
+    int warps = sep_env("COIN_ROI_SEP_WARPS", (int)std::min<int64_t>(8, std::max<int64_t>(ceil_div(p.PH, rows), 4)));
+    warps = std::max(1, std::min(warps, 8));
+    int slabs = sep_env("COIN_ROI_SEP_SLABS", 4);
+    slabs = std::max(1, std::min(slabs, (int)ceil_div(p.C, cc)));
+    if (out_dtype == COIN_F32) return dispatch_sep<float>(p, static_cast<float*>(out), cpl, warps, slabs, s);
+    return dispatch_sep<__half>(p, static_cast<__half*>(out), cpl, warps, slabs, s);
+}
+
+}  // namespace coin

@@ -76,6 +76,33 @@ def test_roi_align_default_fma_mode_within_tolerance(dev, monkeypatch):
         assert float((out.cpu() - ref).abs().max()) < 4e-6
 
 
+@pytest.mark.parametrize("c,ph,pw,sr,aligned", [(3, 7, 7, 0, True), (40, 14, 14, 0, True), (96, 5, 9, 0, True),
+                                                  (64, 7, 7, 2, True), (33, 14, 14, 0, False), (64, 3, 20, 4, True),
+                                                  (32, 1, 1, 0, True), (70, 14, 14, 1, True)])
+def test_roi_align_separable_kernel_cases(dev, monkeypatch, c, ph, pw, sr, aligned):
+    """The default (separable) forward kernel against torchvision CPU over geometry edge cases: channel
+    tails, non-square outputs, fixed sampling ratios (sample spacing > 1 cell), RoIs outside / larger
+    than / much smaller than the map, inverted RoIs, fp16 output."""
+    monkeypatch.setenv("COIN_ROI_EXACT", "0")
+    g = synth.gen(35 + c)
+    h, w = 37, 75
+    x = torch.randn(2, c, h, w, generator=g)
+    boxes = synth.random_boxes(g, 90, 600, 1200, lo=4.0, hi=1100.0, min_side=0.5)
+    extra = torch.tensor([[-100.0, -100.0, -50.0, -50.0], [0.0, 0.0, 1200.0, 600.0], [64.0, 64.0, 64.2, 64.1],
+                          [160.0, 128.0, 32.0, 16.0], [0.0, 0.0, 6400.0, 4800.0], [-300.0, 100.0, 500.0, 130.0],
+                          [1100.0, 500.0, 1500.0, 900.0], [5.0, 5.0, 5.0, 5.0], [1199.0, 0.0, 1200.0, 600.0]])
+    boxes = torch.cat((boxes, extra))
+    rois = torch.cat((torch.randint(0, 2, (boxes.shape[0], 1), generator=g).float(), boxes), dim=1)
+    ref = torchvision.ops.roi_align(x, rois, (ph, pw), 1.0 / 16, sr, aligned)
+    out = coin_b200.ROIAlign((ph, pw), 1.0 / 16, sr, aligned)(x.to(dev), rois.to(dev))
+    close(out, ref, scale=float(x.abs().max()))
+    assert float((out.cpu() - ref).abs().max()) < 4e-6
+    out16 = coin_b200.ROIAlign((ph, pw), 1.0 / 16, sr, aligned)(x.to(dev).half(), rois.to(dev))
+    ref16 = torchvision.ops.roi_align(x.half().float(), rois.half().float(), (ph, pw), 1.0 / 16, sr, aligned)
+    assert out16.dtype == torch.float16
+    assert float((out16.cpu().float() - ref16).abs().max()) < 4e-3
+
+
 def test_roi_align_backward_foggy_shape(dev):
     g = synth.gen(32)
     shape = synth.SHAPES["foggy_cpu"]
