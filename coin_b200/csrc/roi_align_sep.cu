@@ -33,7 +33,6 @@ namespace coin {
 constexpr int kSepTap = 128;     // tap-table entries per axis (PW*grid_w and PH*grid_h must fit)
 constexpr int kSepCells = 32;    // T cells (row x feature column) per unit
 constexpr int kSepChunks = 16;   // max column chunks per RoI
-constexpr int kSepU = 4;         // feature columns in flight per phase-1 iteration
 
 struct SepChunk { int pa, nb, ca, ncol; };  // bins [pa, pa+nb) need feature columns [ca, ca+ncol)
 
@@ -44,6 +43,83 @@ __device__ __forceinline__ XTap make_xtap(float start, float bin, int p, int i, 
     XTap t;
     if (!axis_taps(v, size, t.lo, t.hi, t.l, t.h)) { t.lo = -1; t.hi = -1; t.l = 0.0f; t.h = 0.0f; }
     return t;
+}
+
+// Phase 1 for one output row: T[col][channel] = sum_iy hy*F[ylo][col] + ly*F[yhi][col] for the columns
+// [0, ncol) of the chunk (fb already points at the chunk's first column and this lane's channel).
+// U columns are processed per step with all 2*U*CPL loads issued before the first use. FAST: full channel
+// slab and ncol >= U: the last step is shifted back to end at ncol (recomputing a few columns) so no
+// load needs a predicate.
+template <int U, int CPL, bool FAST>
+__device__ __forceinline__ void sep_phase1_row(const float* __restrict__ fb, const Tap* __restrict__ yt, const int gh,
+                                               const int ncol, const int C, const int cc, const int lane,
+                                               float* __restrict__ trow) {
+    constexpr int P = 32 * CPL + 1;
+    for (int col0 = 0; col0 < ncol; col0 += U) {
+        const int cs = FAST ? min(col0, ncol - U) : col0;
+        float t[U][CPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) t[u][j] = 0.0f;
+        for (int iy = 0; iy < gh; ++iy) {
+            const Tap Y = yt[iy];
+            if (Y.lo < 0) continue;                       // warp-uniform
+            const float* __restrict__ rl = fb + Y.lo + (size_t)cs * C;
+            const float* __restrict__ rh = fb + Y.hi + (size_t)cs * C;
+            float a[U][CPL], b[U][CPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    if (FAST) {
+                        a[u][j] = __ldg(rl + u * C + 32 * j);
+                        b[u][j] = __ldg(rh + u * C + 32 * j);
+                    } else {
+                        const bool ok = cs + u < ncol && lane + 32 * j < cc;
+                        a[u][j] = ok ? __ldg(rl + u * C + 32 * j) : 0.0f;
+                        b[u][j] = ok ? __ldg(rh + u * C + 32 * j) : 0.0f;
+                    }
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) t[u][j] = __fmaf_rn(Y.l, b[u][j], __fmaf_rn(Y.h, a[u][j], t[u][j]));
+        }
+        float* __restrict__ tw = trow + cs * P;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (FAST || cs + u < ncol) {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) tw[u * P + 32 * j] = t[u][j];
+            }
+    }
+}
+
+// Phase 2 inner loop: NT column taps per output, `n` channels starting at the lane's base pointers.
+template <typename OutT, int NT, int P>
+__device__ __forceinline__ void sep_phase2_loop(const float* __restrict__ tb, const int o1, const int o2, const int o3,
+                                                const float w0, const float w1, const float w2, const float w3,
+                                                OutT* __restrict__ ob, const int NB, const int n) {
+    constexpr int UN = NT <= 2 ? 8 : 4;
+    int c = 0;
+    for (; c + UN <= n; c += UN) {
+#pragma unroll
+        for (int q = 0; q < UN; ++q) {
+            float acc = w0 * tb[c + q];
+            acc = __fmaf_rn(w1, tb[o1 + c + q], acc);
+            if (NT >= 3) acc = __fmaf_rn(w2, tb[o2 + c + q], acc);
+            if (NT >= 4) acc = __fmaf_rn(w3, tb[o3 + c + q], acc);
+            ob[(size_t)(c + q) * NB] = from_f32<OutT>(acc);
+        }
+    }
+    for (; c < n; ++c) {
+        float acc = w0 * tb[c];
+        acc = __fmaf_rn(w1, tb[o1 + c], acc);
+        if (NT >= 3) acc = __fmaf_rn(w2, tb[o2 + c], acc);
+        if (NT >= 4) acc = __fmaf_rn(w3, tb[o3 + c], acc);
+        ob[(size_t)c * NB] = from_f32<OutT>(acc);
+    }
 }
 
 // CS: channel stride of the NHWC map in elements when known at compile time (0 = use p.C); PHT/PWT: the
@@ -76,52 +152,62 @@ roi_align_fwd_sep_kernel(const RoiParams p, OutT* __restrict__ out, const int cg
     const bool empty = g.grid_h <= 0 || g.grid_w <= 0;
     const bool tables = !empty && PW <= kSepTap && PH <= kSepTap && (long long)PW * g.grid_w <= kSepTap &&
                         (long long)PH * g.grid_h <= kSepTap;
-    if (tables) {
-        for (int s = threadIdx.x; s < PW * g.grid_w; s += blockDim.x) {
+    if (tables) {   // x taps from the low thread ids, y taps from the high ones: both tables fill concurrently
+        const int nx = PW * g.grid_w, ny = PH * g.grid_h;
+        for (int s = threadIdx.x; s < nx; s += blockDim.x) {
             const int pw = s / g.grid_w;
             xs[s] = make_xtap(g.start_w, g.bin_w, pw, s - pw * g.grid_w, g.grid_w, W);
         }
-        for (int s = threadIdx.x; s < PH * g.grid_h; s += blockDim.x) {
+        for (int s = blockDim.x - 1 - threadIdx.x; s < ny; s += blockDim.x) {
             const int ph = s / g.grid_h;
             ys[s] = make_tap(g.start_h, g.bin_h, ph, s - ph * g.grid_h, g.grid_h, H, W * C);
         }
     }
     __syncthreads();
-    if (tables) {
-        for (int pw = threadIdx.x; pw < PW; pw += blockDim.x) {   // feature-column span of every bin
-            int lo = INT_MAX, hi = -1;
-            for (int ix = 0; ix < g.grid_w; ++ix) {
-                const XTap X = xs[pw * g.grid_w + ix];
-                if (X.lo >= 0) { lo = min(lo, X.lo); hi = max(hi, X.hi); }
-            }
-            blo[pw] = lo; bhi[pw] = hi;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {   // chunk list: warp 0 finds every bin's feature-column span; one chunk when the row fits
         int mode = empty ? 2 : (tables ? 0 : 1), n = 0, maxcol = 1, maxnb = 1;
-        bool any = false;
         if (mode == 0) {
-            int pa = 0;
-            while (pa < PW) {          // greedy chunks: <= kSepCells columns and <= 32 bins each
-                int lo = INT_MAX, hi = -1, pb = pa;
-                while (pb < PW && pb - pa < 32) {
-                    const int nlo = min(lo, blo[pb]), nhi = max(hi, bhi[pb]);
-                    if (nhi >= 0 && nhi - nlo + 1 > kSepCells) break;
-                    lo = nlo; hi = nhi; ++pb;
+            int glo = INT_MAX, ghi = -1;
+            for (int pw = lane; pw < PW; pw += 32) {
+                int lo = INT_MAX, hi = -1;
+                for (int ix = 0; ix < g.grid_w; ++ix) {
+                    const XTap X = xs[pw * g.grid_w + ix];
+                    if (X.lo >= 0) { lo = min(lo, X.lo); hi = max(hi, X.hi); }
                 }
-                if (pb == pa || n == kSepChunks) { mode = 1; break; }   // a single bin wider than the buffer
-                SepChunk c;
-                c.pa = pa; c.nb = pb - pa; c.ca = hi < 0 ? 0 : lo; c.ncol = hi < 0 ? 0 : hi - lo + 1;
-                chunks[n++] = c;
-                any |= hi >= 0;
-                maxcol = max(maxcol, c.ncol); maxnb = max(maxnb, c.nb);
-                pa = pb;
+                blo[pw] = lo; bhi[pw] = hi;
+                glo = min(glo, lo); ghi = max(ghi, hi);
             }
-            if (mode == 0 && !any) mode = 2;   // every x sample lies outside the map
+            glo = __reduce_min_sync(0xffffffffu, glo);
+            ghi = __reduce_max_sync(0xffffffffu, ghi);
+            __syncwarp();
+            if (ghi < 0) {
+                mode = 2;                                   // every x sample lies outside the map
+            } else if (PW <= 32 && ghi - glo + 1 <= kSepCells) {
+                n = 1; maxcol = ghi - glo + 1; maxnb = PW;
+                if (lane == 0) { SepChunk c; c.pa = 0; c.nb = PW; c.ca = glo; c.ncol = maxcol; chunks[0] = c; }
+            } else {                                        // greedy chunks: <= kSepCells columns, <= 32 bins each
+                int pa = 0;                                 // (computed redundantly by every lane of warp 0)
+                while (pa < PW) {
+                    int lo = INT_MAX, hi = -1, pb = pa;
+                    while (pb < PW && pb - pa < 32) {
+                        const int nlo = min(lo, blo[pb]), nhi = max(hi, bhi[pb]);
+                        if (nhi >= 0 && nhi - nlo + 1 > kSepCells) break;
+                        lo = nlo; hi = nhi; ++pb;
+                    }
+                    if (pb == pa || n == kSepChunks) { mode = 1; break; }   // a single bin wider than the buffer
+                    SepChunk c;
+                    c.pa = pa; c.nb = pb - pa; c.ca = hi < 0 ? 0 : lo; c.ncol = hi < 0 ? 0 : hi - lo + 1;
+                    if (lane == 0) chunks[n] = c;
+                    ++n;
+                    maxcol = max(maxcol, c.ncol); maxnb = max(maxnb, c.nb);
+                    pa = pb;
+                }
+            }
         }
-        s_mode = mode; s_nchunks = n;
-        s_rows = max(1, min(min(kSepCells / maxcol, 32 / maxnb), PH));
+        if (lane == 0) {
+            s_mode = mode; s_nchunks = n;
+            s_rows = max(1, min(min(kSepCells / maxcol, 32 / maxnb), PH));
+        }
     }
     __syncthreads();
     const int mode = s_mode;
@@ -182,57 +268,27 @@ roi_align_fwd_sep_kernel(const RoiParams p, OutT* __restrict__ out, const int cg
         const SepChunk ch = chunks[unit - rg * nchunks];
         const int ph0 = rg * rows, nr = min(rows, PH - ph0);
         const int c0 = cg0 + sl * CC, cc = min(CC, C - c0);
-        bool chv[CPL];
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) chv[j] = lane + 32 * j < cc;
         const float* __restrict__ fb = fimg + c0 + lane + (size_t)ch.ca * C;
 
-        // phase 1: T[row][col][channel] for the unit (lane = channel); kSepU independent columns per step
+        // phase 1: T[row][col][channel] for the unit (lane = channel)
         for (int r = 0; r < nr; ++r) {
             const Tap* __restrict__ yt = ys + (ph0 + r) * gh;
             float* __restrict__ trow = Tw + r * ch.ncol * P + lane;
-            for (int col0 = 0; col0 < ch.ncol; col0 += kSepU) {
-                float t[kSepU][CPL];
-                bool cv[kSepU];
-#pragma unroll
-                for (int u = 0; u < kSepU; ++u) {
-                    cv[u] = col0 + u < ch.ncol;
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) t[u][j] = 0.0f;
-                }
-                for (int iy = 0; iy < gh; ++iy) {
-                    const Tap Y = yt[iy];
-                    if (Y.lo < 0) continue;                       // warp-uniform
-                    const float* __restrict__ rl = fb + Y.lo + (size_t)col0 * C;
-                    const float* __restrict__ rh = fb + Y.hi + (size_t)col0 * C;
-                    float a[kSepU][CPL], b[kSepU][CPL];
-#pragma unroll
-                    for (int u = 0; u < kSepU; ++u)
-#pragma unroll
-                        for (int j = 0; j < CPL; ++j) {
-                            a[u][j] = (cv[u] && chv[j]) ? __ldg(rl + u * C + 32 * j) : 0.0f;
-                            b[u][j] = (cv[u] && chv[j]) ? __ldg(rh + u * C + 32 * j) : 0.0f;
-                        }
-#pragma unroll
-                    for (int u = 0; u < kSepU; ++u)
-#pragma unroll
-                        for (int j = 0; j < CPL; ++j)
-                            t[u][j] = __fmaf_rn(Y.l, b[u][j], __fmaf_rn(Y.h, a[u][j], t[u][j]));
-                }
-#pragma unroll
-                for (int u = 0; u < kSepU; ++u)
-                    if (cv[u]) {
-#pragma unroll
-                        for (int j = 0; j < CPL; ++j) trow[(col0 + u) * P + 32 * j] = t[u][j];
-                    }
-            }
+            if (cc == CC && ch.ncol >= 8) sep_phase1_row<8, CPL, true>(fb, yt, gh, ch.ncol, C, cc, lane, trow);
+            else if (cc == CC && ch.ncol >= 4) sep_phase1_row<4, CPL, true>(fb, yt, gh, ch.ncol, C, cc, lane, trow);
+            else sep_phase1_row<4, CPL, false>(fb, yt, gh, ch.ncol, C, cc, lane, trow);
         }
         __syncwarp();
 
-        // phase 2: lane = output bin (row lr, column ch.pa + pwl) of the unit
-        const bool active = lane < nr * ch.nb;
-        const int lr = active ? lane / ch.nb : 0;
-        const int pwl = active ? lane - lr * ch.nb : 0;
+        // phase 2: lane = (channel split, output bin). With <= 16 bins in the unit the two half-warps take
+        // the two halves of the channel slab, so wide RoIs (one row per unit) still use 28 lanes.
+        const int nact = nr * ch.nb;
+        const int nsplit = nact <= 16 ? 2 : 1;
+        const int split = nsplit == 2 ? lane >> 4 : 0;
+        const int idx = nsplit == 2 ? lane & 15 : lane;
+        const bool active = idx < nact;
+        const int lr = active ? idx / ch.nb : 0;
+        const int pwl = active ? idx - lr * ch.nb : 0;
         float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
         int first = -1, span = 0;
         if (active) {
@@ -252,51 +308,27 @@ roi_align_fwd_sep_kernel(const RoiParams p, OutT* __restrict__ out, const int cg
         }
         const int maxspan = __reduce_max_sync(0xffffffffu, span);
         const int cb = first < 0 ? 0 : first - ch.ca;            // first column of the bin inside the chunk
-        const float* __restrict__ tb = Tw + (lr * ch.ncol + cb) * P;
-        OutT* __restrict__ ob = oroi + (size_t)c0 * NB + (ph0 + lr) * PW + ch.pa + pwl;
+        const int half = (CC / 2) * split;                        // first channel of this lane's share
+        const int nch = nsplit == 2 ? max(0, min(cc - half, CC / 2)) : cc;
+        const float* __restrict__ tb = Tw + (lr * ch.ncol + cb) * P + half;
+        OutT* __restrict__ ob = oroi + (size_t)(c0 + half) * NB + (ph0 + lr) * PW + ch.pa + pwl;
         if (maxspan <= 4) {
-            // column offsets clamped into the chunk; a zero weight never multiplies (0 * inf would be NaN)
-            const int lim = max(ch.ncol - 1 - cb, 0);
-            const float* __restrict__ t1 = tb + min(1, lim) * P;
-            const float* __restrict__ t2 = tb + min(2, lim) * P;
-            const float* __restrict__ t3 = tb + min(3, lim) * P;
+            // Tap d of a lane whose bin spans fewer than d+1 columns has weight 0 and re-reads the bin's own
+            // last column, so a zero weight never meets a value the reference would not have touched.
+            const int last = max(span - 1, 0);
+            const int o1 = min(1, last) * P, o2 = min(2, last) * P, o3 = min(3, last) * P;
             w0 *= rcount; w1 *= rcount; w2 *= rcount; w3 *= rcount;
-            const bool u0 = w0 != 0.0f, u1 = w1 != 0.0f, u2 = w2 != 0.0f, u3 = w3 != 0.0f;
-            if (active) {
-                int c = 0;
-                if (maxspan <= 2) {
-                    for (; c + 8 <= cc; c += 8) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float acc = u0 ? w0 * tb[c + q] : 0.0f;
-                            if (u1) acc = __fmaf_rn(w1, t1[c + q], acc);
-                            ob[(size_t)(c + q) * NB] = from_f32<OutT>(acc);
-                        }
-                    }
-                } else {
-                    for (; c + 4 <= cc; c += 4) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float acc = u0 ? w0 * tb[c + q] : 0.0f;
-                            if (u1) acc = __fmaf_rn(w1, t1[c + q], acc);
-                            if (u2) acc = __fmaf_rn(w2, t2[c + q], acc);
-                            if (u3) acc = __fmaf_rn(w3, t3[c + q], acc);
-                            ob[(size_t)(c + q) * NB] = from_f32<OutT>(acc);
-                        }
-                    }
-                }
-                for (; c < cc; ++c) {
-                    float acc = u0 ? w0 * tb[c] : 0.0f;
-                    if (u1) acc = __fmaf_rn(w1, t1[c], acc);
-                    if (u2) acc = __fmaf_rn(w2, t2[c], acc);
-                    if (u3) acc = __fmaf_rn(w3, t3[c], acc);
-                    ob[(size_t)c * NB] = from_f32<OutT>(acc);
-                }
+            if (active && first >= 0) {
+                if (maxspan <= 2) sep_phase2_loop<OutT, 2, P>(tb, o1, o2, o3, w0, w1, w2, w3, ob, NB, nch);
+                else if (maxspan == 3) sep_phase2_loop<OutT, 3, P>(tb, o1, o2, o3, w0, w1, w2, w3, ob, NB, nch);
+                else sep_phase2_loop<OutT, 4, P>(tb, o1, o2, o3, w0, w1, w2, w3, ob, NB, nch);
+            } else if (active) {   // no valid x sample for this bin
+                for (int c = 0; c < nch; ++c) ob[(size_t)c * NB] = from_f32<OutT>(0.0f);
             }
         } else if (active) {   // wide bins (fixed sampling_ratio with large RoIs): per-sample evaluation
             const XTap* xt = xs + (ch.pa + pwl) * gw;
-            const float* __restrict__ trow = Tw + (lr * ch.ncol - ch.ca) * P;
-            for (int c = 0; c < cc; ++c) {
+            const float* __restrict__ trow = Tw + (lr * ch.ncol - ch.ca) * P + half;
+            for (int c = 0; c < nch; ++c) {
                 float acc = 0.0f;
                 for (int ix = 0; ix < gw; ++ix) {
                     const XTap X = xt[ix];
