@@ -374,9 +374,11 @@ int launch_roi_align_fwd_sep(const RoiParams& p, void* out, int out_dtype, cudaS
     const int cc = 32 * cpl;
     // one warp per unit of the common case (two 14-bin rows per unit, or four 7-bin rows)
     const int rows = std::max(1, std::min(32 / std::min(p.PW, 32), p.PH));
-    int warps = sep_env("COIN_ROI_SEP_WARPS", (int)std::min<int64_t>(8, std::max<int64_t>(ceil_div(p.PH, rows), 4)));
+    // small outputs (7x7): little work per unit, so more warps and fewer slabs per CTA (measured)
+    const bool small = p.PH * p.PW <= 64;
+    int warps = sep_env("COIN_ROI_SEP_WARPS", small ? 8 : (int)std::min<int64_t>(8, std::max<int64_t>(ceil_div(p.PH, rows), 4)));
     warps = std::max(1, std::min(warps, 8));
-    int slabs = sep_env("COIN_ROI_SEP_SLABS", 4);
+    int slabs = sep_env("COIN_ROI_SEP_SLABS", small ? 2 : 4);
     slabs = std::max(1, std::min(slabs, (int)ceil_div(p.C, cc)));
     if (out_dtype == COIN_F32) return dispatch_sep<float>(p, static_cast<float*>(out), cpl, warps, slabs, s);
     return dispatch_sep<__half>(p, static_cast<__half*>(out), cpl, warps, slabs, s);

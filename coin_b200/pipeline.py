@@ -65,6 +65,8 @@ class RoIPathStep:
         # w.r.t. the pooled features is the constant G, resident on the device like a weight.
         self.head_grad = torch.randn(shape.images * shape.rois, shape.channels, shape.pooled, shape.pooled,
                                      generator=g).to(device)
+        self._streams: List[torch.cuda.Stream] = []
+        self.overlap = True         # issue independent stages on side streams (False: everything on the caller's stream)
         self.kernel_events = None   # bench.py: {"fwd": [], "bwd": []} to time the two dominant kernels live
 
     # -- data movement -------------------------------------------------------------------------
@@ -93,83 +95,129 @@ class RoIPathStep:
         return sum(v.numel() * v.element_size() for v in pinned.values())
 
     # -- the step --------------------------------------------------------------------------------
+    def _side_streams(self, n: int) -> List[torch.cuda.Stream]:
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        return self._streams[:n]
+
     def run(self, d: Dict[str, torch.Tensor], backward: bool = True) -> Dict[str, object]:
+        """One step. The stages of different images (and the two NMS chains of one image) are independent,
+        so they are issued on separate CUDA streams: the latency-bound single-CTA kernels of one image
+        overlap those of the others, and the HBM-bound ROIAlign forward/backward (which depend only on the
+        feature map and the sampled RoIs) overlap the whole teacher/matching branch. Every side stream is
+        joined into the caller's stream before run() returns."""
         sh, dev = self.shape, self.device
         n_img = sh.images
         img_size = (sh.height, sh.width)
-        k1 = sh.classes + 1
-        nhwc = ops.to_nhwc_f32(d["features"])
+        main = torch.cuda.current_stream()
+        if not self.overlap:
+            return self._run(d, backward, [main] * (3 * n_img + 1))
+        side = self._side_streams(3 * n_img + 1)
+        start = main.record_event()
+        for st in side:
+            st.wait_event(start)
+        out = self._run(d, backward, side)
+        for st in side:
+            main.wait_stream(st)
+        return out
 
-        # ---- teacher branch, launches for every image first (no host sync inside the loop)
-        dets, cloud_boxes, rpn = [], [], []
+    def _run(self, d, backward, streams) -> Dict[str, object]:
+        sh, dev = self.shape, self.device
+        n_img = sh.images
+        img_size = (sh.height, sh.width)
+        main = torch.cuda.current_stream()
+        s_roi, s_img = streams[0], streams[1:]
+        scale = (1.0 / sh.stride,)
+        size = (sh.pooled, sh.pooled)
+        ev = self.kernel_events
+        out: Dict[str, object] = {"dets": [], "abc": [], "roi_labels": [], "rpn_labels": [], "rpn_keep": []}
+
+        # ---- ROIAlign forward (S4) and backward (S5) over the sampled RoIs: own stream, needs only the map
+        with torch.cuda.stream(s_roi):
+            nhwc = ops.to_nhwc_f32(d["features"])
+            rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
+                              for i in range(n_img)])
+            out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
+                                                  events=ev["fwd"] if ev else None)
+            if backward:
+                n, c, h, w = d["features"].shape
+                out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
+                                                              0, True, [torch.float32],
+                                                              events=ev["bwd"] if ev else None)[0]
+
+        # ---- teacher branch and RPN NMS: one stream per image and chain, no host sync inside the loop
+        dets, cloud_boxes, rpn = [None] * n_img, [None] * n_img, [None] * n_img
         for i in range(n_img):
-            dec = ops.apply_deltas(d[f"{i}.teacher_deltas"], d[f"{i}.teacher_rois"], self.BBOX_WEIGHTS,
-                                   clip_to=img_size)                                                    # T1
-            dets.append(ops.det_postprocess(dec, d[f"{i}.teacher_probs"], img_size, self.SCORE_THRESH,
-                                            self.NMS_THRESH, self.TOPK, sync=False))                      # T2
-            cloud_boxes.append(ops.boxes_scale_flip(d[f"{i}.cloud.gt_boxes"], sh.width / (sh.width * ORIG_SCALE),
-                                                    sh.height / (sh.height * ORIG_SCALE), "no", img_size))  # T3
-            rpn.append(ops.batched_nms(d[f"{i}.rpn_boxes"], d[f"{i}.rpn_scores"], None, self.RPN_NMS_THRESH,
-                                       "plain", sh.rpn_post_nms, sync=False))                             # S1
+            with torch.cuda.stream(s_img[i]):
+                dec = ops.apply_deltas(d[f"{i}.teacher_deltas"], d[f"{i}.teacher_rois"], self.BBOX_WEIGHTS,
+                                       clip_to=img_size)                                                    # T1
+                dets[i] = ops.det_postprocess(dec, d[f"{i}.teacher_probs"], img_size, self.SCORE_THRESH,
+                                              self.NMS_THRESH, self.TOPK, sync=False)                       # T2
+                cloud_boxes[i] = ops.boxes_scale_flip(d[f"{i}.cloud.gt_boxes"], sh.width / (sh.width * ORIG_SCALE),
+                                                      sh.height / (sh.height * ORIG_SCALE), "no", img_size)  # T3
+            with torch.cuda.stream(s_img[n_img + i]):
+                rpn[i] = ops.batched_nms(d[f"{i}.rpn_boxes"], d[f"{i}.rpn_scores"], None, self.RPN_NMS_THRESH,
+                                         "plain", sh.rpn_post_nms, sync=False)                              # S1
+        for st in s_img[: 2 * n_img]:
+            main.wait_stream(st)
         counts1 = torch.stack([x[5] for x in dets] + [x[1] for x in rpn]).view(-1).cpu()                 # sync 1
         n_det = counts1[:n_img].tolist()
         n_rpn = counts1[n_img:].tolist()
 
-        # ---- knowledge separation (T4): two launches per image
+        # ---- knowledge separation (T4): one launch per image and tag, each on its own stream
         raws = []
         for i in range(n_img):
             b, s, p, c, _, _ = dets[i]
             nd = n_det[i]
-            for tag in ("RCNN", "RPN"):
-                raws.append(ops.match_abc(cloud_boxes[i], d[f"{i}.cloud.gt_classes"], d[f"{i}.cloud.scores"],
-                                          b[:nd], c[:nd], s[:nd], tag, self.MATCH_THRESH, self.w_a, sync=False))
+            for t, tag in enumerate(("RCNN", "RPN")):
+                st = s_img[2 * i + t]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    raws.append(ops.match_abc(cloud_boxes[i], d[f"{i}.cloud.gt_classes"], d[f"{i}.cloud.scores"],
+                                              b[:nd], c[:nd], s[:nd], tag, self.MATCH_THRESH, self.w_a, sync=False))
+        for st in s_img[: 2 * n_img]:
+            main.wait_stream(st)
         counts2 = torch.stack([r["counts"] for r in raws]).cpu().tolist()                                 # sync 2
 
-        out: Dict[str, object] = {"dets": [], "abc": [], "roi_labels": [], "rpn_labels": [], "rpn_keep": []}
-        c_rois = []
+        c_rois = [None] * n_img
         for i in range(n_img):
-            b, s, p, c, roi_idx, _ = dets[i]
-            nd = n_det[i]
-            out["dets"].append({"pred_boxes": b[:nd], "scores": s[:nd], "probs": p[:nd], "pred_classes": c[:nd],
-                                "roi_index": roi_idx[:nd]})
-            out["rpn_keep"].append(rpn[i][0][: n_rpn[i]])
-            cloud = {"gt_boxes": cloud_boxes[i], "gt_classes": d[f"{i}.cloud.gt_classes"],
-                     "scores": d[f"{i}.cloud.scores"], "probs": d[f"{i}.cloud.probs"]}
-            clip = {"gt_boxes": b[:nd], "gt_classes": c[:nd], "scores": s[:nd], "probs": p[:nd]}
-            per_tag = {}
-            for t, tag in enumerate(("RCNN", "RPN")):
-                r = ops.match_abc_narrow(raws[2 * i + t], counts2[2 * i + t])
-                per_tag[tag] = self._pack(r, cloud, clip, tag)
-            out["abc"].append(per_tag)
+            st = s_img[2 * n_img + i]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                b, s, p, c, roi_idx, _ = dets[i]
+                nd = n_det[i]
+                out["dets"].append({"pred_boxes": b[:nd], "scores": s[:nd], "probs": p[:nd], "pred_classes": c[:nd],
+                                    "roi_index": roi_idx[:nd]})
+                out["rpn_keep"].append(rpn[i][0][: n_rpn[i]])
+                cloud = {"gt_boxes": cloud_boxes[i], "gt_classes": d[f"{i}.cloud.gt_classes"],
+                         "scores": d[f"{i}.cloud.scores"], "probs": d[f"{i}.cloud.probs"]}
+                clip = {"gt_boxes": b[:nd], "gt_classes": c[:nd], "scores": s[:nd], "probs": p[:nd]}
+                per_tag = {}
+                for t, tag in enumerate(("RCNN", "RPN")):
+                    r = ops.match_abc_narrow(raws[2 * i + t], counts2[2 * i + t])
+                    per_tag[tag] = self._pack(r, cloud, clip, tag)
+                out["abc"].append(per_tag)
 
-            a, bb, cc = per_tag["RCNN"]
-            gt = torch.cat((a["gt_boxes"], bb["gt_boxes"], cc["gt_boxes"]))
-            props = torch.cat((d[f"{i}.proposals"], a["gt_boxes"], bb["gt_boxes"]))   # add_ground_truth_to_proposals
-            idx, lab = ops.iou_match(gt, props, [0.5], [0, 1], False)                                      # S3
-            la, lb, lc = a["gt_boxes"].shape[0], bb["gt_boxes"].shape[0], cc["gt_boxes"].shape[0]
-            ops.relabel_roi_(idx, lab, la + lb, la + lb + lc)
-            out["roi_labels"].append((idx, lab))
+                a, bb, cc = per_tag["RCNN"]
+                gt = torch.cat((a["gt_boxes"], bb["gt_boxes"], cc["gt_boxes"]))
+                props = torch.cat((d[f"{i}.proposals"], a["gt_boxes"], bb["gt_boxes"]))   # add_ground_truth_to_proposals
+                idx, lab = ops.iou_match(gt, props, [0.5], [0, 1], False)                                  # S3
+                la, lb, lc = a["gt_boxes"].shape[0], bb["gt_boxes"].shape[0], cc["gt_boxes"].shape[0]
+                ops.relabel_roi_(idx, lab, la + lb, la + lb + lc)
+                out["roi_labels"].append((idx, lab))
 
-            a2, _, c2 = per_tag["RPN"]
-            gt2 = torch.cat((a2["gt_boxes"], c2["gt_boxes"]))
-            idx2, lab2 = ops.iou_match(gt2, self.anchors, [0.3, 0.7], [0, -1, 1], True)                    # S2
-            out["rpn_labels"].append(ops.relabel_rpn_(idx2, lab2, a2["gt_boxes"].shape[0], c2["gt_boxes"].shape[0]))
-            cb = cc["gt_boxes"]
-            c_rois.append(torch.cat((torch.full((cb.shape[0], 1), float(i), device=dev), cb), dim=1))
+                a2, _, c2 = per_tag["RPN"]
+                gt2 = torch.cat((a2["gt_boxes"], c2["gt_boxes"]))
+                idx2, lab2 = ops.iou_match(gt2, self.anchors, [0.3, 0.7], [0, -1, 1], True)                # S2
+                out["rpn_labels"].append(ops.relabel_rpn_(idx2, lab2, a2["gt_boxes"].shape[0], c2["gt_boxes"].shape[0]))
+                cb = cc["gt_boxes"]
+                c_rois[i] = torch.cat((torch.full((cb.shape[0], 1), float(i), device=dev), cb), dim=1)
 
-        # ---- ROIAlign forward (S4) and backward (S5)
-        rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
-                          for i in range(n_img)])
-        scale = (1.0 / sh.stride,)
-        size = (sh.pooled, sh.pooled)
-        ev = self.kernel_events
-        out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
-                                              events=ev["fwd"] if ev else None)
-        out["pooled_c"] = ops.roi_align_forward([nhwc], scale, torch.cat(c_rois), None, size, 0, True, torch.float32)
-        if backward:
-            n, c, h, w = d["features"].shape
-            out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size, 0,
-                                                          True, [torch.float32], events=ev["bwd"] if ev else None)[0]
+        # ---- ROIAlign forward on the private (C) boxes, behind the big forward/backward on the RoI stream
+        for st in s_img[2 * n_img:]:
+            s_roi.wait_stream(st)
+        with torch.cuda.stream(s_roi):
+            out["pooled_c"] = ops.roi_align_forward([nhwc], scale, torch.cat(c_rois), None, size, 0, True, torch.float32)
         out["summary"] = {"dets": n_det, "rpn_keep": n_rpn, "abc": [c2[:3] for c2 in counts2]}
         return out
 
