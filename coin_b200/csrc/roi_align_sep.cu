@@ -352,6 +352,229 @@ static int launch_sep(const RoiParams& p, OutT* out, int warps, int slabs, cudaS
     return check_launch("roi_align_fwd_sep_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward: the adjoint of the separable forward
+//   grad_in[y][x][c] += 1/count * sum_{ph,pw} Wy[ph][y] * Wx[pw][x] * g[c][ph][pw]
+// One warp owns a unit = R (<= 2) output rows x all PW bins x a 32*CPL-channel slab:
+//   stage   (lane = bin): the unit's grad_out values, coalesced from [K,C,PH,PW], into a per-warp shared
+//           tile G[bin][channel] with an odd pitch (conflict-free both ways);
+//   walk    (lane = channel): one pass along x for both rows at once (they share the x taps) with a
+//           two-column register window accumulating sum_pw Wx * g;
+//   flush   when a column leaves the window: for every feature row y touched by the unit (the y taps of
+//           its rows merged into a table once per CTA), ONE fp32 RED of Wy-weighted window values -
+//           rows of the unit that share a feature row share the atomic.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdYEnt = 16;    // merged y-table entries per unit
+constexpr int kBwdUnits = 16;   // units per RoI handled by the tables (PH <= 32 with two rows per unit)
+
+struct YEnt { int off; float w0, w1; int pad; };   // feature-row offset (y*W*C), weights of unit rows 0 and 1
+
+template <typename GT, int CPL, int CS>
+__global__ void __launch_bounds__(224, 3)
+roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int cgroups, const int slabs) {
+    constexpr int CC = 32 * CPL, P = CC + 1;
+    extern __shared__ float gsm[];                 // [nwarps][32][P]
+    __shared__ XTap xs[kSepTap];
+    __shared__ Tap ys[kSepTap];
+    __shared__ YEnt ytab[kBwdUnits][kBwdYEnt];
+    __shared__ int ycnt[kBwdUnits];
+    __shared__ int s_mode;                         // 0: separable, 1: direct
+
+    const int k = blockIdx.x / cgroups;
+    const int cg0 = (blockIdx.x - k * cgroups) * (CC * slabs);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
+    const coin_level_t L = p.lv[lvl];
+    const int H = L.H, W = L.W;
+    const int C = CS ? CS : p.C, PH = p.PH, PW = p.PW, NB = PH * PW;
+    const RoiGeom g = roi_geometry(p.rois + 5 * (size_t)k, L.spatial_scale, PH, PW, p.sampling_ratio, p.aligned);
+    float* __restrict__ gimg = const_cast<float*>(L.feat_nhwc) + (size_t)g.batch * H * W * C;
+    const float rcount = 1.0f / g.count;
+    const int nslab = min(slabs, (int)((C - cg0 + CC - 1) / CC));
+    const GT* __restrict__ groi = go + (size_t)k * C * NB;
+    if (g.grid_h <= 0 || g.grid_w <= 0) return;    // no samples: no gradient
+    const int gh = g.grid_h, gw = g.grid_w;
+    const int R = PW <= 16 && PH >= 2 ? 2 : 1;     // rows per unit (R*PW bins <= 32 lanes)
+    const int nunits = (PH + R - 1) / R;
+    const bool tables = PW <= 32 && (long long)PW * gw <= kSepTap && (long long)PH * gh <= kSepTap && nunits <= kBwdUnits;
+    if (threadIdx.x == 0) s_mode = tables ? 0 : 1;
+    if (tables) {
+        const int nx = PW * gw, ny = PH * gh;
+        for (int s = threadIdx.x; s < nx; s += blockDim.x) {
+            const int pw = s / gw;
+            xs[s] = make_xtap(g.start_w, g.bin_w, pw, s - pw * gw, gw, W);
+        }
+        for (int s = blockDim.x - 1 - threadIdx.x; s < ny; s += blockDim.x) {
+            const int ph = s / gh;
+            ys[s] = make_tap(g.start_h, g.bin_h, ph, s - ph * gh, gh, H, W * C);
+        }
+    }
+    __syncthreads();
+    if (tables) {
+        for (int u = threadIdx.x; u < nunits; u += blockDim.x) {   // merged y table of every unit
+            int n = 0;
+            bool overflow = false;
+            for (int r = 0; r < R && u * R + r < PH; ++r)
+                for (int iy = 0; iy < gh; ++iy) {
+                    const Tap Y = ys[(u * R + r) * gh + iy];
+                    if (Y.lo < 0) continue;
+                    for (int t = 0; t < 2; ++t) {
+                        const int off = t ? Y.hi : Y.lo;
+                        const float w = (t ? Y.l : Y.h) * rcount;
+                        int e = 0;
+                        while (e < n && ytab[u][e].off != off) ++e;
+                        if (e == n) {
+                            if (n == kBwdYEnt) { overflow = true; break; }
+                            ytab[u][e].off = off; ytab[u][e].w0 = 0.0f; ytab[u][e].w1 = 0.0f; ytab[u][e].pad = 0;
+                            ++n;
+                        }
+                        if (r == 0) ytab[u][e].w0 += w; else ytab[u][e].w1 += w;
+                    }
+                }
+            ycnt[u] = n;
+            if (overflow) s_mode = 1;
+        }
+    }
+    __syncthreads();
+
+    if (s_mode == 1) {   // exotic geometry: direct 4-tap scatter
+        for (int sl = 0; sl < nslab; ++sl) {
+            const int c0 = cg0 + sl * CC;
+            for (int b = warp; b < NB; b += nwarps) {
+                const int ph = b / PW, pw = b - ph * PW;
+                float gv[CPL];
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    const int c = c0 + lane + 32 * j;
+                    gv[j] = c < C ? to_f32(groi[(size_t)c * NB + b]) * rcount : 0.0f;
+                }
+                for (int iy = 0; iy < gh; ++iy) {
+                    const Tap Y = make_tap(g.start_h, g.bin_h, ph, iy, gh, H, W * C);
+                    if (Y.lo < 0) continue;
+                    for (int ix = 0; ix < gw; ++ix) {
+                        const Tap X = make_tap(g.start_w, g.bin_w, pw, ix, gw, W, C);
+                        if (X.lo < 0) continue;
+                        const float w1 = Y.h * X.h, w2 = Y.h * X.l, w3 = Y.l * X.h, w4 = Y.l * X.l;
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) {
+                            const int c = c0 + lane + 32 * j;
+                            if (c < C) {
+                                float* f = gimg + c;
+                                atomicAdd(f + Y.lo + X.lo, w1 * gv[j]);
+                                atomicAdd(f + Y.lo + X.hi, w2 * gv[j]);
+                                atomicAdd(f + Y.hi + X.lo, w3 * gv[j]);
+                                atomicAdd(f + Y.hi + X.hi, w4 * gv[j]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    float* __restrict__ Gw = gsm + (size_t)warp * 32 * P;
+    for (int item = warp; item < nunits * nslab; item += nwarps) {
+        const int sl = item / nunits, unit = item - sl * nunits;
+        const int ph0 = unit * R, nr = min(R, PH - ph0);
+        const int c0 = cg0 + sl * CC, cc = min(CC, C - c0);
+        const int nbu = nr * PW;
+        // ---- stage: lane = bin, coalesced rows of grad_out -> G[bin][channel]
+        {
+            const GT* __restrict__ gp = groi + (size_t)c0 * NB + ph0 * PW + lane;
+            float* __restrict__ gw_ = Gw + lane * P;
+            if (lane < nbu) {
+                int c = 0;
+                for (; c + 8 <= cc; c += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = to_f32(__ldg(gp + (size_t)(c + q) * NB));
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) gw_[c + q] = v[q];
+                }
+                for (; c < cc; ++c) gw_[c] = to_f32(__ldg(gp + (size_t)c * NB));
+            }
+        }
+        __syncwarp();
+        // ---- walk + flush: lane = channel
+        bool chv[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) chv[j] = lane + 32 * j < cc;
+        float* __restrict__ gb = gimg + c0 + lane;
+        const YEnt* __restrict__ yt = ytab[unit];
+        const int ne = ycnt[unit];
+        float a0[2][CPL], a1[2][CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) { a0[0][j] = a0[1][j] = a1[0][j] = a1[1][j] = 0.0f; }
+        int col0 = -1, col1 = -1;
+        auto flush = [&](const float (&a)[2][CPL], int col) {
+            float* __restrict__ gc = gb + (size_t)col * C;
+            for (int e = 0; e < ne; ++e) {
+                const YEnt E = yt[e];
+#pragma unroll
+                for (int j = 0; j < CPL; ++j)
+                    if (chv[j]) atomicAdd(gc + E.off + 32 * j, __fmaf_rn(E.w1, a[1][j], E.w0 * a[0][j]));
+            }
+        };
+        if (ne > 0) {
+            for (int pw = 0; pw < PW; ++pw) {
+                float g0[CPL], g1[CPL];
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    g0[j] = chv[j] ? Gw[pw * P + lane + 32 * j] : 0.0f;
+                    g1[j] = (chv[j] && nr == 2) ? Gw[(PW + pw) * P + lane + 32 * j] : 0.0f;
+                }
+                for (int ix = 0; ix < gw; ++ix) {
+                    const XTap X = xs[pw * gw + ix];
+                    if (X.lo < 0) continue;
+                    if (X.lo != col0 || X.hi != col1) {
+                        if (col0 >= 0 && X.lo == col1 && col1 != col0) {
+                            flush(a0, col0);
+#pragma unroll
+                            for (int j = 0; j < CPL; ++j) {
+                                a0[0][j] = a1[0][j]; a0[1][j] = a1[1][j];
+                                a1[0][j] = 0.0f;     a1[1][j] = 0.0f;
+                            }
+                        } else {
+                            if (col0 >= 0) {
+                                flush(a0, col0);
+                                if (col1 != col0) flush(a1, col1);
+                            }
+#pragma unroll
+                            for (int j = 0; j < CPL; ++j) { a0[0][j] = a0[1][j] = a1[0][j] = a1[1][j] = 0.0f; }
+                        }
+                        col0 = X.lo;
+                        col1 = X.hi;
+                    }
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) {
+                        a0[0][j] = __fmaf_rn(X.h, g0[j], a0[0][j]);
+                        a0[1][j] = __fmaf_rn(X.h, g1[j], a0[1][j]);
+                        a1[0][j] = __fmaf_rn(X.l, g0[j], a1[0][j]);
+                        a1[1][j] = __fmaf_rn(X.l, g1[j], a1[1][j]);
+                    }
+                }
+            }
+            if (col0 >= 0) {
+                flush(a0, col0);
+                if (col1 != col0) flush(a1, col1);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <typename GT, int CPL, int CS>
+static int launch_bwd_sep(const RoiParams& p, const GT* go, int warps, int slabs, cudaStream_t s) {
+    constexpr int CC = 32 * CPL;
+    auto kern = roi_align_bwd_sep_kernel<GT, CPL, CS>;
+    const size_t smem = (size_t)warps * 32 * (CC + 1) * sizeof(float);
+    if (smem > 24 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int cgroups = (int)ceil_div(p.C, CC * slabs);
+    kern<<<(unsigned)(p.K * cgroups), 32 * warps, smem, s>>>(p, go, cgroups, slabs);
+    return check_launch("roi_align_bwd_sep_kernel");
+}
+
 static int sep_env(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -382,6 +605,26 @@ int launch_roi_align_fwd_sep(const RoiParams& p, void* out, int out_dtype, cudaS
     slabs = std::max(1, std::min(slabs, (int)ceil_div(p.C, cc)));
     if (out_dtype == COIN_F32) return dispatch_sep<float>(p, static_cast<float*>(out), cpl, warps, slabs, s);
     return dispatch_sep<__half>(p, static_cast<__half*>(out), cpl, warps, slabs, s);
+}
+
+
+int launch_roi_align_bwd_sep(const RoiParams& p, const void* grad_out, int grad_dtype, cudaStream_t s) {
+    const int cpl = p.C <= 32 ? 1 : 2;
+    const int R = p.PW <= 16 && p.PH >= 2 ? 2 : 1;
+    int warps = sep_env("COIN_ROI_BWD_WARPS", (int)std::min<int64_t>(7, std::max<int64_t>(ceil_div(p.PH, R), 4)));
+    warps = std::max(1, std::min(warps, 7));   // the kernel is compiled for <= 224 threads
+    int slabs = sep_env("COIN_ROI_BWD_SLABS", 4);
+    slabs = std::max(1, std::min(slabs, (int)ceil_div(p.C, 32 * cpl)));
+    if (grad_dtype == COIN_F32) {
+        const float* g = static_cast<const float*>(grad_out);
+        if (cpl == 1) return launch_bwd_sep<float, 1, 0>(p, g, warps, slabs, s);
+        if (p.C == 1024) return launch_bwd_sep<float, 2, 1024>(p, g, warps, slabs, s);
+        return launch_bwd_sep<float, 2, 0>(p, g, warps, slabs, s);
+    }
+    const __half* g = static_cast<const __half*>(grad_out);
+    if (cpl == 1) return launch_bwd_sep<__half, 1, 0>(p, g, warps, slabs, s);
+    if (p.C == 1024) return launch_bwd_sep<__half, 2, 1024>(p, g, warps, slabs, s);
+    return launch_bwd_sep<__half, 2, 0>(p, g, warps, slabs, s);
 }
 
 }  // namespace coin

@@ -94,5 +94,7 @@ __device__ __forceinline__ Tap make_tap(float start, float bin, int p, int i, in
 
 // host-side launch of the separable forward kernel (roi_align_sep.cu)
 int launch_roi_align_fwd_sep(const RoiParams& p, void* out, int out_dtype, cudaStream_t s);
+// host-side launch of the separable backward kernel (roi_align_sep.cu); PW <= 32 only
+int launch_roi_align_bwd_sep(const RoiParams& p, const void* grad_out, int grad_dtype, cudaStream_t s);
 
 }  // namespace coin
