@@ -366,10 +366,51 @@ static int launch_sep(const RoiParams& p, OutT* out, int warps, int slabs, cudaS
 // ------------------------------------------------------------------------------------------------
 constexpr int kBwdYEnt = 16;    // merged y-table entries per unit
 constexpr int kBwdUnits = 16;   // units per RoI handled by the tables (PH <= 32 with two rows per unit)
+constexpr int kBwdCols = 128;   // feature columns of one RoI handled by the column program
+constexpr int kBwdEnt = 2 * kSepTap;   // (bin, weight) entries of the column program
 
 struct YEnt { int off; float w0, w1; int pad; };   // feature-row offset (y*W*C), weights of unit rows 0 and 1
+struct CEnt { int bin; float w; };                 // one bin's combined x weight on a feature column
 
-template <typename GT, int CPL, int CS>
+// walk + flush for one unit (lane = channel). FULL: the whole 32*CPL-channel slab is inside C.
+template <int CPL, bool FULL>
+__device__ __forceinline__ void bwd_walk(const float* __restrict__ Gw, float* __restrict__ gb, const int C, const int PW,
+                                         const int nr, const int cc, const int lane, const int cmin, const int ncols,
+                                         const int* __restrict__ colstart, const CEnt* __restrict__ cent,
+                                         const YEnt* __restrict__ yt, const int ne) {
+    constexpr int P = 32 * CPL + 1;
+    const float* __restrict__ G0 = Gw + lane;
+    const float* __restrict__ G1 = Gw + (nr == 2 ? PW * P : 0) + lane;
+    const float s1 = nr == 2 ? 1.0f : 0.0f;      // a single-row unit has no second row
+    for (int ci = 0; ci < ncols; ++ci) {
+        const int e0 = colstart[ci], e1 = colstart[ci + 1];
+        if (e0 == e1) continue;
+        float a0[CPL], a1[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) { a0[j] = 0.0f; a1[j] = 0.0f; }
+        for (int e = e0; e < e1; ++e) {
+            const CEnt E = cent[e];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const bool ok = FULL || lane + 32 * j < cc;
+                const float g0 = ok ? G0[E.bin * P + 32 * j] : 0.0f;
+                const float g1 = ok ? G1[E.bin * P + 32 * j] : 0.0f;
+                a0[j] = __fmaf_rn(E.w, g0, a0[j]);
+                a1[j] = __fmaf_rn(E.w, g1, a1[j]);
+            }
+        }
+        float* __restrict__ gc = gb + (size_t)(cmin + ci) * C;
+        for (int e = 0; e < ne; ++e) {
+            const YEnt Y = yt[e];
+            const float w1 = Y.w1 * s1;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j)
+                if (FULL || lane + 32 * j < cc) atomicAdd(gc + Y.off + 32 * j, __fmaf_rn(w1, a1[j], Y.w0 * a0[j]));
+        }
+    }
+}
+
+template <typename GT, int CPL, int CS, int PHT, int PWT>
 __global__ void __launch_bounds__(224, 3)
 roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int cgroups, const int slabs) {
     constexpr int CC = 32 * CPL, P = CC + 1;
@@ -378,7 +419,9 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
     __shared__ Tap ys[kSepTap];
     __shared__ YEnt ytab[kBwdUnits][kBwdYEnt];
     __shared__ int ycnt[kBwdUnits];
-    __shared__ int s_mode;                         // 0: separable, 1: direct
+    __shared__ int colstart[kBwdCols + 1];
+    __shared__ CEnt cent[kBwdEnt];
+    __shared__ int s_mode, s_cmin, s_cmax;         // mode 0: separable, 1: direct
 
     const int k = blockIdx.x / cgroups;
     const int cg0 = (blockIdx.x - k * cgroups) * (CC * slabs);
@@ -386,7 +429,7 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
     const coin_level_t L = p.lv[lvl];
     const int H = L.H, W = L.W;
-    const int C = CS ? CS : p.C, PH = p.PH, PW = p.PW, NB = PH * PW;
+    const int C = CS ? CS : p.C, PH = PHT ? PHT : p.PH, PW = PWT ? PWT : p.PW, NB = PH * PW;
     const RoiGeom g = roi_geometry(p.rois + 5 * (size_t)k, L.spatial_scale, PH, PW, p.sampling_ratio, p.aligned);
     float* __restrict__ gimg = const_cast<float*>(L.feat_nhwc) + (size_t)g.batch * H * W * C;
     const float rcount = 1.0f / g.count;
@@ -397,7 +440,7 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
     const int R = PW <= 16 && PH >= 2 ? 2 : 1;     // rows per unit (R*PW bins <= 32 lanes)
     const int nunits = (PH + R - 1) / R;
     const bool tables = PW <= 32 && (long long)PW * gw <= kSepTap && (long long)PH * gh <= kSepTap && nunits <= kBwdUnits;
-    if (threadIdx.x == 0) s_mode = tables ? 0 : 1;
+    if (threadIdx.x == 0) { s_mode = tables ? 0 : 1; s_cmin = INT_MAX; s_cmax = -1; }
     if (tables) {
         const int nx = PW * gw, ny = PH * gh;
         for (int s = threadIdx.x; s < nx; s += blockDim.x) {
@@ -411,7 +454,8 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
     }
     __syncthreads();
     if (tables) {
-        for (int u = threadIdx.x; u < nunits; u += blockDim.x) {   // merged y table of every unit
+        // merged y table of every unit (one thread per unit, from the high thread ids)
+        for (int u = blockDim.x - 1 - threadIdx.x; u < nunits; u += blockDim.x) {
             int n = 0;
             bool overflow = false;
             for (int r = 0; r < R && u * R + r < PH; ++r)
@@ -433,6 +477,64 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
                 }
             ycnt[u] = n;
             if (overflow) s_mode = 1;
+        }
+        // feature-column range of the RoI (warp 0)
+        if (warp == 0) {
+            int lo = INT_MAX, hi = -1;
+            for (int s = lane; s < PW * gw; s += 32) {
+                const XTap X = xs[s];
+                if (X.lo >= 0) { lo = min(lo, X.lo); hi = max(hi, X.hi); }
+            }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0) { s_cmin = lo; s_cmax = hi; }
+        }
+    }
+    __syncthreads();
+    const int cmin = s_cmin, ncols = s_cmax < 0 ? 0 : s_cmax - s_cmin + 1;
+    if (tables && ncols == 0) return;              // every x sample lies outside the map
+    if (tables && ncols > kBwdCols) { if (threadIdx.x == 0) s_mode = 1; }
+    else if (tables) {
+        // column program, pass 1: entries per column = bins with a non-empty weight on it
+        for (int ci = threadIdx.x; ci < ncols; ci += blockDim.x) {
+            const int col = cmin + ci;
+            int n = 0;
+            for (int pw = 0; pw < PW; ++pw) {
+                bool hit = false;
+                for (int ix = 0; ix < gw; ++ix) {
+                    const XTap X = xs[pw * gw + ix];
+                    hit |= X.lo >= 0 && (X.lo == col || X.hi == col);
+                }
+                n += hit;
+            }
+            colstart[ci + 1] = n;
+        }
+    }
+    __syncthreads();
+    if (s_mode == 0) {
+        if (threadIdx.x == 0) {   // exclusive prefix over <= kBwdCols columns
+            int acc = 0;
+            colstart[0] = 0;
+            for (int ci = 0; ci < ncols; ++ci) { acc += colstart[ci + 1]; colstart[ci + 1] = acc; }
+            if (acc > kBwdEnt) s_mode = 1;
+        }
+    }
+    __syncthreads();
+    if (s_mode == 0) {
+        for (int ci = threadIdx.x; ci < ncols; ci += blockDim.x) {   // pass 2: fill (bin, combined weight)
+            const int col = cmin + ci;
+            int at = colstart[ci];
+            for (int pw = 0; pw < PW; ++pw) {
+                float w = 0.0f;
+                bool hit = false;
+                for (int ix = 0; ix < gw; ++ix) {
+                    const XTap X = xs[pw * gw + ix];
+                    if (X.lo < 0) continue;
+                    if (X.lo == col) { w += X.h; hit = true; }
+                    if (X.hi == col) { w += X.l; hit = true; }
+                }
+                if (hit) { cent[at].bin = pw; cent[at].w = w; ++at; }
+            }
         }
     }
     __syncthreads();
@@ -479,100 +581,47 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
         const int ph0 = unit * R, nr = min(R, PH - ph0);
         const int c0 = cg0 + sl * CC, cc = min(CC, C - c0);
         const int nbu = nr * PW;
+        const int ne = ycnt[unit];
+        if (ne == 0) continue;                     // every y sample of the unit lies outside the map
         // ---- stage: lane = bin, coalesced rows of grad_out -> G[bin][channel]
-        {
+        if (lane < nbu) {
             const GT* __restrict__ gp = groi + (size_t)c0 * NB + ph0 * PW + lane;
             float* __restrict__ gw_ = Gw + lane * P;
-            if (lane < nbu) {
-                int c = 0;
-                for (; c + 8 <= cc; c += 8) {
-                    float v[8];
+            int c = 0;
+            for (; c + 16 <= cc; c += 16) {
+                float v[16];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = to_f32(__ldg(gp + (size_t)(c + q) * NB));
+                for (int q = 0; q < 16; ++q) v[q] = to_f32(__ldg(gp + (size_t)(c + q) * NB));
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) gw_[c + q] = v[q];
-                }
-                for (; c < cc; ++c) gw_[c] = to_f32(__ldg(gp + (size_t)c * NB));
+                for (int q = 0; q < 16; ++q) gw_[c + q] = v[q];
             }
+            for (; c < cc; ++c) gw_[c] = to_f32(__ldg(gp + (size_t)c * NB));
         }
         __syncwarp();
-        // ---- walk + flush: lane = channel
-        bool chv[CPL];
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) chv[j] = lane + 32 * j < cc;
         float* __restrict__ gb = gimg + c0 + lane;
-        const YEnt* __restrict__ yt = ytab[unit];
-        const int ne = ycnt[unit];
-        float a0[2][CPL], a1[2][CPL];
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) { a0[0][j] = a0[1][j] = a1[0][j] = a1[1][j] = 0.0f; }
-        int col0 = -1, col1 = -1;
-        auto flush = [&](const float (&a)[2][CPL], int col) {
-            float* __restrict__ gc = gb + (size_t)col * C;
-            for (int e = 0; e < ne; ++e) {
-                const YEnt E = yt[e];
-#pragma unroll
-                for (int j = 0; j < CPL; ++j)
-                    if (chv[j]) atomicAdd(gc + E.off + 32 * j, __fmaf_rn(E.w1, a[1][j], E.w0 * a[0][j]));
-            }
-        };
-        if (ne > 0) {
-            for (int pw = 0; pw < PW; ++pw) {
-                float g0[CPL], g1[CPL];
-#pragma unroll
-                for (int j = 0; j < CPL; ++j) {
-                    g0[j] = chv[j] ? Gw[pw * P + lane + 32 * j] : 0.0f;
-                    g1[j] = (chv[j] && nr == 2) ? Gw[(PW + pw) * P + lane + 32 * j] : 0.0f;
-                }
-                for (int ix = 0; ix < gw; ++ix) {
-                    const XTap X = xs[pw * gw + ix];
-                    if (X.lo < 0) continue;
-                    if (X.lo != col0 || X.hi != col1) {
-                        if (col0 >= 0 && X.lo == col1 && col1 != col0) {
-                            flush(a0, col0);
-#pragma unroll
-                            for (int j = 0; j < CPL; ++j) {
-                                a0[0][j] = a1[0][j]; a0[1][j] = a1[1][j];
-                                a1[0][j] = 0.0f;     a1[1][j] = 0.0f;
-                            }
-                        } else {
-                            if (col0 >= 0) {
-                                flush(a0, col0);
-                                if (col1 != col0) flush(a1, col1);
-                            }
-#pragma unroll
-                            for (int j = 0; j < CPL; ++j) { a0[0][j] = a0[1][j] = a1[0][j] = a1[1][j] = 0.0f; }
-                        }
-                        col0 = X.lo;
-                        col1 = X.hi;
-                    }
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j) {
-                        a0[0][j] = __fmaf_rn(X.h, g0[j], a0[0][j]);
-                        a0[1][j] = __fmaf_rn(X.h, g1[j], a0[1][j]);
-                        a1[0][j] = __fmaf_rn(X.l, g0[j], a1[0][j]);
-                        a1[1][j] = __fmaf_rn(X.l, g1[j], a1[1][j]);
-                    }
-                }
-            }
-            if (col0 >= 0) {
-                flush(a0, col0);
-                if (col1 != col0) flush(a1, col1);
-            }
-        }
+        if (cc == CC) bwd_walk<CPL, true>(Gw, gb, C, PW, nr, cc, lane, cmin, ncols, colstart, cent, ytab[unit], ne);
+        else bwd_walk<CPL, false>(Gw, gb, C, PW, nr, cc, lane, cmin, ncols, colstart, cent, ytab[unit], ne);
         __syncwarp();
     }
 }
 
-template <typename GT, int CPL, int CS>
+template <typename GT, int CPL, int CS, int PHT, int PWT>
 static int launch_bwd_sep(const RoiParams& p, const GT* go, int warps, int slabs, cudaStream_t s) {
     constexpr int CC = 32 * CPL;
-    auto kern = roi_align_bwd_sep_kernel<GT, CPL, CS>;
+    auto kern = roi_align_bwd_sep_kernel<GT, CPL, CS, PHT, PWT>;
     const size_t smem = (size_t)warps * 32 * (CC + 1) * sizeof(float);
     if (smem > 24 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int cgroups = (int)ceil_div(p.C, CC * slabs);
     kern<<<(unsigned)(p.K * cgroups), 32 * warps, smem, s>>>(p, go, cgroups, slabs);
     return check_launch("roi_align_bwd_sep_kernel");
+}
+
+template <typename GT>
+static int dispatch_bwd_sep(const RoiParams& p, const GT* g, int cpl, int warps, int slabs, cudaStream_t s) {
+    if (cpl == 1) return launch_bwd_sep<GT, 1, 0, 0, 0>(p, g, warps, slabs, s);
+    if (p.C == 1024 && p.PH == 14 && p.PW == 14) return launch_bwd_sep<GT, 2, 1024, 14, 14>(p, g, warps, slabs, s);
+    if (p.C == 1024 && p.PH == 7 && p.PW == 7) return launch_bwd_sep<GT, 2, 1024, 7, 7>(p, g, warps, slabs, s);
+    return launch_bwd_sep<GT, 2, 0, 0, 0>(p, g, warps, slabs, s);
 }
 
 static int sep_env(const char* name, int dflt) {
@@ -615,16 +664,8 @@ int launch_roi_align_bwd_sep(const RoiParams& p, const void* grad_out, int grad_
     warps = std::max(1, std::min(warps, 7));   // the kernel is compiled for <= 224 threads
     int slabs = sep_env("COIN_ROI_BWD_SLABS", 4);
     slabs = std::max(1, std::min(slabs, (int)ceil_div(p.C, 32 * cpl)));
-    if (grad_dtype == COIN_F32) {
-        const float* g = static_cast<const float*>(grad_out);
-        if (cpl == 1) return launch_bwd_sep<float, 1, 0>(p, g, warps, slabs, s);
-        if (p.C == 1024) return launch_bwd_sep<float, 2, 1024>(p, g, warps, slabs, s);
-        return launch_bwd_sep<float, 2, 0>(p, g, warps, slabs, s);
-    }
-    const __half* g = static_cast<const __half*>(grad_out);
-    if (cpl == 1) return launch_bwd_sep<__half, 1, 0>(p, g, warps, slabs, s);
-    if (p.C == 1024) return launch_bwd_sep<__half, 2, 1024>(p, g, warps, slabs, s);
-    return launch_bwd_sep<__half, 2, 0>(p, g, warps, slabs, s);
+    if (grad_dtype == COIN_F32) return dispatch_bwd_sep<float>(p, static_cast<const float*>(grad_out), cpl, warps, slabs, s);
+    return dispatch_bwd_sep<__half>(p, static_cast<const __half*>(grad_out), cpl, warps, slabs, s);
 }
 
 }  // namespace coin
