@@ -24,6 +24,20 @@ class CoinLevel(Structure):
     _fields_ = [("feat_nhwc", c_void_p), ("H", c_int), ("W", c_int), ("spatial_scale", c_float)]
 
 
+class CoinSeg(Structure):
+    _fields_ = [("ptr", c_void_p), ("count_dev", c_void_p), ("count", c_int64), ("prefix", c_float)]
+
+
+class CoinDets(Structure):
+    _fields_ = [("boxes", c_void_p), ("classes", c_void_p), ("scores", c_void_p), ("probs", c_void_p)]
+
+
+class CoinPseudo(Structure):
+    _fields_ = [("boxes", c_void_p), ("classes", c_void_p), ("classes_online", c_void_p),
+                ("scores_online", c_void_p), ("scores_offline", c_void_p), ("probs_online", c_void_p),
+                ("probs_offline", c_void_p)]
+
+
 P = c_void_p
 _SIGNATURES = {
     # name: (restype, [argtypes])
@@ -62,6 +76,19 @@ _SIGNATURES = {
     "coin_match_abc_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "coin_match_abc": (c_int, [P, P, P, c_int64, P, P, P, c_int64, c_int, c_float, c_float, c_int64,
                                P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    # sync-free (device-count) variants
+    "coin_roi_align_fwd_dev": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, P, P]),
+    "coin_iou_match_dev": (c_int, [P, c_int64, P, P, c_int64, P, POINTER(c_float), c_int, POINTER(ctypes.c_int8),
+                                   c_int, P, P, P, P, P]),
+    "coin_relabel_roi_dev": (c_int, [P, P, c_int64, P, P, P, P, P]),
+    "coin_relabel_rpn_dev": (c_int, [P, P, c_int64, P, P, P, P, P]),
+    "coin_match_abc_dev": (c_int, [P, P, P, c_int64, P, P, P, c_int64, P, c_int, c_float, c_float, c_int64,
+                                   P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "coin_concat_rows": (c_int, [POINTER(CoinSeg), c_int, c_int, c_int, P, c_int64, P, P]),
+    "coin_abc_pack": (c_int, [POINTER(CoinDets), c_int64, POINTER(CoinDets), c_int64, P, c_int, c_int,
+                              P, P, P, P, P, P, P, POINTER(CoinPseudo), POINTER(CoinPseudo), POINTER(CoinPseudo),
+                              c_int64, P]),
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())

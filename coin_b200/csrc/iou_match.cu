@@ -50,12 +50,17 @@ __global__ void pairwise_iou_kernel(const float4* __restrict__ b1, int64_t N, co
 }
 
 // Fused IoU + column arg-max (+ optional row maxima). One thread per column.
+// n_dev / m_dev: optional device-side live counts (<= the host capacities N / M) for sync-free chaining.
 template <bool kRowMax>
 __global__ void iou_match_kernel(const float4* __restrict__ gt, int64_t N, const float4* __restrict__ boxes,
                                  int64_t M, MatcherCfg cfg, int64_t* __restrict__ matches,
-                                 int8_t* __restrict__ labels, float* __restrict__ vals, int* __restrict__ row_max) {
+                                 int8_t* __restrict__ labels, float* __restrict__ vals, int* __restrict__ row_max,
+                                 const int32_t* __restrict__ n_dev, const int32_t* __restrict__ m_dev) {
     __shared__ float4 srow[kRowTile];
     __shared__ float sarea[kRowTile];
+    if (n_dev) N = min((int64_t)max(__ldg(n_dev), 0), N);
+    if (m_dev) M = min((int64_t)max(__ldg(m_dev), 0), M);
+    if ((int64_t)blockIdx.x * blockDim.x >= M) return;   // capacity launch: whole CTA beyond the live columns
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = j < M;
     const float4 b = live ? __ldg(boxes + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -83,6 +88,12 @@ __global__ void iou_match_kernel(const float4* __restrict__ gt, int64_t N, const
         }
     }
     if (!live) return;
+    if (N == 0) {   // Matcher's empty-matrix rule (decided on the device when N is a device count)
+        matches[j] = 0;
+        labels[j] = cfg.labels[0];
+        if (vals) vals[j] = 0.0f;
+        return;
+    }
     matches[j] = best_i;
     labels[j] = bucket_label(cfg, best);
     if (vals) vals[j] = best;
@@ -90,10 +101,14 @@ __global__ void iou_match_kernel(const float4* __restrict__ gt, int64_t N, const
 
 // Low-quality rule: every column whose IoU with some GT row equals that row's maximum gets label 1.
 __global__ void iou_low_quality_kernel(const float4* __restrict__ gt, int64_t N, const float4* __restrict__ boxes,
-                                       int64_t M, const float* __restrict__ row_max, int8_t* __restrict__ labels) {
+                                       int64_t M, const float* __restrict__ row_max, int8_t* __restrict__ labels,
+                                       const int32_t* __restrict__ n_dev, const int32_t* __restrict__ m_dev) {
     __shared__ float4 srow[kRowTile];
     __shared__ float sarea[kRowTile];
     __shared__ float smax[kRowTile];
+    if (n_dev) N = min((int64_t)max(__ldg(n_dev), 0), N);
+    if (m_dev) M = min((int64_t)max(__ldg(m_dev), 0), M);
+    if ((int64_t)blockIdx.x * blockDim.x >= M) return;
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = j < M;
     const float4 b = live ? __ldg(boxes + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -166,8 +181,13 @@ __global__ void empty_matcher_kernel(int64_t M, int8_t label0, int64_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// lens: optional device int32 lengths {len_a, len_b, len_c} of the pseudo-GT sets (c_begin = a+b, c_end = a+b+c)
 __global__ void relabel_roi_kernel(const int64_t* __restrict__ matches, int8_t* __restrict__ labels, int64_t M,
-                                   int64_t c_begin, int64_t c_end) {
+                                   int64_t c_begin, int64_t c_end, const int32_t* __restrict__ len_a,
+                                   const int32_t* __restrict__ len_b, const int32_t* __restrict__ len_c,
+                                   const int32_t* __restrict__ m_dev) {
+    if (len_a) { c_begin = (int64_t)__ldg(len_a) + __ldg(len_b); c_end = c_begin + __ldg(len_c); }
+    if (m_dev) M = min((int64_t)max(__ldg(m_dev), 0), M);
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= M) return;
     const int64_t m = matches[j];
@@ -176,7 +196,9 @@ __global__ void relabel_roi_kernel(const int64_t* __restrict__ matches, int8_t* 
 
 __global__ void relabel_rpn_kernel(int64_t* __restrict__ matches, int8_t* __restrict__ labels, int64_t M,
                                    int64_t len_a, int64_t len_c, int64_t* __restrict__ distill_idx,
-                                   int8_t* __restrict__ distill_labels) {
+                                   int8_t* __restrict__ distill_labels, const int32_t* __restrict__ len_a_dev,
+                                   const int32_t* __restrict__ len_c_dev) {
+    if (len_a_dev) { len_a = __ldg(len_a_dev); len_c = __ldg(len_c_dev); }
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= M) return;
     const int64_t m = matches[j];
@@ -307,10 +329,11 @@ extern "C" int coin_pairwise_iou(const float* b1, int64_t N, const float* b2, in
     return check_launch("pairwise_iou_kernel");
 }
 
-extern "C" int coin_iou_match(const float* gt, int64_t N, const float* boxes, int64_t M,
-                              const float* thresholds_host, int nthr, const int8_t* labels_host,
-                              int allow_low_quality, int64_t* matches, int8_t* match_labels,
-                              float* matched_vals, float* row_max_ws, coin_stream_t stream) {
+static int iou_match_impl(const float* gt, int64_t N, const float* boxes, int64_t M,
+                          const float* thresholds_host, int nthr, const int8_t* labels_host,
+                          int allow_low_quality, int64_t* matches, int8_t* match_labels,
+                          float* matched_vals, float* row_max_ws, const int32_t* n_dev, const int32_t* m_dev,
+                          coin_stream_t stream) {
     MatcherCfg cfg;
     if (int rc = make_cfg(cfg, thresholds_host, nthr, labels_host)) return rc;
     COIN_REQUIRE(N >= 0 && M >= 0, "iou_match: bad sizes");
@@ -328,16 +351,36 @@ extern "C" int coin_iou_match(const float* gt, int64_t N, const float* boxes, in
         cudaMemsetAsync(row_max_ws, 0, N * sizeof(float), s);
         iou_match_kernel<true><<<blocks, 128, 0, s>>>(reinterpret_cast<const float4*>(gt), N,
                                                       reinterpret_cast<const float4*>(boxes), M, cfg, matches,
-                                                      match_labels, matched_vals, reinterpret_cast<int*>(row_max_ws));
+                                                      match_labels, matched_vals, reinterpret_cast<int*>(row_max_ws),
+                                                      n_dev, m_dev);
         if (int rc = check_launch("iou_match_kernel")) return rc;
         iou_low_quality_kernel<<<blocks, 128, 0, s>>>(reinterpret_cast<const float4*>(gt), N,
-                                                      reinterpret_cast<const float4*>(boxes), M, row_max_ws, match_labels);
+                                                      reinterpret_cast<const float4*>(boxes), M, row_max_ws, match_labels,
+                                                      n_dev, m_dev);
         return check_launch("iou_low_quality_kernel");
     }
     iou_match_kernel<false><<<blocks, 128, 0, s>>>(reinterpret_cast<const float4*>(gt), N,
                                                    reinterpret_cast<const float4*>(boxes), M, cfg, matches,
-                                                   match_labels, matched_vals, nullptr);
+                                                   match_labels, matched_vals, nullptr, n_dev, m_dev);
     return check_launch("iou_match_kernel");
+}
+
+extern "C" int coin_iou_match(const float* gt, int64_t N, const float* boxes, int64_t M,
+                              const float* thresholds_host, int nthr, const int8_t* labels_host,
+                              int allow_low_quality, int64_t* matches, int8_t* match_labels,
+                              float* matched_vals, float* row_max_ws, coin_stream_t stream) {
+    return iou_match_impl(gt, N, boxes, M, thresholds_host, nthr, labels_host, allow_low_quality, matches, match_labels,
+                          matched_vals, row_max_ws, nullptr, nullptr, stream);
+}
+
+extern "C" int coin_iou_match_dev(const float* gt, int64_t N_cap, const int32_t* n_dev, const float* boxes,
+                                  int64_t M_cap, const int32_t* m_dev, const float* thresholds_host, int nthr,
+                                  const int8_t* labels_host, int allow_low_quality, int64_t* matches,
+                                  int8_t* match_labels, float* matched_vals, float* row_max_ws,
+                                  coin_stream_t stream) {
+    COIN_REQUIRE(N_cap >= 1, "iou_match_dev: N_cap must be >= 1 (an empty set is a device count of 0)");
+    return iou_match_impl(gt, N_cap, boxes, M_cap, thresholds_host, nthr, labels_host, allow_low_quality, matches,
+                          match_labels, matched_vals, row_max_ws, n_dev, m_dev, stream);
 }
 
 extern "C" int coin_matcher(const float* quality, int64_t N, int64_t M, const float* thresholds_host, int nthr,
@@ -372,7 +415,19 @@ extern "C" int coin_relabel_roi(const int64_t* matches, int8_t* match_labels, in
     COIN_REQUIRE(M >= 0, "relabel_roi: bad size");
     if (M == 0) return COIN_OK;
     COIN_REQUIRE(matches && match_labels, "relabel_roi: null pointer");
-    relabel_roi_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(matches, match_labels, M, c_begin, c_end);
+    relabel_roi_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(matches, match_labels, M, c_begin, c_end,
+                                                                                nullptr, nullptr, nullptr, nullptr);
+    return check_launch("relabel_roi_kernel");
+}
+
+extern "C" int coin_relabel_roi_dev(const int64_t* matches, int8_t* match_labels, int64_t M_cap, const int32_t* m_dev,
+                                    const int32_t* len_a, const int32_t* len_b, const int32_t* len_c,
+                                    coin_stream_t stream) {
+    COIN_REQUIRE(M_cap >= 0, "relabel_roi_dev: bad size");
+    if (M_cap == 0) return COIN_OK;
+    COIN_REQUIRE(matches && match_labels && len_a && len_b && len_c, "relabel_roi_dev: null pointer");
+    relabel_roi_kernel<<<(unsigned)ceil_div(M_cap, 256), 256, 0, as_stream(stream)>>>(matches, match_labels, M_cap, 0, 0,
+                                                                                    len_a, len_b, len_c, m_dev);
     return check_launch("relabel_roi_kernel");
 }
 
@@ -382,7 +437,18 @@ extern "C" int coin_relabel_rpn(int64_t* matches, int8_t* labels, int64_t M, int
     if (M == 0) return COIN_OK;
     COIN_REQUIRE(matches && labels && distill_idx && distill_labels, "relabel_rpn: null pointer");
     relabel_rpn_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(matches, labels, M, len_a, len_c,
-                                                                                distill_idx, distill_labels);
+                                                                                distill_idx, distill_labels, nullptr, nullptr);
+    return check_launch("relabel_rpn_kernel");
+}
+
+extern "C" int coin_relabel_rpn_dev(int64_t* matches, int8_t* labels, int64_t M, const int32_t* len_a,
+                                    const int32_t* len_c, int64_t* distill_idx, int8_t* distill_labels,
+                                    coin_stream_t stream) {
+    COIN_REQUIRE(M >= 0, "relabel_rpn_dev: bad size");
+    if (M == 0) return COIN_OK;
+    COIN_REQUIRE(matches && labels && distill_idx && distill_labels && len_a && len_c, "relabel_rpn_dev: null pointer");
+    relabel_rpn_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(matches, labels, M, 0, 0, distill_idx,
+                                                                                distill_labels, len_a, len_c);
     return check_launch("relabel_rpn_kernel");
 }
 

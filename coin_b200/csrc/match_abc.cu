@@ -23,6 +23,7 @@ struct AbcArgs {
     const int64_t *oncls, *offcls;
     const float *ons, *offs;
     int nc, nd, tag;
+    const int32_t* nd_dev;   // optional device-side count of CLIP-detector detections (<= nd)
     float thr, w_a;
     int cap;
     int32_t *a_on, *a_off, *b_on, *b_off, *c_on, *c_off, *counts;
@@ -138,7 +139,7 @@ __device__ int dedup_order(const float4* box, int L, const AbcArgs& a, int32_t* 
 
 __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a) {
     __shared__ int s_tmp, s_flag[4];
-    const int nc = a.nc, nd = a.nd;
+    const int nc = a.nc, nd = a.nd_dev ? min(max(*a.nd_dev, 0), a.nd) : a.nd;
     int status = 0;
     // In the empty-side branches both members of a pair come from the same detection set.
     const bool on_empty = (nc == 0), off_empty = (nd == 0);
@@ -458,12 +459,12 @@ extern "C" size_t coin_match_abc_workspace_bytes(int64_t nc, int64_t nd) {
     return total + 256;
 }
 
-extern "C" int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float* on_scores, int64_t nc,
-                              const float* off_boxes, const int64_t* off_classes, const float* off_scores,
-                              int64_t nd, int tag, float iou_thr, float weight_for_box_a, int64_t cap_pairs,
-                              int32_t* a_on, int32_t* a_off, float* a_boxes, int32_t* b_on, int32_t* b_off,
-                              float* b_boxes, int32_t* c_on, int32_t* c_off, int32_t* counts, void* ws,
-                              size_t ws_bytes, coin_stream_t stream) {
+static int match_abc_impl(const float* on_boxes, const int64_t* on_classes, const float* on_scores, int64_t nc,
+                          const float* off_boxes, const int64_t* off_classes, const float* off_scores,
+                          int64_t nd, const int32_t* nd_dev, int tag, float iou_thr, float weight_for_box_a,
+                          int64_t cap_pairs, int32_t* a_on, int32_t* a_off, float* a_boxes, int32_t* b_on,
+                          int32_t* b_off, float* b_boxes, int32_t* c_on, int32_t* c_off, int32_t* counts, void* ws,
+                          size_t ws_bytes, coin_stream_t stream) {
     COIN_REQUIRE(nc >= 0 && nd >= 0 && counts, "match_abc: bad arguments");
     COIN_REQUIRE(nc <= COIN_ABC_MAX && nd <= COIN_ABC_MAX, "match_abc: at most %d detections per side", COIN_ABC_MAX);
     COIN_REQUIRE(tag == COIN_TAG_RCNN || tag == COIN_TAG_RPN, "match_abc: bad tag %d", tag);
@@ -481,9 +482,32 @@ extern "C" int coin_match_abc(const float* on_boxes, const int64_t* on_classes, 
     if (ws_bytes < total) return fail(COIN_ERR_CAPACITY, "match_abc: workspace too small (%zu < %zu)", ws_bytes, total);
     a.onb = reinterpret_cast<const float4*>(on_boxes); a.offb = reinterpret_cast<const float4*>(off_boxes);
     a.oncls = on_classes; a.offcls = off_classes; a.ons = on_scores; a.offs = off_scores;
-    a.nc = (int)nc; a.nd = (int)nd; a.tag = tag; a.thr = iou_thr; a.w_a = weight_for_box_a; a.cap = (int)cap_pairs;
+    a.nc = (int)nc; a.nd = (int)nd; a.nd_dev = nd_dev; a.tag = tag; a.thr = iou_thr; a.w_a = weight_for_box_a; a.cap = (int)cap_pairs;
     a.a_on = a_on; a.a_off = a_off; a.b_on = b_on; a.b_off = b_off; a.c_on = c_on; a.c_off = c_off; a.counts = counts;
     a.a_box = reinterpret_cast<float4*>(a_boxes); a.b_box = reinterpret_cast<float4*>(b_boxes);
     match_abc_kernel<<<1, 256, 0, s>>>(a);
     return check_launch("match_abc_kernel");
+}
+
+extern "C" int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float* on_scores, int64_t nc,
+                              const float* off_boxes, const int64_t* off_classes, const float* off_scores,
+                              int64_t nd, int tag, float iou_thr, float weight_for_box_a, int64_t cap_pairs,
+                              int32_t* a_on, int32_t* a_off, float* a_boxes, int32_t* b_on, int32_t* b_off,
+                              float* b_boxes, int32_t* c_on, int32_t* c_off, int32_t* counts, void* ws,
+                              size_t ws_bytes, coin_stream_t stream) {
+    return match_abc_impl(on_boxes, on_classes, on_scores, nc, off_boxes, off_classes, off_scores, nd, nullptr, tag,
+                          iou_thr, weight_for_box_a, cap_pairs, a_on, a_off, a_boxes, b_on, b_off, b_boxes, c_on, c_off,
+                          counts, ws, ws_bytes, stream);
+}
+
+extern "C" int coin_match_abc_dev(const float* on_boxes, const int64_t* on_classes, const float* on_scores, int64_t nc,
+                                  const float* off_boxes, const int64_t* off_classes, const float* off_scores,
+                                  int64_t nd_cap, const int32_t* nd_dev, int tag, float iou_thr,
+                                  float weight_for_box_a, int64_t cap_pairs, int32_t* a_on, int32_t* a_off,
+                                  float* a_boxes, int32_t* b_on, int32_t* b_off, float* b_boxes, int32_t* c_on,
+                                  int32_t* c_off, int32_t* counts, void* ws, size_t ws_bytes, coin_stream_t stream) {
+    COIN_REQUIRE(nd_cap >= 1 && nd_dev, "match_abc_dev: nd_cap must be >= 1 and nd_dev non-null");
+    return match_abc_impl(on_boxes, on_classes, on_scores, nc, off_boxes, off_classes, off_scores, nd_cap, nd_dev, tag,
+                          iou_thr, weight_for_box_a, cap_pairs, a_on, a_off, a_boxes, b_on, b_off, b_boxes, c_on, c_off,
+                          counts, ws, ws_bytes, stream);
 }

@@ -72,6 +72,7 @@ roi_align_fwd_kernel(const RoiParams p, OutT* __restrict__ out, const int chunks
     __shared__ Tap xs[kTapCap], ys[kTapCap];
     OutT* tile = reinterpret_cast<OutT*>(smem_raw);  // [32*CPL][PH*PW] == the CTA's contiguous output region
     const int k = blockIdx.x / chunks;
+    if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
     const int c0 = (blockIdx.x - k * chunks) * (32 * CPL);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
@@ -210,6 +211,7 @@ roi_align_bwd_kernel(const RoiParams p, const GT* __restrict__ grad_out, const i
     __shared__ __align__(8) uint64_t mbar;
     const GT* tile = reinterpret_cast<const GT*>(smem_raw);  // [32*CPL][PH*PW]
     const int k = blockIdx.x / chunks;
+    if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
     const int c0 = (blockIdx.x - k * chunks) * (32 * CPL);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
@@ -394,7 +396,7 @@ static int fill_params(RoiParams& p, const coin_level_t* levels, int nlevels, co
         p.lv[i] = levels[i];
     }
     for (int i = nlevels; i < COIN_MAX_LEVELS; ++i) p.lv[i] = levels[0];
-    p.rois = rois; p.roi_level = nlevels > 1 ? roi_level : nullptr;
+    p.rois = rois; p.roi_level = nlevels > 1 ? roi_level : nullptr; p.k_dev = nullptr;
     p.C = C; p.K = K; p.PH = PH; p.PW = PW; p.sampling_ratio = sr; p.aligned = aligned;
     return COIN_OK;
 }
@@ -468,6 +470,25 @@ extern "C" int coin_roi_align_fwd(const coin_level_t* levels_host, int nlevels, 
     if (K == 0) return COIN_OK;
     COIN_REQUIRE(out, "roi_align_fwd: out is null");
     // COIN_ROI_EXACT: 0 (default) separable fast kernel; 1 bit-exact parity kernel; 2 the parity kernel's FMA variant
+    const int mode = env_int("COIN_ROI_EXACT", 0);
+    if (mode == 0) return launch_roi_align_fwd_sep(p, out, out_dtype, as_stream(stream));
+    LaunchCfg cfg;
+    if (int rc = pick_cfg(cfg, C, PH, PW, out_dtype == COIN_F32 ? 4 : 2, "COIN_ROI_FWD")) return rc;
+    cudaStream_t s = as_stream(stream);
+    if (out_dtype == COIN_F32) COIN_DISPATCH_ROI(launch_fwd, float, static_cast<float*>(out));
+    COIN_DISPATCH_ROI(launch_fwd, __half, static_cast<__half*>(out));
+}
+
+extern "C" int coin_roi_align_fwd_dev(const coin_level_t* levels_host, int nlevels, const float* rois,
+                                      const int32_t* roi_level, void* out, int out_dtype, int C, int K_cap, int PH,
+                                      int PW, int sampling_ratio, int aligned, const int32_t* k_dev,
+                                      coin_stream_t stream) {
+    RoiParams p;
+    if (int rc = fill_params(p, levels_host, nlevels, rois, roi_level, C, K_cap, PH, PW, sampling_ratio, aligned)) return rc;
+    COIN_REQUIRE(out_dtype == COIN_F32 || out_dtype == COIN_F16, "roi_align_fwd: bad out_dtype %d", out_dtype);
+    if (K_cap == 0) return COIN_OK;
+    COIN_REQUIRE(out, "roi_align_fwd: out is null");
+    p.k_dev = k_dev;
     const int mode = env_int("COIN_ROI_EXACT", 0);
     if (mode == 0) return launch_roi_align_fwd_sep(p, out, out_dtype, as_stream(stream));
     LaunchCfg cfg;

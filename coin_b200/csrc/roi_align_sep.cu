@@ -30,6 +30,11 @@
 
 namespace coin {
 
+static inline int sep_env(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 constexpr int kSepTap = 128;     // tap-table entries per axis (PW*grid_w and PH*grid_h must fit)
 constexpr int kSepCells = 32;    // T cells (row x feature column) per unit
 constexpr int kSepChunks = 16;   // max column chunks per RoI
@@ -137,6 +142,7 @@ roi_align_fwd_sep_kernel(const RoiParams p, OutT* __restrict__ out, const int cg
     __shared__ int s_nchunks, s_rows, s_mode;      // mode 0: separable, 1: direct, 2: all zero
 
     const int k = blockIdx.x / cgroups;
+    if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
     const int cg0 = (blockIdx.x - k * cgroups) * (CC * slabs);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
@@ -410,7 +416,7 @@ __device__ __forceinline__ void bwd_walk(const float* __restrict__ Gw, float* __
     }
 }
 
-template <typename GT, int CPL, int CS, int PHT, int PWT>
+template <typename GT, int CPL, int CS, int PHT, int PWT, int SB>
 __global__ void __launch_bounds__(224, 3)
 roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int cgroups, const int slabs) {
     constexpr int CC = 32 * CPL, P = CC + 1;
@@ -424,6 +430,7 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
     __shared__ int s_mode, s_cmin, s_cmax;         // mode 0: separable, 1: direct
 
     const int k = blockIdx.x / cgroups;
+    if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
     const int cg0 = (blockIdx.x - k * cgroups) * (CC * slabs);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
@@ -588,12 +595,12 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
             const GT* __restrict__ gp = groi + (size_t)c0 * NB + ph0 * PW + lane;
             float* __restrict__ gw_ = Gw + lane * P;
             int c = 0;
-            for (; c + 16 <= cc; c += 16) {
-                float v[16];
+            for (; c + SB <= cc; c += SB) {   // SB loads in flight per lane
+                float v[SB];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = to_f32(__ldg(gp + (size_t)(c + q) * NB));
+                for (int q = 0; q < SB; ++q) v[q] = to_f32(__ldg(gp + (size_t)(c + q) * NB));
 #pragma unroll
-                for (int q = 0; q < 16; ++q) gw_[c + q] = v[q];
+                for (int q = 0; q < SB; ++q) gw_[c + q] = v[q];
             }
             for (; c < cc; ++c) gw_[c] = to_f32(__ldg(gp + (size_t)c * NB));
         }
@@ -605,10 +612,10 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
     }
 }
 
-template <typename GT, int CPL, int CS, int PHT, int PWT>
+template <typename GT, int CPL, int CS, int PHT, int PWT, int SB>
 static int launch_bwd_sep(const RoiParams& p, const GT* go, int warps, int slabs, cudaStream_t s) {
     constexpr int CC = 32 * CPL;
-    auto kern = roi_align_bwd_sep_kernel<GT, CPL, CS, PHT, PWT>;
+    auto kern = roi_align_bwd_sep_kernel<GT, CPL, CS, PHT, PWT, SB>;
     const size_t smem = (size_t)warps * 32 * (CC + 1) * sizeof(float);
     if (smem > 24 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int cgroups = (int)ceil_div(p.C, CC * slabs);
@@ -618,15 +625,15 @@ static int launch_bwd_sep(const RoiParams& p, const GT* go, int warps, int slabs
 
 template <typename GT>
 static int dispatch_bwd_sep(const RoiParams& p, const GT* g, int cpl, int warps, int slabs, cudaStream_t s) {
-    if (cpl == 1) return launch_bwd_sep<GT, 1, 0, 0, 0>(p, g, warps, slabs, s);
-    if (p.C == 1024 && p.PH == 14 && p.PW == 14) return launch_bwd_sep<GT, 2, 1024, 14, 14>(p, g, warps, slabs, s);
-    if (p.C == 1024 && p.PH == 7 && p.PW == 7) return launch_bwd_sep<GT, 2, 1024, 7, 7>(p, g, warps, slabs, s);
-    return launch_bwd_sep<GT, 2, 0, 0, 0>(p, g, warps, slabs, s);
-}
-
-static int sep_env(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
+    const int sb = sep_env("COIN_ROI_BWD_SB", 16);
+    if (p.C == 1024 && p.PH == 14 && p.PW == 14) {
+        if (cpl == 1) return launch_bwd_sep<GT, 1, 1024, 14, 14, 16>(p, g, warps, slabs, s);
+        if (sb == 32) return launch_bwd_sep<GT, 2, 1024, 14, 14, 32>(p, g, warps, slabs, s);
+        return launch_bwd_sep<GT, 2, 1024, 14, 14, 16>(p, g, warps, slabs, s);
+    }
+    if (cpl == 1) return launch_bwd_sep<GT, 1, 0, 0, 0, 16>(p, g, warps, slabs, s);
+    if (p.C == 1024 && p.PH == 7 && p.PW == 7) return launch_bwd_sep<GT, 2, 1024, 7, 7, 16>(p, g, warps, slabs, s);
+    return launch_bwd_sep<GT, 2, 0, 0, 0, 16>(p, g, warps, slabs, s);
 }
 
 template <typename OutT>
@@ -658,11 +665,11 @@ int launch_roi_align_fwd_sep(const RoiParams& p, void* out, int out_dtype, cudaS
 
 
 int launch_roi_align_bwd_sep(const RoiParams& p, const void* grad_out, int grad_dtype, cudaStream_t s) {
-    const int cpl = p.C <= 32 ? 1 : 2;
+    const int cpl = p.C <= 32 ? 1 : (sep_env("COIN_ROI_BWD_CPL", 2) == 1 ? 1 : 2);
     const int R = p.PW <= 16 && p.PH >= 2 ? 2 : 1;
     int warps = sep_env("COIN_ROI_BWD_WARPS", (int)std::min<int64_t>(7, std::max<int64_t>(ceil_div(p.PH, R), 4)));
     warps = std::max(1, std::min(warps, 7));   // the kernel is compiled for <= 224 threads
-    int slabs = sep_env("COIN_ROI_BWD_SLABS", 4);
+    int slabs = sep_env("COIN_ROI_BWD_SLABS", p.PH * p.PW <= 64 ? 4 : 8);
     slabs = std::max(1, std::min(slabs, (int)ceil_div(p.C, 32 * cpl)));
     if (grad_dtype == COIN_F32) return dispatch_bwd_sep<float>(p, static_cast<const float*>(grad_out), cpl, warps, slabs, s);
     return dispatch_bwd_sep<__half>(p, static_cast<const __half*>(grad_out), cpl, warps, slabs, s);

@@ -10,6 +10,7 @@ struct RoiParams {
     coin_level_t lv[COIN_MAX_LEVELS];
     const float* rois;
     const int32_t* roi_level;
+    const int32_t* k_dev;   // optional device-side live RoI count (<= K): CTAs of RoIs beyond it exit
     int C, K, PH, PW, sampling_ratio, aligned;
 };
 

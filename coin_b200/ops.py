@@ -73,6 +73,13 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
 
 
+def _count(t: torch.Tensor) -> torch.Tensor:
+    """A device-side count: one int32 element (typically a view into a larger counts tensor)."""
+    if t.device.type != "cuda" or t.dtype != torch.int32 or t.numel() != 1:
+        raise ValueError("coin_b200: a device count must be a 1-element int32 CUDA tensor")
+    return t
+
+
 # ------------------------------------------------------------------------------------------------
 # ROIAlign
 # ------------------------------------------------------------------------------------------------
@@ -99,8 +106,10 @@ def _levels(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float]):
 
 def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
                       roi_level: Optional[torch.Tensor], output_size: Tuple[int, int], sampling_ratio: int,
-                      aligned: bool, out_dtype: torch.dtype, events: Optional[list] = None) -> torch.Tensor:
-    """events: optional list; a (start, end) CUDA-event pair bracketing the kernel launch is appended."""
+                      aligned: bool, out_dtype: torch.dtype, events: Optional[list] = None,
+                      k_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """events: optional list; a (start, end) CUDA-event pair bracketing the kernel launch is appended.
+    k_dev: optional device int32 live RoI count (<= K): rows of the result beyond it are not written."""
     rois = _f32c(rois, "rois")
     if rois.dim() != 2 or rois.shape[1] != 5:
         raise ValueError(f"coin_b200: rois must have shape [K, 5], got {tuple(rois.shape)}")
@@ -110,9 +119,14 @@ def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float
     if roi_level is not None:
         roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
     pair = _event_pair(events)
-    check(lib.coin_roi_align_fwd(_levels(feats_nhwc, scales), len(feats_nhwc), _ptr(rois), _ptr(roi_level), _ptr(out),
-                                 _dtype_code(out_dtype), c, k, ph, pw, int(sampling_ratio), int(bool(aligned)),
-                                 _stream()))
+    if k_dev is None:
+        check(lib.coin_roi_align_fwd(_levels(feats_nhwc, scales), len(feats_nhwc), _ptr(rois), _ptr(roi_level),
+                                     _ptr(out), _dtype_code(out_dtype), c, k, ph, pw, int(sampling_ratio),
+                                     int(bool(aligned)), _stream()))
+    else:
+        check(lib.coin_roi_align_fwd_dev(_levels(feats_nhwc, scales), len(feats_nhwc), _ptr(rois), _ptr(roi_level),
+                                         _ptr(out), _dtype_code(out_dtype), c, k, ph, pw, int(sampling_ratio),
+                                         int(bool(aligned)), _ptr(_count(k_dev)), _stream()))
     _event_close(pair)
     return out
 
@@ -410,3 +424,133 @@ def match_abc_narrow(raw, counts):
     return {"a_on": a_on[:na].long(), "a_off": a_off[:na].long(), "a_boxes": a_box[:na],
             "b_on": b_on[:nb].long(), "b_off": b_off[:nb].long(), "b_boxes": b_box[:nb],
             "c_on": c_on[nc_off:ncc].long(), "c_off": c_off[:nc_off].long()}
+
+
+# ------------------------------------------------------------------------------------------------
+# sync-free (device-count) variants: worst-case buffers + device int32 lengths, no host round trip
+# ------------------------------------------------------------------------------------------------
+def concat_rows(segments, width_out: Optional[int] = None, out_cap: Optional[int] = None):
+    """segments: list of (tensor [n, w] fp32, count_dev or None, prefix float). Returns (out [cap, width_out],
+    device int32 count). == torch.cat of the live prefixes (optionally with a leading prefix column)."""
+    n = len(segments)
+    arr = (_lib.CoinSeg * n)()
+    keep = []
+    width_in = int(segments[0][0].shape[1])
+    worst = 0
+    for i, (t, cnt, prefix) in enumerate(segments):
+        t = _f32c(t, "segment")
+        keep.append(t)
+        arr[i].ptr = t.data_ptr()
+        arr[i].count_dev = 0 if cnt is None else _count(cnt).data_ptr()
+        arr[i].count = int(t.shape[0])
+        arr[i].prefix = float(prefix)
+        worst += int(t.shape[0])
+    width_out = width_in if width_out is None else int(width_out)
+    cap = worst if out_cap is None else int(out_cap)
+    dev = keep[0].device
+    out = torch.empty((max(cap, 1), width_out), dtype=torch.float32, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    check(lib.coin_concat_rows(arr, n, width_in, width_out, _ptr(out), cap, _ptr(count), _stream()))
+    return out, count
+
+
+def iou_match_dev(gt: torch.Tensor, n_dev: Optional[torch.Tensor], boxes: torch.Tensor, m_dev: Optional[torch.Tensor],
+                  thresholds: Sequence[float], labels: Sequence[int], allow_low_quality: bool):
+    """iou_match with device-side live counts of gt rows / columns. Outputs have the capacity of `boxes`."""
+    gt, boxes = _boxes(gt, "gt_boxes"), _boxes(boxes, "boxes")
+    n, m = gt.shape[0], boxes.shape[0]
+    matches = torch.empty((m,), dtype=torch.int64, device=boxes.device)
+    mlabels = torch.empty((m,), dtype=torch.int8, device=boxes.device)
+    ws = torch.empty((max(n, 1),), dtype=torch.float32, device=boxes.device) if allow_low_quality else None
+    thr, lab = _matcher_cfg(thresholds, labels)
+    check(lib.coin_iou_match_dev(_ptr(gt), n, _ptr(None if n_dev is None else _count(n_dev)), _ptr(boxes), m,
+                                 _ptr(None if m_dev is None else _count(m_dev)), thr, len(thresholds), lab,
+                                 int(bool(allow_low_quality)), _ptr(matches), _ptr(mlabels), _ptr(None), _ptr(ws),
+                                 _stream()))
+    return matches, mlabels
+
+
+def relabel_roi_dev_(matches, labels, m_dev, len_a, len_b, len_c):
+    check(lib.coin_relabel_roi_dev(_ptr(matches), _ptr(labels), matches.numel(),
+                                   _ptr(None if m_dev is None else _count(m_dev)), _ptr(_count(len_a)),
+                                   _ptr(_count(len_b)), _ptr(_count(len_c)), _stream()))
+    return labels
+
+
+def relabel_rpn_dev_(matches, labels, len_a, len_c):
+    didx = torch.empty_like(matches)
+    dlab = torch.empty_like(labels)
+    check(lib.coin_relabel_rpn_dev(_ptr(matches), _ptr(labels), matches.numel(), _ptr(_count(len_a)),
+                                   _ptr(_count(len_c)), _ptr(didx), _ptr(dlab), _stream()))
+    return labels, matches, didx, dlab
+
+
+def match_abc_fields_dev(on: dict, off: dict, nd_dev: torch.Tensor, tag: str, iou_thr: float, weight_for_box_a: float):
+    """Knowledge separation + field gathers with the CLIP-detector detection count on the device.
+    on / off: dicts with gt_boxes [n,4], gt_classes int64 [n], scores [n], probs [n,k1] (off is padded to
+    its capacity; nd_dev holds the live count). Returns (A, B or None, C, counts): padded field dicts with
+    the reference's names and the device int32 counts [nA, nB, nC, status, nC_off, 0, 0, 0]."""
+    on_boxes, off_boxes = _boxes(on["gt_boxes"], "online boxes"), _boxes(off["gt_boxes"], "offline boxes")
+    on_cls, off_cls = _i64c(on["gt_classes"], "online classes"), _i64c(off["gt_classes"], "offline classes")
+    on_s, off_s = _f32c(on["scores"], "online scores"), _f32c(off["scores"], "offline scores")
+    on_p, off_p = _f32c(on["probs"], "online probs"), _f32c(off["probs"], "offline probs")
+    nc, nd = on_boxes.shape[0], off_boxes.shape[0]
+    k1 = int(on_p.shape[1])
+    dev = on_boxes.device
+    cap = nc * nd + nc + nd
+    i32 = lambda n: torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    i64 = lambda n: torch.empty((n,), dtype=torch.int64, device=dev)
+    a_on, a_off, b_on, b_off = i32(cap), i32(cap), i32(cap), i32(cap)
+    c_on, c_off = i32(nc + nd), i32(nc + nd)
+    a_box, b_box = f32(max(cap, 1), 4), f32(max(cap, 1), 4)
+    counts = torch.zeros((8,), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.coin_match_abc_workspace_bytes(nc, nd), dev)
+    code = {"RCNN": _lib.TAG_RCNN, "RPN": _lib.TAG_RPN}[tag]
+    check(lib.coin_match_abc_dev(_ptr(on_boxes), _ptr(on_cls), _ptr(on_s), nc, _ptr(off_boxes), _ptr(off_cls),
+                                 _ptr(off_s), nd, _ptr(_count(nd_dev)), code, float(iou_thr), float(weight_for_box_a),
+                                 cap, _ptr(a_on), _ptr(a_off), _ptr(a_box), _ptr(b_on), _ptr(b_off), _ptr(b_box),
+                                 _ptr(c_on), _ptr(c_off), _ptr(counts), _ptr(ws), ws.numel(), _stream()))
+
+    def pseudo(n, boxes, split):
+        d = {"gt_boxes": boxes}
+        if split:
+            d["gt_classes_offline"], d["gt_classes_online"] = i64(n), i64(n)
+        else:
+            d["gt_classes"] = i64(n)
+        d["gt_scores_online"], d["gt_scores_offline"] = f32(n), f32(n)
+        d["gt_probs_online"], d["gt_probs_offline"] = f32(n, k1), f32(n, k1)
+        return d
+
+    a = pseudo(max(cap, 1), a_box, False)
+    b = pseudo(max(cap, 1), b_box, True) if tag == "RCNN" else None
+    c = {"gt_boxes": f32(max(nc + nd, 1), 4), "gt_classes": i64(max(nc + nd, 1)), "gt_scores": f32(max(nc + nd, 1)),
+         "gt_probs": f32(max(nc + nd, 1), k1)}
+
+    def dets_struct(boxes, cls, s, p):
+        st = _lib.CoinDets()
+        st.boxes, st.classes, st.scores, st.probs = boxes.data_ptr(), cls.data_ptr(), s.data_ptr(), p.data_ptr()
+        return st
+
+    def pseudo_struct(d, kind):
+        st = _lib.CoinPseudo()
+        st.boxes = d["gt_boxes"].data_ptr()
+        if kind == "C":
+            st.classes, st.scores_online, st.probs_online = (d["gt_classes"].data_ptr(), d["gt_scores"].data_ptr(),
+                                                             d["gt_probs"].data_ptr())
+            return st
+        st.classes = (d["gt_classes_offline"] if kind == "B" else d["gt_classes"]).data_ptr()
+        if kind == "B":
+            st.classes_online = d["gt_classes_online"].data_ptr()
+        st.scores_online, st.scores_offline = d["gt_scores_online"].data_ptr(), d["gt_scores_offline"].data_ptr()
+        st.probs_online, st.probs_offline = d["gt_probs_online"].data_ptr(), d["gt_probs_offline"].data_ptr()
+        return st
+
+    on_st, off_st = dets_struct(on_boxes, on_cls, on_s, on_p), dets_struct(off_boxes, off_cls, off_s, off_p)
+    a_st, c_st = pseudo_struct(a, "A"), pseudo_struct(c, "C")
+    b_st = pseudo_struct(b, "B") if b is not None else None
+    check(lib.coin_abc_pack(ctypes.byref(on_st), nc, ctypes.byref(off_st), nd, _ptr(_count(nd_dev)), k1, code,
+                            _ptr(a_on), _ptr(a_off), _ptr(b_on), _ptr(b_off), _ptr(c_on), _ptr(c_off), _ptr(counts),
+                            ctypes.byref(a_st), ctypes.byref(b_st) if b_st is not None else None, ctypes.byref(c_st),
+                            cap, _stream()))
+    return a, b, c, counts

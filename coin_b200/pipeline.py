@@ -221,6 +221,182 @@ class RoIPathStep:
         out["summary"] = {"dets": n_det, "rpn_keep": n_rpn, "abc": [c2[:3] for c2 in counts2]}
         return out
 
+    # -- sync-free step: fixed launch sequence, device-side lengths, CUDA-graph capturable ------------
+    def run_static(self, d: Dict[str, torch.Tensor], backward: bool = True) -> Dict[str, object]:
+        """The same step as run() with NO host round trip: every variable-length set lives in a worst-case
+        buffer with its length in device memory (the *_dev entry points of libcoinops), so the launch
+        sequence is independent of the data and can be captured in a CUDA graph (capture()/replay()).
+        Returns padded tensors plus ``counts`` (one device int32 vector); finalize() reads the counts back
+        once and narrows the buffers to the dict format of run()."""
+        main = torch.cuda.current_stream()
+        n_img = self.shape.images
+        side = self._side_streams(3 * n_img + 1) if self.overlap else [main] * (3 * n_img + 1)
+        start = main.record_event()
+        for st in side:
+            if st is not main:
+                st.wait_event(start)
+        out = self._run_static(d, backward, side)
+        for st in side:
+            if st is not main:
+                main.wait_stream(st)
+        return out
+
+    def _run_static(self, d, backward, streams) -> Dict[str, object]:
+        sh, dev = self.shape, self.device
+        n_img = sh.images
+        img_size = (sh.height, sh.width)
+        s_roi, s_img = streams[0], streams[1:]
+        scale = (1.0 / sh.stride,)
+        size = (sh.pooled, sh.pooled)
+        out: Dict[str, object] = {"dets": [], "abc": [], "roi_labels": [], "rpn_labels": [], "rpn_keep": []}
+        counts: List[torch.Tensor] = []     # device int32 tensors, concatenated at the end
+        slots: Dict[str, int] = {}          # name -> offset into the concatenated counts vector
+
+        def slot(name, t):
+            slots[name] = sum(int(c.numel()) for c in counts)
+            counts.append(t.view(-1))
+
+        with torch.cuda.stream(s_roi):
+            nhwc = ops.to_nhwc_f32(d["features"])
+            rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
+                              for i in range(n_img)])
+            out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32)
+            if backward:
+                n, c, h, w = d["features"].shape
+                out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
+                                                              0, True, [torch.float32])[0]
+
+        c_segs = []
+        for i in range(n_img):
+            st_t, st_p = s_img[i], s_img[n_img + i]
+            with torch.cuda.stream(st_p):                                                                 # S1
+                keep, nkeep = ops.batched_nms(d[f"{i}.rpn_boxes"], d[f"{i}.rpn_scores"], None, self.RPN_NMS_THRESH,
+                                              "plain", sh.rpn_post_nms, sync=False)
+            with torch.cuda.stream(st_t):
+                dec = ops.apply_deltas(d[f"{i}.teacher_deltas"], d[f"{i}.teacher_rois"], self.BBOX_WEIGHTS,
+                                       clip_to=img_size)                                                    # T1
+                b, s, p, c, roi_idx, ndet = ops.det_postprocess(dec, d[f"{i}.teacher_probs"], img_size,
+                                                                self.SCORE_THRESH, self.NMS_THRESH, self.TOPK,
+                                                                sync=False)                                 # T2
+                cloud = {"gt_boxes": ops.boxes_scale_flip(d[f"{i}.cloud.gt_boxes"], sh.width / (sh.width * ORIG_SCALE),
+                                                          sh.height / (sh.height * ORIG_SCALE), "no", img_size),  # T3
+                         "gt_classes": d[f"{i}.cloud.gt_classes"], "scores": d[f"{i}.cloud.scores"],
+                         "probs": d[f"{i}.cloud.probs"]}
+                clip = {"gt_boxes": b, "gt_classes": c, "scores": s, "probs": p}
+                det_done = st_t.record_event()
+            out["dets"].append({"pred_boxes": b, "scores": s, "probs": p, "pred_classes": c, "roi_index": roi_idx})
+            out["rpn_keep"].append(keep)
+            out.setdefault("_keepalive", []).append(cloud)   # read by another stream: must outlive this iteration
+            slot(f"det{i}", ndet)
+            slot(f"rpn{i}", nkeep)
+
+            per_tag = {}
+            # tag RCNN continues on the teacher stream, tag RPN on the image's third stream
+            for tag, st in (("RCNN", st_t), ("RPN", s_img[2 * n_img + i])):
+                st.wait_event(det_done)
+                with torch.cuda.stream(st):
+                    a, bb, cc, cnt = ops.match_abc_fields_dev(cloud, clip, ndet, tag, self.MATCH_THRESH, self.w_a)  # T4
+                    slot(f"abc{i}.{tag}", cnt)
+                    per_tag[tag] = (a, bb, cc)
+                    n_a, n_b, n_c = cnt[0:1], cnt[1:2], cnt[2:3]
+                    if tag == "RCNN":
+                        gt, n_gt = ops.concat_rows([(a["gt_boxes"], n_a, 0.0), (bb["gt_boxes"], n_b, 0.0),
+                                                    (cc["gt_boxes"], n_c, 0.0)])
+                        props, n_props = ops.concat_rows([(d[f"{i}.proposals"], None, 0.0), (a["gt_boxes"], n_a, 0.0),
+                                                          (bb["gt_boxes"], n_b, 0.0)])   # add_ground_truth_to_proposals
+                        idx, lab = ops.iou_match_dev(gt, n_gt, props, n_props, [0.5], [0, 1], False)       # S3
+                        ops.relabel_roi_dev_(idx, lab, n_props, n_a, n_b, n_c)
+                        out["roi_labels"].append((idx, lab))
+                        slot(f"props{i}", n_props)
+                        c_segs.append((cc["gt_boxes"], n_c, float(i), st.record_event()))
+                    else:
+                        gt2, n_gt2 = ops.concat_rows([(a["gt_boxes"], n_a, 0.0), (cc["gt_boxes"], n_c, 0.0)])
+                        idx2, lab2 = ops.iou_match_dev(gt2, n_gt2, self.anchors, None, [0.3, 0.7], [0, -1, 1], True)  # S2
+                        out["rpn_labels"].append(ops.relabel_rpn_dev_(idx2, lab2, n_a, n_c))
+            out["abc"].append(per_tag)
+
+        # ---- ROIAlign forward on the private (C) boxes of every image, behind the big kernels
+        for seg in c_segs:
+            s_roi.wait_event(seg[3])
+        with torch.cuda.stream(s_roi):
+            c_rois, n_c_rois = ops.concat_rows([seg[:3] for seg in c_segs], width_out=5)
+            out["pooled_c"] = ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32,
+                                                    k_dev=n_c_rois)
+            slot("c_rois", n_c_rois)
+            cat_done = s_roi.record_event()
+        torch.cuda.current_stream().wait_event(cat_done)
+        for st in streams:
+            if st is not torch.cuda.current_stream():
+                torch.cuda.current_stream().wait_stream(st)
+        out["counts"] = torch.cat(counts)
+        out["slots"] = slots
+        return out
+
+    def finalize(self, out: Dict[str, object], counts_host=None) -> Dict[str, object]:
+        """One D2H read of the counts vector, then narrow every padded buffer: the result has the format
+        of run() (and of oracle/pipeline_ref.run)."""
+        cnt = (out["counts"].cpu() if counts_host is None else counts_host).tolist()
+        sl = out["slots"]
+        n_img = self.shape.images
+        res: Dict[str, object] = {"dets": [], "abc": [], "roi_labels": [], "rpn_labels": out["rpn_labels"],
+                                  "rpn_keep": [], "pooled": out["pooled"]}
+        if "grad_features" in out:
+            res["grad_features"] = out["grad_features"]
+        summary_abc = []
+        for i in range(n_img):
+            nd = cnt[sl[f"det{i}"]]
+            res["dets"].append({k: v[:nd] for k, v in out["dets"][i].items()})
+            res["rpn_keep"].append(out["rpn_keep"][i][: cnt[sl[f"rpn{i}"]]])
+            per_tag = {}
+            for tag in ("RCNN", "RPN"):
+                o = sl[f"abc{i}.{tag}"]
+                na, nb, ncc, status = cnt[o], cnt[o + 1], cnt[o + 2], cnt[o + 3]
+                if status & 16:
+                    raise AssertionError("match_abc: a cloud self-cluster has a single class (util.py:488 assert)")
+                if status & 8:
+                    raise AssertionError("match_abc: a duplicate group holds several boxes of the matched class")
+                if status & 4:
+                    raise RuntimeError("match_abc: pair capacity exceeded")
+                a, b, c = out["abc"][i][tag]
+                per_tag[tag] = ({k: v[:na] for k, v in a.items()},
+                                None if b is None else {k: v[:nb] for k, v in b.items()},
+                                {k: v[:ncc] for k, v in c.items()})
+                summary_abc.append([na, nb, ncc])
+            res["abc"].append(per_tag)
+            m = cnt[sl[f"props{i}"]]
+            idx, lab = out["roi_labels"][i]
+            res["roi_labels"].append((idx[:m], lab[:m]))
+        res["pooled_c"] = out["pooled_c"][: cnt[sl["c_rois"]]]
+        res["summary"] = {"dets": [cnt[sl[f"det{i}"]] for i in range(n_img)],
+                          "rpn_keep": [cnt[sl[f"rpn{i}"]] for i in range(n_img)], "abc": summary_abc}
+        return res
+
+    # -- CUDA graph ---------------------------------------------------------------------------------
+    def capture(self, d: Dict[str, torch.Tensor], backward: bool = True, warmup: int = 2):
+        """Captures run_static over the (static) input tensors ``d`` into a CUDA graph. Later steps copy
+        new inputs into the same tensors (copy_inputs) and call replay()."""
+        self._graph_in = d
+        cap_stream = torch.cuda.Stream(device=self.device)
+        cap_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap_stream):
+            for _ in range(warmup):       # allocator warm-up and lazy module loading outside the capture
+                self.run_static(d, backward)
+        torch.cuda.current_stream().wait_stream(cap_stream)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=cap_stream):
+            self._graph_out = self.run_static(d, backward)
+        return self._graph_out
+
+    def copy_inputs(self, src: Dict[str, torch.Tensor]) -> None:
+        """Copies one step's inputs (pinned host or device tensors) into the captured graph's input tensors."""
+        for k, v in self._graph_in.items():
+            v.copy_(src[k], non_blocking=True)
+
+    def replay(self) -> Dict[str, object]:
+        self._graph.replay()
+        return self._graph_out
+
     @staticmethod
     def _pack(r, cloud, clip, tag):
         """Gather the reference's A / B / C fields (trainer.py:393-455) from the index lists."""

@@ -254,6 +254,95 @@ int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float
                    int32_t* b_off, float* b_boxes, int32_t* c_on, int32_t* c_off, int32_t* counts,
                    void* ws, size_t ws_bytes, coin_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Sync-free ("device-count") variants
+ *   In the reference every stage boundary of CoinTrainer.run_step (coin/engine/trainer.py:160-218)
+ *   is a host round trip: nonzero()/tolist()/len() on device tensors decide the shapes of the next
+ *   stage (trainer.py:364-391,469; clip_roi_heads.py:345-362; rpn.py:209-228; fast_rcnn.py:151-166).
+ *   These entry points take the live lengths as DEVICE int32 values next to host-known capacities:
+ *   every launch is sized for the capacity and threads beyond the live length exit, so the whole
+ *   step is a fixed launch sequence (capturable in a CUDA graph) with one count read-back at the end.
+ * ------------------------------------------------------------------------------------------- */
+
+/* coin_roi_align_fwd with a device-side live RoI count *k_dev <= K_cap (NULL: K_cap). Rows of `out`
+ * beyond the live count are left untouched. */
+int coin_roi_align_fwd_dev(const coin_level_t* levels_host, int nlevels, const float* rois,
+                           const int32_t* roi_level, void* out, int out_dtype, int C, int K_cap, int PH,
+                           int PW, int sampling_ratio, int aligned, const int32_t* k_dev,
+                           coin_stream_t stream);
+
+/* coin_iou_match with device-side live counts *n_dev <= N_cap (gt rows) and *m_dev <= M_cap (columns);
+ * either may be NULL. A live N of 0 applies Matcher's empty-matrix rule on the device. Entries of the
+ * outputs beyond the live M are left untouched. row_max_ws: fp32 [N_cap] iff allow_low_quality. */
+int coin_iou_match_dev(const float* gt, int64_t N_cap, const int32_t* n_dev, const float* boxes,
+                       int64_t M_cap, const int32_t* m_dev, const float* thresholds_host, int nthr,
+                       const int8_t* labels_host, int allow_low_quality, int64_t* matches,
+                       int8_t* match_labels, float* matched_vals, float* row_max_ws, coin_stream_t stream);
+
+/* coin_relabel_roi / coin_relabel_rpn with the pseudo-GT set lengths read from device memory
+ * (clip_roi_heads.py:358-362: C rows are [len_a+len_b, len_a+len_b+len_c); rpn.py:214-228). */
+int coin_relabel_roi_dev(const int64_t* matches, int8_t* match_labels, int64_t M_cap, const int32_t* m_dev,
+                         const int32_t* len_a, const int32_t* len_b, const int32_t* len_c,
+                         coin_stream_t stream);
+int coin_relabel_rpn_dev(int64_t* matches, int8_t* labels, int64_t M, const int32_t* len_a,
+                         const int32_t* len_c, int64_t* distill_idx, int8_t* distill_labels,
+                         coin_stream_t stream);
+
+/* coin_match_abc with the CLIP-detector detection count read from device memory (*nd_dev <= nd_cap):
+ * chains behind coin_det_postprocess without reading its count back. */
+int coin_match_abc_dev(const float* on_boxes, const int64_t* on_classes, const float* on_scores, int64_t nc,
+                       const float* off_boxes, const int64_t* off_classes, const float* off_scores,
+                       int64_t nd_cap, const int32_t* nd_dev, int tag, float iou_thr, float weight_for_box_a,
+                       int64_t cap_pairs, int32_t* a_on, int32_t* a_off, float* a_boxes, int32_t* b_on,
+                       int32_t* b_off, float* b_boxes, int32_t* c_on, int32_t* c_off, int32_t* counts,
+                       void* ws, size_t ws_bytes, coin_stream_t stream);
+
+/* One segment of a row concatenation: `count` rows at `ptr` (or *count_dev <= count rows when
+ * count_dev is non-NULL); `prefix` is the value of the extra leading column, if any. */
+typedef struct {
+    const float* ptr;
+    const int32_t* count_dev;
+    int64_t count;
+    float prefix;
+} coin_seg_t;
+
+/* out = cat(segments) row-wise; width_out == width_in, or width_in + 1 to prepend the per-segment
+ * `prefix` column (the batch index of convert_boxes_to_pooler_format). *out_count (device int32, may be
+ * NULL) receives the total number of rows written (clamped to out_cap). Replaces Boxes.cat /
+ * add_ground_truth_to_proposals (clip_roi_heads.py:345-353, rpn.py:209-212) for device-length sets. */
+int coin_concat_rows(const coin_seg_t* segs_host, int nseg, int width_in, int width_out, float* out,
+                     int64_t out_cap, int32_t* out_count, coin_stream_t stream);
+
+/* One detection set (device pointers): boxes [n,4], classes int64 [n], scores [n], probs [n,k1]. */
+typedef struct {
+    const float* boxes;
+    const int64_t* classes;
+    const float* scores;
+    const float* probs;
+} coin_dets_t;
+
+/* One pseudo-label set of match_dual_teacher, capacity rows each (trainer.py:393-455). A and B: `classes`
+ * = the CLIP-detector ("offline") class, classes_online (B only) = the cloud class, scores/probs of both
+ * sides; their boxes are the a_boxes / b_boxes of coin_match_abc. C: boxes, classes, scores_online = the
+ * single score, probs_online = the single prob row (the *_offline members are ignored). */
+typedef struct {
+    float* boxes;
+    int64_t* classes;
+    int64_t* classes_online;
+    float* scores_online;
+    float* scores_offline;
+    float* probs_online;
+    float* probs_offline;
+} coin_pseudo_t;
+
+/* Gathers the A / B / C fields from the index lists and counts of coin_match_abc[_dev]. */
+int coin_abc_pack(const coin_dets_t* online_host, int64_t nc, const coin_dets_t* offline_host,
+                  int64_t nd_cap, const int32_t* nd_dev, int k1, int tag, const int32_t* a_on,
+                  const int32_t* a_off, const int32_t* b_on, const int32_t* b_off, const int32_t* c_on,
+                  const int32_t* c_off, const int32_t* counts, const coin_pseudo_t* a_out_host,
+                  const coin_pseudo_t* b_out_host, const coin_pseudo_t* c_out_host, int64_t cap_pairs,
+                  coin_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -61,3 +61,54 @@ def test_step_full_size_properties(dev):
     for i in range(shape.images):
         idx, lab = out["roi_labels"][i]
         assert int(idx.min()) >= 0 and set(lab.unique().tolist()) <= {-1, 0, 1}
+
+
+@pytest.mark.parametrize("w_a", [1.0, 0.5])
+def test_static_step_and_graph_replay_match_oracle(dev, w_a):
+    """The sync-free step (device-side lengths, *_dev entry points): eager, and captured in a CUDA graph and
+    replayed on fresh inputs, against the CPU oracle."""
+    shape = synth.SHAPES["tiny"]
+    batch = synth.image_batch(shape)
+    step = pipeline.RoIPathStep(shape, dev, weight_for_box_a=w_a)
+    budget = 0.0 if w_a == 1.0 else 1e-3
+    want = pipeline_ref.run(batch, backward=True, weight_for_box_a=w_a)
+    got = step.finalize(step.run_static(step.to_device(batch), backward=True))
+    pipeline_ref.compare(got, want, label_budget=budget)
+    assert got["summary"]["dets"] == want["summary"]["dets"]
+    # capture on the inputs of ANOTHER batch, then replay on this one: the graph must not bake in any length
+    other = synth.image_batch(shape, seed=synth.SEED + 7)
+    d_static = step.to_device(other)
+    step.capture(d_static, backward=True)
+    want_other = pipeline_ref.run(other, backward=True, weight_for_box_a=w_a)
+    pipeline_ref.compare(step.finalize(step.replay()), want_other, label_budget=budget)
+    step.copy_inputs(step.host_inputs(batch))
+    got2 = step.finalize(step.replay())
+    pipeline_ref.compare(got2, want, label_budget=budget)
+    assert got2["summary"] == got["summary"]
+
+
+def test_static_step_equals_eager_step_full_size(dev):
+    """configs[1] at full size: the graph-replayed sync-free step returns exactly what the eager step returns."""
+    shape = synth.SHAPES["foggy_roi_head"]
+    batch = synth.image_batch(shape)
+    step = pipeline.RoIPathStep(shape, dev)
+    d = step.to_device(batch)
+    eager = step.run(d, backward=False)
+    step.capture(d, backward=False)
+    got = step.finalize(step.replay())
+    assert got["summary"]["dets"] == eager["summary"]["dets"] and got["summary"]["rpn_keep"] == eager["summary"]["rpn_keep"]
+    for i in range(shape.images):
+        for k, v in eager["dets"][i].items():
+            assert torch.equal(got["dets"][i][k], v), k
+        assert torch.equal(got["rpn_keep"][i], eager["rpn_keep"][i])
+        for tag in ("RCNN", "RPN"):
+            for ge, ee in zip(got["abc"][i][tag], eager["abc"][i][tag]):
+                assert (ge is None) == (ee is None)
+                if ee is not None:
+                    for k, v in ee.items():
+                        assert torch.equal(ge[k], v), (i, tag, k)
+        for ge, ee in zip(got["roi_labels"][i], eager["roi_labels"][i]):
+            assert torch.equal(ge, ee)
+        for ge, ee in zip(got["rpn_labels"][i], eager["rpn_labels"][i]):
+            assert torch.equal(ge, ee)
+    assert torch.equal(got["pooled"], eager["pooled"]) and torch.equal(got["pooled_c"], eager["pooled_c"])
