@@ -181,54 +181,67 @@ def main():
     d = step.h2d(pinned)
     torch.cuda.synchronize()
 
-    # ---- device-resident throughput -------------------------------------------------------------
+    # ---- the step as ONE CUDA graph: run_static (device-side lengths, no host round trip) captured once,
+    #      with an external CUDA-event pair around each of the two ROIAlign kernels inside the graph
     ev = {"fwd": [], "bwd": []}
+    launches0 = _lib.lib.coin_launch_count()
+    step.run_static(d, backward=True)              # eager once: counts the launches of one step
+    torch.cuda.synchronize()
+    launches_per_step = _lib.lib.coin_launch_count() - launches0
+    step.kernel_events = ev
+    step.capture(d, backward=True)                 # graph inputs = the resident tensors `d`
     step.kernel_events = None
+
+    # ---- device-resident throughput: K graph replays back to back, inputs already in HBM ---------------
     for _ in range(max(args.warmup, 3)):
-        step.run(d, backward=True)
+        step.replay()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = _lib.lib.coin_launch_count()
-    step.kernel_events = ev
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record()
     for _ in range(args.steps):
-        out = step.run(d, backward=True)
+        out = step.replay()
     t1.record()
     barrier()
-    launches = _lib.lib.coin_launch_count() - launches0
     clocks = sampler.stop()
-    step.kernel_events = None
     ms = t0.elapsed_time(t1)
-    k_fwd = statistics.mean(a.elapsed_time(b) for a, b in ev["fwd"])
-    k_bwd = statistics.mean(a.elapsed_time(b) for a, b in ev["bwd"])
+    launches = launches_per_step * args.steps
+    # kernel durations inside the graph: replay, then read the external event pairs (one sample per replay)
+    fwd_ms, bwd_ms = [], []
+    for _ in range(args.steps):
+        step.replay()
+        torch.cuda.synchronize()
+        fwd_ms.append(ev["fwd"][0][0].elapsed_time(ev["fwd"][0][1]))
+        bwd_ms.append(ev["bwd"][0][0].elapsed_time(ev["bwd"][0][1]))
+    k_fwd, k_bwd = statistics.mean(fwd_ms), statistics.mean(bwd_ms)
 
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the results, every step ---------
-    res = step.result_tensors(out)
-    host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res]
-    d2h_bytes = sum(t.numel() * t.element_size() for t in res)
+    # ---- end to end: pinned host inputs -> H2D -> graph replay -> counts D2H -> live results D2H, every step
     h2d_bytes = step.input_bytes(pinned)
+    host_cache = {}
 
     def e2e_step():
-        dd = step.h2d(pinned)
-        o = step.run(dd, backward=True)
-        for t, h in zip(step.result_tensors(o), host_out):
-            if t.shape == h.shape:
-                h.copy_(t, non_blocking=True)
-            else:  # variable-length results: copy into a fresh pinned buffer of the right size
-                h2 = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                h2.copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # results are on the host when the step ends
+        step.copy_inputs(pinned)                                   # H2D into the graph's input tensors
+        o = step.replay()
+        res = step.result_tensors(step.finalize(o))                # one D2H of the counts (sync), then narrow
+        nbytes = 0
+        for i, t in enumerate(res):
+            h = host_cache.get(i)
+            if h is None or h.numel() < t.numel() or h.dtype != t.dtype:
+                h = host_cache[i] = torch.empty((max(t.numel(), 1),), dtype=t.dtype).pin_memory()
+            h[: t.numel()].copy_(t.reshape(-1), non_blocking=True)
+            nbytes += t.numel() * t.element_size()
+        torch.cuda.current_stream().synchronize()                  # results are on the host when the step ends
+        return nbytes + o["counts"].numel() * 4
 
     for _ in range(3):
-        e2e_step()
+        d2h_bytes = e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        e2e_step()
+        d2h_bytes = e2e_step()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -269,14 +282,18 @@ def main():
                            "pooled": shape.pooled, "feature_map": [n, c, h, w], "classes": shape.classes,
                            "teacher_rois": shape.teacher_rois, "rpn_pre_nms": shape.rpn_pre_nms,
                            "l2": "per-step working set (2 x 1.23 GB pooled/grad tensors) >> 126 MB L2",
+                           "execution": "one CUDA graph per step (sync-free step, device-side lengths); ROIAlign "
+                                        "forward/backward overlap the teacher/matching branch on separate streams",
+                           "kernel_timing": "external CUDA-event pairs captured inside the graph around the two "
+                                            "ROIAlign kernels, read after each of `steps` extra replays",
                            "launches_per_step": launches / args.steps},
                 "clocks": clocks,
                 "e2e": {"value": world * n * args.steps / (ms_e2e / 1e3), "unit": UNIT,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps,
                         "boundary": "pinned host inputs (feature map, RoIs, deltas, scores, cloud detections, RPN "
-                                    "boxes) -> device; detections, A/B/C sets, labels, keep lists and the "
-                                    "feature-map gradient -> pinned host"},
+                                    "boxes) -> device; graph replay; lengths -> host (1 sync); detections, A/B/C "
+                                    "sets, labels, keep lists and the feature-map gradient -> pinned host"},
                 "gpu_launches": int(launches),
                 "roofline": roofline}
         # CPU baseline: N=1 only, rank 0, bounded sample = one image of the batch through every stage

@@ -58,7 +58,10 @@ def _dtype_code(dt: torch.dtype) -> int:
 def _event_pair(events):
     if events is None:
         return None
-    pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    # inside a CUDA-graph capture the pair becomes two event-record NODES (external events): every replay
+    # re-records them, so elapsed_time() after a replay is the kernel's duration inside the graph
+    ext = torch.cuda.is_current_stream_capturing()
+    pair = (torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext))
     pair[0].record()
     events.append(pair)
     return pair

@@ -260,11 +260,14 @@ class RoIPathStep:
             nhwc = ops.to_nhwc_f32(d["features"])
             rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
                               for i in range(n_img)])
-            out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32)
+            ev = self.kernel_events
+            out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
+                                                  events=ev["fwd"] if ev else None)
             if backward:
                 n, c, h, w = d["features"].shape
                 out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
-                                                              0, True, [torch.float32])[0]
+                                                              0, True, [torch.float32],
+                                                              events=ev["bwd"] if ev else None)[0]
 
         c_segs = []
         for i in range(n_img):
@@ -378,9 +381,11 @@ class RoIPathStep:
         self._graph_in = d
         cap_stream = torch.cuda.Stream(device=self.device)
         cap_stream.wait_stream(torch.cuda.current_stream())
+        ev, self.kernel_events = self.kernel_events, None   # timing events belong to the captured launches only
         with torch.cuda.stream(cap_stream):
             for _ in range(warmup):       # allocator warm-up and lazy module loading outside the capture
                 self.run_static(d, backward)
+        self.kernel_events = ev
         torch.cuda.current_stream().wait_stream(cap_stream)
         torch.cuda.synchronize(self.device)
         self._graph = torch.cuda.CUDAGraph()
