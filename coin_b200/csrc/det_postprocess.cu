@@ -169,7 +169,7 @@ extern "C" int coin_det_postprocess(const float* boxes, const float* scores, int
     const unsigned rb = (unsigned)ceil_div(R, 128);
     dp_rows_kernel<<<rb, 128, 0, s>>>(boxes, scores, (int)R, k1, kreg, score_thresh, w.row_valid, w.row_cnt);
     if (int rc = check_launch("dp_rows_kernel")) return rc;
-    dp_scan_kernel<<<1, 1024, 0, s>>>(w.row_valid, w.row_cnt, (int)R, w.row_rank, w.row_off, w.n_cand);
+    dp_scan_kernel<<<1, 256, 0, s>>>(w.row_valid, w.row_cnt, (int)R, w.row_rank, w.row_off, w.n_cand);
     if (int rc = check_launch("dp_scan_kernel")) return rc;
     dp_compact_kernel<<<rb, 128, 0, s>>>(boxes, scores, (int)R, k1, kreg, img_h, img_w, score_thresh, w.row_valid,
                                          w.row_rank, w.row_off, w.cand_box, w.cand_score, w.cand_cls, w.cand_row, w.cand_src);

@@ -95,7 +95,7 @@ __global__ void gather_sorted_kernel(const uint64_t* __restrict__ keys, const fl
 }
 
 // Single-CTA path for n <= kSmallSort: key generation, bitonic sort, max-reduce and gather fused.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 small_sort_gather_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes,
                          const int64_t* __restrict__ idxs, int n_cap, const int32_t* __restrict__ n_dev,
                          int strategy_in, float4* __restrict__ sboxes, int32_t* __restrict__ scls,
@@ -154,10 +154,16 @@ small_sort_gather_kernel(const float* __restrict__ scores, const float4* __restr
 }
 
 // 64 x (4*64) tile of the upper-triangular suppression mask per CTA; row-major [n][colblocks] so
-// that the sweep reads whole rows coalesced. Bits are set only for j > i.
+// that the sweep reads whole rows coalesced. Bits are set only for j > i. For the diagonal tiles the
+// transposed word is emitted as well: lower[i] = { j < i in the same 64-row tile : IoU(j, i) > thr }
+// (IoU is bitwise symmetric), which lets the sweep resolve a tile by fixed-point iteration.
+// Pairs with an empty intersection are rejected before the division (their IoU is 0 or NaN, never > thr
+// for thr >= 0); FAST = false keeps the plain evaluation for negative thresholds.
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ scls,
-                const int32_t* __restrict__ meta, int colblocks, float thr, uint64_t* __restrict__ mask) {
+                const int32_t* __restrict__ meta, int colblocks, float thr, uint64_t* __restrict__ mask,
+                uint64_t* __restrict__ lower) {
     const int n = meta[0];
     const bool same_class_only = meta[1] == COIN_NMS_VANILLA;
     const int rt = blockIdx.y;                 // row tile
@@ -184,81 +190,118 @@ nms_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ s
     const float area_a = box_area(a);
     const int32_t cls_a = __ldg(scls + i);
     const int jn = min(64, n - ct * 64);
-    const int j0 = (ct == rt) ? r + 1 : 0;
-    uint64_t word = 0;
-    for (int j = j0; j < jn; ++j) {
-        const bool cls_ok = !same_class_only || cc[threadIdx.y][j] == cls_a;
-        if (cls_ok && iou_tv(a, area_a, cb[threadIdx.y][j], ca[threadIdx.y][j]) > thr) word |= 1ull << j;
+    const bool diag = ct == rt;
+    uint64_t word = 0, low = 0;
+    for (int j = diag ? 0 : 0; j < jn; ++j) {
+        if (diag && j == r) continue;
+        const float4 b = cb[threadIdx.y][j];
+        bool hit;
+        if (FAST) {
+            const float w = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+            const float h = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+            if (!(w > 0.0f && h > 0.0f)) continue;     // empty intersection (or NaN): IoU is 0 or NaN
+            const float inter = w * h;
+            hit = inter / (area_a + ca[threadIdx.y][j] - inter) > thr;
+        } else {
+            hit = iou_tv(a, area_a, b, ca[threadIdx.y][j]) > thr;
+        }
+        if (hit && (!same_class_only || cc[threadIdx.y][j] == cls_a)) {
+            if (!diag || j > r) word |= 1ull << j; else low |= 1ull << j;
+        }
     }
     mask[(size_t)i * colblocks + ct] = word;
+    if (diag) lower[i] = low;
 }
 
-// Single-CTA sweep over 64-row tiles: the intra-tile dependency chain is resolved by one thread on
-// 64-bit words, the kept rows are then OR-ed into the `removed` bit-vector by all threads.
-__global__ void __launch_bounds__(1024)
-nms_sweep_kernel(const uint64_t* __restrict__ mask, const int32_t* __restrict__ order,
-                 const int32_t* __restrict__ meta, int stride, int64_t max_keep, int64_t* __restrict__ keep,
-                 int32_t* __restrict__ nkeep) {
+// Single-CTA sweep over 64-row tiles. Warp 0 resolves a tile by FIXED-POINT iteration on the transposed
+// diagonal words: kept = alive & ~any(lower & kept), repeated until stable (the unique solution of the
+// greedy recurrence; a few rounds instead of a 64-step serial chain). The other warps OR the mask rows of
+// the PREVIOUS tile's kept boxes into the `removed` bit-vector one tile behind (each thread owns its
+// columns, no atomics); the one column warp 0 needs immediately (tile t-1 -> column t) is prefetched by
+// warp 0 itself before the kept set is known. 256 threads / ~2 KB of static shared memory: the CTA fits
+// next to resident HBM-bound kernels of other streams.
+__global__ void __launch_bounds__(256)
+nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__ lower,
+                 const int32_t* __restrict__ order, const int32_t* __restrict__ meta, int stride, int64_t max_keep,
+                 int64_t* __restrict__ keep, int32_t* __restrict__ nkeep) {
     extern __shared__ uint64_t removed[];  // colblocks words
     const int n = meta[0];
     const int colblocks = (n + 63) >> 6;   // live column blocks; `stride` is the row pitch of `mask`
-    __shared__ uint64_t diag[2][64];
-    __shared__ uint64_t s_kept;
-    __shared__ int s_krow[64];
-    for (int c = threadIdx.x; c < colblocks; c += blockDim.x) removed[c] = 0;
-    if (threadIdx.x < 64) diag[0][threadIdx.x] = threadIdx.x < n ? mask[(size_t)threadIdx.x * stride] : 0;
+    __shared__ uint64_t s_kept[2];
+    __shared__ int s_krow[2][64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < colblocks; c += blockDim.x) removed[c] = 0;
+    if (tid < 2) s_kept[tid] = 0;
     __syncthreads();
     int64_t nk = 0;
     const int64_t limit = max_keep >= 0 ? max_keep : (int64_t)n;
+    uint64_t pref0 = 0, pref1 = 0;          // warp 0: mask[(t-1)*64 + lane (+32)][t]
+    uint64_t low0 = 0, low1 = 0;            // warp 0: lower words of tile t
+    if (warp == 0) {
+        if (lane < n) low0 = lower[lane];
+        if (lane + 32 < n) low1 = lower[lane + 32];
+    }
     for (int t = 0; t < colblocks && nk < limit; ++t) {
         const int buf = t & 1;
-        const int nr = min(64, n - t * 64);
-        // prefetch next tile's diagonal words (independent of `removed`)
-        uint64_t next_diag = 0;
-        if (threadIdx.x < 64 && t + 1 < colblocks) {
-            const int row = (t + 1) * 64 + threadIdx.x;
-            if (row < n) next_diag = mask[(size_t)row * stride + t + 1];
-        }
-        if (threadIdx.x == 0) {
-            uint64_t cur = removed[t];
+        if (warp == 0) {
+            const uint64_t prev = t > 0 ? s_kept[buf ^ 1] : 0ull;
+            uint64_t v = ((prev >> lane) & 1ull ? pref0 : 0ull) | ((prev >> (lane + 32)) & 1ull ? pref1 : 0ull);
+            const uint32_t vlo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
+            const uint32_t vhi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
+            uint64_t cur = removed[t] | ((uint64_t)vhi << 32 | vlo);
+            const int nr = min(64, n - t * 64);
             if (nr < 64) cur |= ~0ull << nr;
-            uint64_t kept = 0;
-#pragma unroll
-            for (int r = 0; r < 64; ++r) {
-                const uint64_t alive = ((cur >> r) & 1ull) ^ 1ull;
-                kept |= alive << r;
-                cur |= alive ? diag[buf][r] : 0ull;
+            // prefetch for the next tile (independent of this tile's result)
+            uint64_t npref0 = 0, npref1 = 0, nlow0 = 0, nlow1 = 0;
+            if (t + 1 < colblocks) {
+                const int r0 = t * 64 + lane, r1 = r0 + 32;
+                if (r0 < n) npref0 = mask[(size_t)r0 * stride + t + 1];
+                if (r1 < n) npref1 = mask[(size_t)r1 * stride + t + 1];
+                const int q0 = (t + 1) * 64 + lane, q1 = q0 + 32;
+                if (q0 < n) nlow0 = lower[q0];
+                if (q1 < n) nlow1 = lower[q1];
             }
-            // honour max_keep: drop kept rows beyond the limit
-            int64_t room = limit - nk;
-            if ((int64_t)__popcll(kept) > room) {
-                uint64_t trimmed = 0, k = kept;
-                for (int64_t q = 0; q < room; ++q) { trimmed |= k & (~k + 1); k &= k - 1; }
-                kept = trimmed;
+            const bool a0 = !((cur >> lane) & 1ull), a1 = !((cur >> (lane + 32)) & 1ull);
+            uint64_t kept = (uint64_t)__ballot_sync(0xffffffffu, a1) << 32 | __ballot_sync(0xffffffffu, a0);
+            while (true) {
+                const bool k0 = a0 && !(low0 & kept), k1 = a1 && !(low1 & kept);
+                const uint64_t nxt = (uint64_t)__ballot_sync(0xffffffffu, k1) << 32 | __ballot_sync(0xffffffffu, k0);
+                if (nxt == kept) break;
+                kept = nxt;
             }
-            s_kept = kept;
+            // honour max_keep: drop the kept rows beyond the limit (keep[:max_keep])
+            const int64_t room = limit - nk;
+            while ((int64_t)__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
+            if (lane == 0) s_kept[buf] = kept;
+            if ((kept >> lane) & 1ull) {
+                const int pos = __popcll(kept & ((1ull << lane) - 1ull));
+                s_krow[buf][pos] = lane;
+                keep[nk + pos] = order[t * 64 + lane];
+            }
+            if ((kept >> (lane + 32)) & 1ull) {
+                const int pos = __popcll(kept & ((1ull << (lane + 32)) - 1ull));
+                s_krow[buf][pos] = lane + 32;
+                keep[nk + pos] = order[t * 64 + lane + 32];
+            }
+            pref0 = npref0; pref1 = npref1; low0 = nlow0; low1 = nlow1;
+        } else if (t > 0) {
+            // helpers: tile t-1's kept rows -> removed[c] for c >= t+1 (column t was warp 0's prefetch)
+            const uint64_t prev = s_kept[buf ^ 1];
+            const int np = __popcll(prev);
+            if (np) {
+                const int* rows = s_krow[buf ^ 1];
+                const size_t base = (size_t)(t - 1) * 64;
+                for (int c = t + 1 + (tid - 32); c < colblocks; c += blockDim.x - 32) {
+                    uint64_t acc = 0;
+                    for (int q = 0; q < np; ++q) acc |= mask[(base + rows[q]) * stride + c];
+                    if (acc) removed[c] |= acc;
+                }
+            }
         }
         __syncthreads();
-        const uint64_t kept = s_kept;
-        const int nkept = __popcll(kept);
-        if (threadIdx.x < 64 && (kept >> threadIdx.x & 1ull)) {
-            const int pos = __popcll(kept & ((1ull << threadIdx.x) - 1ull));
-            s_krow[pos] = threadIdx.x;
-            keep[nk + pos] = order[t * 64 + threadIdx.x];
-        }
-        if (threadIdx.x < 64) diag[buf ^ 1][threadIdx.x] = next_diag;
-        __syncthreads();
-        const int ncols = colblocks - t - 1;
-        const int items = nkept * ncols;
-        for (int it = threadIdx.x; it < items; it += blockDim.x) {
-            const int q = it / ncols, c = it - q * ncols + t + 1;
-            const uint64_t w = mask[(size_t)(t * 64 + s_krow[q]) * stride + c];
-            if (w) atomicOr(reinterpret_cast<unsigned long long*>(&removed[c]), (unsigned long long)w);
-        }
-        nk += nkept;
-        __syncthreads();
+        nk += __popcll(s_kept[buf]);
     }
-    if (threadIdx.x == 0) *nkeep = (int32_t)nk;
+    if (tid == 0) *nkeep = (int32_t)nk;
 }
 
 struct NmsWs {
@@ -269,6 +312,7 @@ struct NmsWs {
     float4* sboxes;
     float* max_coord;
     uint64_t* mask;
+    uint64_t* lower;
     size_t total;
 };
 
@@ -301,6 +345,7 @@ static NmsWs carve_nms(void* ws, int64_t n) {
         w.cub_tmp = c.take<char>(w.cub_bytes);
     }
     w.mask = c.take<uint64_t>((size_t)n * colblocks);
+    w.lower = c.take<uint64_t>((size_t)n);
     w.total = c.used();
     return w;
 }
@@ -326,7 +371,7 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
     if (n <= kSmallSort) {
         int npow = 1;
         while (npow < n) npow <<= 1;
-        small_sort_gather_kernel<<<1, 1024, npow * sizeof(uint64_t), s>>>(scores, b4, idxs, n, n_dev, strategy, w.sboxes,
+        small_sort_gather_kernel<<<1, 256, npow * sizeof(uint64_t), s>>>(scores, b4, idxs, n, n_dev, strategy, w.sboxes,
                                                                           w.scls, w.order, w.meta);
         if (int rc = check_launch("small_sort_gather_kernel")) return rc;
     } else {
@@ -347,11 +392,15 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
         if (int rc = check_launch("gather_sorted_kernel")) return rc;
     }
     dim3 grid((unsigned)ceil_div(colblocks, 4), (unsigned)colblocks), block(64, 4);
-    nms_mask_kernel<<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, round_down_to_float(thr), w.mask);
+    const float thr_f = round_down_to_float(thr);
+    if (thr_f >= 0.0f)
+        nms_mask_kernel<true><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower);
+    else
+        nms_mask_kernel<false><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower);
     if (int rc = check_launch("nms_mask_kernel")) return rc;
     const size_t smem = (size_t)colblocks * sizeof(uint64_t);
     if (smem > 48 * 1024) cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nms_sweep_kernel<<<1, 1024, smem, s>>>(w.mask, w.order, w.meta, colblocks, max_keep, keep, nkeep);
+    nms_sweep_kernel<<<1, 256, smem, s>>>(w.mask, w.lower, w.order, w.meta, colblocks, max_keep, keep, nkeep);
     return check_launch("nms_sweep_kernel");
 }
 

@@ -20,6 +20,7 @@ Host round trips: two per BATCH (the detection counts after T2, the A/B/C counts
 single small D2H copy; the reference has several per image (trainer.py:469, nonzero()/tolist()).
 Everything else is asynchronous launches of libcoinops kernels on the current stream.
 """
+import os
 from typing import Dict, List
 
 import torch
@@ -66,7 +67,9 @@ class RoIPathStep:
         self.head_grad = torch.randn(shape.images * shape.rois, shape.channels, shape.pooled, shape.pooled,
                                      generator=g).to(device)
         self._streams: List[torch.cuda.Stream] = []
+        self.roi_gate = os.environ.get("COIN_ROI_GATE", "none")   # none | det | det+rpn (see _run_static)
         self.overlap = True         # issue independent stages on side streams (False: everything on the caller's stream)
+        self.timeline = None        # tools/step_timeline.py: dict name -> external CUDA event recorded in the graph
         self.kernel_events = None   # bench.py: {"fwd": [], "bwd": []} to time the two dominant kernels live
 
     # -- data movement -------------------------------------------------------------------------
@@ -96,8 +99,12 @@ class RoIPathStep:
 
     # -- the step --------------------------------------------------------------------------------
     def _side_streams(self, n: int) -> List[torch.cuda.Stream]:
+        """Stream 0 carries the HBM-bound ROIAlign forward/backward at normal priority; the others carry the
+        short latency-bound kernels at HIGH priority, so their CTAs are scheduled as soon as a ROIAlign CTA
+        retires instead of queueing behind the whole ROIAlign grid."""
         while len(self._streams) < n:
-            self._streams.append(torch.cuda.Stream(device=self.device))
+            prio = 0 if not self._streams else -1
+            self._streams.append(torch.cuda.Stream(device=self.device, priority=prio))
         return self._streams[:n]
 
     def run(self, d: Dict[str, torch.Tensor], backward: bool = True) -> Dict[str, object]:
@@ -241,6 +248,13 @@ class RoIPathStep:
                 main.wait_stream(st)
         return out
 
+    def _mark(self, name: str) -> None:
+        """Named timestamp on the current stream (only when a timeline is being collected)."""
+        if self.timeline is not None:
+            e = torch.cuda.Event(enable_timing=True, external=torch.cuda.is_current_stream_capturing())
+            e.record()
+            self.timeline[name] = e
+
     def _run_static(self, d, backward, streams) -> Dict[str, object]:
         sh, dev = self.shape, self.device
         n_img = sh.images
@@ -256,25 +270,23 @@ class RoIPathStep:
             slots[name] = sum(int(c.numel()) for c in counts)
             counts.append(t.view(-1))
 
+        self._mark("start")
         with torch.cuda.stream(s_roi):
             nhwc = ops.to_nhwc_f32(d["features"])
             rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
                               for i in range(n_img)])
-            ev = self.kernel_events
-            out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
-                                                  events=ev["fwd"] if ev else None)
-            if backward:
-                n, c, h, w = d["features"].shape
-                out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
-                                                              0, True, [torch.float32],
-                                                              events=ev["bwd"] if ev else None)[0]
+            nhwc_ready = s_roi.record_event()
 
-        c_segs = []
+        # ---- teacher detections (T1-T3) and RPN NMS (S1): one stream per image and chain
+        clouds, clips, ndets, det_done, gate = [], [], [], [], []
         for i in range(n_img):
             st_t, st_p = s_img[i], s_img[n_img + i]
             with torch.cuda.stream(st_p):                                                                 # S1
                 keep, nkeep = ops.batched_nms(d[f"{i}.rpn_boxes"], d[f"{i}.rpn_scores"], None, self.RPN_NMS_THRESH,
                                               "plain", sh.rpn_post_nms, sync=False)
+                self._mark(f"img{i}.rpn_nms_done")
+                if self.roi_gate == "det+rpn":
+                    gate.append(st_p.record_event())
             with torch.cuda.stream(st_t):
                 dec = ops.apply_deltas(d[f"{i}.teacher_deltas"], d[f"{i}.teacher_rois"], self.BBOX_WEIGHTS,
                                        clip_to=img_size)                                                    # T1
@@ -285,21 +297,49 @@ class RoIPathStep:
                                                           sh.height / (sh.height * ORIG_SCALE), "no", img_size),  # T3
                          "gt_classes": d[f"{i}.cloud.gt_classes"], "scores": d[f"{i}.cloud.scores"],
                          "probs": d[f"{i}.cloud.probs"]}
-                clip = {"gt_boxes": b, "gt_classes": c, "scores": s, "probs": p}
-                det_done = st_t.record_event()
+                self._mark(f"img{i}.det_done")
+                det_done.append(st_t.record_event())
+            clouds.append(cloud)
+            clips.append({"gt_boxes": b, "gt_classes": c, "scores": s, "probs": p})
+            ndets.append(ndet)
             out["dets"].append({"pred_boxes": b, "scores": s, "probs": p, "pred_classes": c, "roi_index": roi_idx})
             out["rpn_keep"].append(keep)
-            out.setdefault("_keepalive", []).append(cloud)   # read by another stream: must outlive this iteration
             slot(f"det{i}", ndet)
             slot(f"rpn{i}", nkeep)
+        if self.roi_gate in ("det", "det+rpn"):
+            gate += det_done
+        out["_keepalive"] = (clouds, clips)   # read by other streams: must outlive this function's locals
 
+        # ---- ROIAlign forward (S4) and backward (S5) over the sampled RoIs: needs only the map. roi_gate
+        #      optionally holds it back until the short, resource-hungry kernels of the chains above (sorts,
+        #      masks) have had the machine to themselves.
+        for e in gate:
+            s_roi.wait_event(e)
+        with torch.cuda.stream(s_roi):
+            self._mark("roi.begin_fwd")
+            ev = self.kernel_events
+            out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
+                                                  events=ev["fwd"] if ev else None)
+            self._mark("roi.end_fwd")
+            if backward:
+                n, c, h, w = d["features"].shape
+                out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
+                                                              0, True, [torch.float32],
+                                                              events=ev["bwd"] if ev else None)[0]
+                self._mark("roi.end_bwd")
+
+        # ---- knowledge separation (T4) and labelling (S3, S2): tag RCNN continues on the teacher stream,
+        #      tag RPN on the image's third stream
+        c_segs = []
+        for i in range(n_img):
+            cloud, clip, ndet = clouds[i], clips[i], ndets[i]
             per_tag = {}
-            # tag RCNN continues on the teacher stream, tag RPN on the image's third stream
-            for tag, st in (("RCNN", st_t), ("RPN", s_img[2 * n_img + i])):
-                st.wait_event(det_done)
+            for tag, st in (("RCNN", s_img[i]), ("RPN", s_img[2 * n_img + i])):
+                st.wait_event(det_done[i])
                 with torch.cuda.stream(st):
                     a, bb, cc, cnt = ops.match_abc_fields_dev(cloud, clip, ndet, tag, self.MATCH_THRESH, self.w_a)  # T4
                     slot(f"abc{i}.{tag}", cnt)
+                    self._mark(f"img{i}.abc_{tag}_done")
                     per_tag[tag] = (a, bb, cc)
                     n_a, n_b, n_c = cnt[0:1], cnt[1:2], cnt[2:3]
                     if tag == "RCNN":
@@ -311,27 +351,34 @@ class RoIPathStep:
                         ops.relabel_roi_dev_(idx, lab, n_props, n_a, n_b, n_c)
                         out["roi_labels"].append((idx, lab))
                         slot(f"props{i}", n_props)
+                        self._mark(f"img{i}.roi_labels_done")
                         c_segs.append((cc["gt_boxes"], n_c, float(i), st.record_event()))
                     else:
                         gt2, n_gt2 = ops.concat_rows([(a["gt_boxes"], n_a, 0.0), (cc["gt_boxes"], n_c, 0.0)])
                         idx2, lab2 = ops.iou_match_dev(gt2, n_gt2, self.anchors, None, [0.3, 0.7], [0, -1, 1], True)  # S2
                         out["rpn_labels"].append(ops.relabel_rpn_dev_(idx2, lab2, n_a, n_c))
+                        self._mark(f"img{i}.rpn_labels_done")
             out["abc"].append(per_tag)
 
-        # ---- ROIAlign forward on the private (C) boxes of every image, behind the big kernels
+        # ---- ROIAlign forward on the private (C) boxes of every image: a high-priority stream, so it does
+        #      not wait for the big forward/backward to drain
+        s_c = s_img[0]
         for seg in c_segs:
-            s_roi.wait_event(seg[3])
-        with torch.cuda.stream(s_roi):
+            s_c.wait_event(seg[3])
+        s_c.wait_event(nhwc_ready)
+        with torch.cuda.stream(s_c):
             c_rois, n_c_rois = ops.concat_rows([seg[:3] for seg in c_segs], width_out=5)
             out["pooled_c"] = ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32,
                                                     k_dev=n_c_rois)
             slot("c_rois", n_c_rois)
-            cat_done = s_roi.record_event()
+            self._mark("roi.pooled_c_done")
+            cat_done = s_c.record_event()
         torch.cuda.current_stream().wait_event(cat_done)
         for st in streams:
             if st is not torch.cuda.current_stream():
                 torch.cuda.current_stream().wait_stream(st)
         out["counts"] = torch.cat(counts)
+        self._mark("end")
         out["slots"] = slots
         return out
 
