@@ -160,7 +160,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from coin_b200 import _lib, pipeline, synth
+    from coin_b200 import _lib, pipeline, sharding, synth
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -215,41 +215,40 @@ def main():
         torch.cuda.synchronize()
         fwd_ms.append(ev["fwd"][0][0].elapsed_time(ev["fwd"][0][1]))
         bwd_ms.append(ev["bwd"][0][0].elapsed_time(ev["bwd"][0][1]))
-    k_fwd, k_bwd = statistics.mean(fwd_ms), statistics.mean(bwd_ms)
+    k_fwd_step, k_bwd_step = statistics.mean(fwd_ms), statistics.mean(bwd_ms)
+    # the same two launches ALONE on the device (nothing else resident): CUDA events on the launching stream
+    # around each launch; the 1.23 GB pooled / gradient tensors exceed the 126 MB L2, so every launch is cold
+    iso = {"fwd": [], "bwd": []}
+    step.time_roi_kernels(d, iso, iters=max(args.steps, 10), warmup=3)
+    torch.cuda.synchronize()
+    k_fwd = statistics.mean(a.elapsed_time(b) for a, b in iso["fwd"])
+    k_bwd = statistics.mean(a.elapsed_time(b) for a, b in iso["bwd"])
 
-    # ---- end to end: pinned host inputs -> H2D -> graph replay -> counts D2H -> live results D2H, every step
+    # ---- end to end: every step copies its inputs from pinned host memory, replays the graph, reads the
+    #      lengths back and copies the live results to pinned host memory; consecutive steps are double
+    #      buffered (H2D of step n+1 and D2H of step n-1 overlap the graph of step n)
     h2d_bytes = step.input_bytes(pinned)
-    host_cache = {}
-
-    def e2e_step():
-        step.copy_inputs(pinned)                                   # H2D into the graph's input tensors
-        o = step.replay()
-        res = step.result_tensors(step.finalize(o))                # one D2H of the counts (sync), then narrow
-        nbytes = 0
-        for i, t in enumerate(res):
-            h = host_cache.get(i)
-            if h is None or h.numel() < t.numel() or h.dtype != t.dtype:
-                h = host_cache[i] = torch.empty((max(t.numel(), 1),), dtype=t.dtype).pin_memory()
-            h[: t.numel()].copy_(t.reshape(-1), non_blocking=True)
-            nbytes += t.numel() * t.element_size()
-        torch.cuda.current_stream().synchronize()                  # results are on the host when the step ends
-        return nbytes + o["counts"].numel() * 4
-
-    for _ in range(3):
-        d2h_bytes = e2e_step()
+    pipe = pipeline.PipelinedSteps(step, d, backward=True)
+    pipe.run(pinned, 4)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        d2h_bytes = e2e_step()
+    pipe.run(pinned, args.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    d2h_bytes = pipe.d2h_bytes
+    # un-pipelined latency of ONE end-to-end step (H2D -> graph -> lengths -> D2H, nothing overlapped)
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    for _ in range(5):
+        pipe.run(pinned, 1)
+    l1.record()
+    barrier()
+    ms_e2e_latency = l0.elapsed_time(l1) / 5
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e, k_fwd, k_bwd], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, k_fwd, k_bwd = t.tolist()
+    ms, ms_e2e, k_fwd, k_bwd, k_fwd_step, k_bwd_step = sharding.max_over_ranks(
+        [ms, ms_e2e, k_fwd, k_bwd, k_fwd_step, k_bwd_step], device=dev)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -264,18 +263,24 @@ def main():
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f)
-        kernels = {
-            "roi_align_fwd_kernel": {"ms": k_fwd, "algorithmic_bytes": fwd_bytes, "achieved_gbs": fwd_bytes / k_fwd / 1e6,
-                                     "frac": fwd_bytes / k_fwd / 1e6 / peak},
-            "roi_align_bwd_kernel": {"ms": k_bwd, "algorithmic_bytes": bwd_bytes, "achieved_gbs": bwd_bytes / k_bwd / 1e6,
-                                     "frac": bwd_bytes / k_bwd / 1e6 / peak},
-        }
+        def kern(ms_alone, ms_in_step, nbytes):
+            # ms: the launch alone on the device; ms_in_step: the same launch inside the graph-replayed step,
+            # where it shares the SMs with the latency-bound kernels of the other streams
+            return {"ms": ms_alone, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / ms_alone / 1e6,
+                    "frac": nbytes / ms_alone / 1e6 / peak, "ms_in_step": ms_in_step,
+                    "achieved_gbs_in_step": nbytes / ms_in_step / 1e6, "frac_in_step": nbytes / ms_in_step / 1e6 / peak}
+
+        kernels = {"roi_align_fwd_sep_kernel": kern(k_fwd, k_fwd_step, fwd_bytes),
+                   "roi_align_bwd_sep_kernel": kern(k_bwd, k_bwd_step, bwd_bytes)}
         dom = max(kernels, key=lambda name: kernels[name]["ms"])
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                     "peak_source": peak_src, "unit": "GB/s", "frac": kernels[dom]["frac"],
-                    "traffic": traffic.get(dom), "share_of_step": kernels[dom]["ms"] / (ms / args.steps),
+                    "traffic": traffic.get(dom),
+                    "share_of_step": kernels[dom]["ms_in_step"] / (ms / args.steps),
+                    "timing": "achieved/frac: the launch timed alone with CUDA events on its stream (burst peak); "
+                              "*_in_step: the same launch inside the graph, overlapped with the other streams",
                     "kernels": kernels}
-        line = {"metric": METRIC, "value": world * n * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+        line = {"metric": METRIC, "value": sharding.whole_job_rate(n, world, args.steps, ms), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "images_per_step_per_gpu": n, "rois_per_image": shape.rois,
@@ -284,16 +289,19 @@ def main():
                            "l2": "per-step working set (2 x 1.23 GB pooled/grad tensors) >> 126 MB L2",
                            "execution": "one CUDA graph per step (sync-free step, device-side lengths); ROIAlign "
                                         "forward/backward overlap the teacher/matching branch on separate streams",
-                           "kernel_timing": "external CUDA-event pairs captured inside the graph around the two "
-                                            "ROIAlign kernels, read after each of `steps` extra replays",
+                           "kernel_timing": "ms_in_step: external CUDA-event pairs captured inside the graph around "
+                                            "the two ROIAlign kernels, read after each of `steps` extra replays; "
+                                            "ms: the same launches alone, events around each launch",
                            "launches_per_step": launches / args.steps},
                 "clocks": clocks,
-                "e2e": {"value": world * n * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+                "e2e": {"value": sharding.whole_job_rate(n, world, args.steps, ms_e2e), "unit": UNIT,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                        "ms_per_step": ms_e2e / args.steps,
-                        "boundary": "pinned host inputs (feature map, RoIs, deltas, scores, cloud detections, RPN "
-                                    "boxes) -> device; graph replay; lengths -> host (1 sync); detections, A/B/C "
-                                    "sets, labels, keep lists and the feature-map gradient -> pinned host"},
+                        "ms_per_step": ms_e2e / args.steps, "ms_latency_one_step": ms_e2e_latency,
+                        "boundary": "every step: pinned host inputs (feature map, RoIs, deltas, scores, cloud "
+                                    "detections, RPN boxes) -> device; graph replay; lengths -> host; detections, "
+                                    "A/B/C sets, labels, keep lists and the feature-map gradient -> pinned host. "
+                                    "Steps are double buffered (H2D of n+1 and D2H of n-1 overlap the graph of n); "
+                                    "ms_latency_one_step is the same step with nothing overlapped"},
                 "gpu_launches": int(launches),
                 "roofline": roofline}
         # CPU baseline: N=1 only, rank 0, bounded sample = one image of the batch through every stage

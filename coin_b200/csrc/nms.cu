@@ -293,7 +293,14 @@ nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__
                 const size_t base = (size_t)(t - 1) * 64;
                 for (int c = t + 1 + (tid - 32); c < colblocks; c += blockDim.x - 32) {
                     uint64_t acc = 0;
-                    for (int q = 0; q < np; ++q) acc |= mask[(base + rows[q]) * stride + c];
+                    for (int q = 0; q < np; q += 8) {   // 8 independent loads in flight per thread
+                        uint64_t w[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            w[u] = q + u < np ? mask[(base + rows[q + u]) * stride + c] : 0ull;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc |= w[u];
+                    }
                     if (acc) removed[c] |= acc;
                 }
             }

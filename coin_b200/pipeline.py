@@ -56,16 +56,20 @@ class RoIPathStep:
     RPN_NMS_THRESH = 0.7
     MATCH_THRESH = 0.5                      # CLOUD.MATCHER.IOU_THRESHOLDS (config.py:143)
 
-    def __init__(self, shape: Shape, device, weight_for_box_a: float = 1.0, seed: int = 2024):
+    def __init__(self, shape: Shape, device, weight_for_box_a: float = 1.0, seed: int = 2024, share=None):
+        """share: another RoIPathStep of the same shape whose constants (anchors, head gradient) are reused
+        (a second graph instance for double buffering must not duplicate the 1.2 GB head gradient)."""
         self.shape, self.device, self.w_a = shape, device, weight_for_box_a
-        self.anchors = anchors_for(shape).to(device)
-        hf, wf = shape.feat_hw
-        g = torch.Generator(device="cpu")
-        g.manual_seed(seed + 1)
-        # The box head behind ROIAlign is stood in for by a linear functional <pooled, G>: its gradient
-        # w.r.t. the pooled features is the constant G, resident on the device like a weight.
-        self.head_grad = torch.randn(shape.images * shape.rois, shape.channels, shape.pooled, shape.pooled,
-                                     generator=g).to(device)
+        if share is not None:
+            self.anchors, self.head_grad = share.anchors, share.head_grad
+        else:
+            self.anchors = anchors_for(shape).to(device)
+            g = torch.Generator(device="cpu")
+            g.manual_seed(seed + 1)
+            # The box head behind ROIAlign is stood in for by a linear functional <pooled, G>: its gradient
+            # w.r.t. the pooled features is the constant G, resident on the device like a weight.
+            self.head_grad = torch.randn(shape.images * shape.rois, shape.channels, shape.pooled, shape.pooled,
+                                         generator=g).to(device)
         self._streams: List[torch.cuda.Stream] = []
         self.roi_gate = os.environ.get("COIN_ROI_GATE", "none")   # none | det | det+rpn (see _run_static)
         self.overlap = True         # issue independent stages on side streams (False: everything on the caller's stream)
@@ -421,6 +425,21 @@ class RoIPathStep:
                           "rpn_keep": [cnt[sl[f"rpn{i}"]] for i in range(n_img)], "abc": summary_abc}
         return res
 
+    def time_roi_kernels(self, d, events: Dict[str, list], iters: int = 10, warmup: int = 3) -> None:
+        """Launches the step's two dominant kernels (ROIAlign forward / backward over the sampled RoIs) alone
+        on the current stream, `iters` times, appending a CUDA-event pair per launch to events['fwd'/'bwd']."""
+        sh, dev = self.shape, self.device
+        nhwc = ops.to_nhwc_f32(d["features"])
+        rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
+                          for i in range(sh.images)])
+        n, c, h, w = d["features"].shape
+        size, scale = (sh.pooled, sh.pooled), (1.0 / sh.stride,)
+        for it in range(warmup + iters):
+            ev = events if it >= warmup else {"fwd": None, "bwd": None}
+            ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32, events=ev["fwd"])
+            ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size, 0, True, [torch.float32],
+                                   events=ev["bwd"])
+
     # -- CUDA graph ---------------------------------------------------------------------------------
     def capture(self, d: Dict[str, torch.Tensor], backward: bool = True, warmup: int = 2):
         """Captures run_static over the (static) input tensors ``d`` into a CUDA graph. Later steps copy
@@ -490,3 +509,74 @@ class RoIPathStep:
         if "grad_features" in out:
             res.append(out["grad_features"])
         return res
+
+
+class PipelinedSteps:
+    """End-to-end execution of consecutive steps with double buffering: while the graph of step n runs, the
+    inputs of step n+1 travel host -> device and the results of step n-1 travel device -> host (three
+    streams, two graph instances). Every step still pays its own H2D copy from pinned host memory, its own
+    length read-back and its own D2H copy of the live results; only their latency is overlapped."""
+
+    def __init__(self, first: RoIPathStep, d_first: Dict[str, torch.Tensor], backward: bool = True):
+        dev = first.device
+        self.slots = [first, RoIPathStep(first.shape, dev, first.w_a, share=first)]
+        if not hasattr(first, "_graph"):
+            first.capture(d_first, backward)
+        self.slots[1].capture({k: v.clone() for k, v in d_first.items()}, backward)
+        self.s_in, self.s_c, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.counts_host = [torch.empty(s._graph_out["counts"].shape, dtype=torch.int32).pin_memory() for s in self.slots]
+        self.h2d_done = [None, None]
+        self.compute_done = [None, None]
+        self.d2h_done = [None, None]
+        self.host_cache = [{}, {}]
+        self.d2h_bytes = 0
+
+    def _h2d(self, n, pinned):
+        s = n % 2
+        with torch.cuda.stream(self.s_in):
+            if self.compute_done[s] is not None:
+                self.s_in.wait_event(self.compute_done[s])      # the graph of step n-2 has read these inputs
+            self.slots[s].copy_inputs(pinned)
+            self.h2d_done[s] = self.s_in.record_event()
+
+    def _compute(self, n):
+        s = n % 2
+        with torch.cuda.stream(self.s_c):
+            self.s_c.wait_event(self.h2d_done[s])
+            if self.d2h_done[s] is not None:
+                self.s_c.wait_event(self.d2h_done[s])           # the results of step n-2 have left these buffers
+            out = self.slots[s].replay()
+            self.counts_host[s].copy_(out["counts"], non_blocking=True)
+            self.compute_done[s] = self.s_c.record_event()
+
+    def _d2h(self, n):
+        s = n % 2
+        self.compute_done[s].synchronize()                      # the lengths of step n are on the host
+        step = self.slots[s]
+        res = step.result_tensors(step.finalize(step._graph_out, counts_host=self.counts_host[s]))
+        cache, nbytes = self.host_cache[s], self.counts_host[s].numel() * 4
+        with torch.cuda.stream(self.s_out):
+            for i, t in enumerate(res):
+                h = cache.get(i)
+                if h is None or h.numel() < t.numel() or h.dtype != t.dtype:
+                    h = cache[i] = torch.empty((max(t.numel(), 1),), dtype=t.dtype).pin_memory()
+                h[: t.numel()].copy_(t.reshape(-1), non_blocking=True)
+                nbytes += t.numel() * t.element_size()
+            self.d2h_done[s] = self.s_out.record_event()
+        self.d2h_bytes = nbytes
+
+    def run(self, pinned: Dict[str, torch.Tensor], steps: int) -> None:
+        """`steps` end-to-end steps on the same pinned inputs; returns when every result is on the host."""
+        for st in (self.s_in, self.s_c, self.s_out):
+            st.wait_stream(torch.cuda.current_stream())
+        self._h2d(0, pinned)
+        for n in range(steps):
+            if n + 1 < steps:
+                self._h2d(n + 1, pinned)
+            self._compute(n)
+            if n > 0:
+                self._d2h(n - 1)
+        self._d2h(steps - 1)
+        self.s_out.synchronize()
+        for st in (self.s_in, self.s_c, self.s_out):
+            torch.cuda.current_stream().wait_stream(st)
