@@ -22,7 +22,7 @@ struct AbcArgs {
     const float4 *onb, *offb;
     const int64_t *oncls, *offcls;
     const float *ons, *offs;
-    int nc, nd, tag;
+    int nc, nd, tag, use_smem;
     const int32_t* nd_dev;   // optional device-side count of CLIP-detector detections (<= nd)
     float thr, w_a;
     int cap;
@@ -137,9 +137,53 @@ __device__ int dedup_order(const float4* box, int L, const AbcArgs& a, int32_t* 
     return n + ng;
 }
 
-__global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a) {
+// Scratch placement: the kernel is a long chain of small dependent phases, so the latency of its scratch
+// arrays is what it costs. With <= kAbcN detections per side the per-detection and per-row arrays live in
+// shared memory, and so do the pair lists when the number of common pairs fits kAbcPairs; otherwise the
+// global workspace is used (same code, pointers swapped).
+constexpr int kAbcN = 128;
+constexpr int kAbcPairs = 320;
+constexpr size_t kAbcInputBytes = (size_t)kAbcN * (16 + 16 + 8 + 8 + 4 + 4);   // staged copies of both detection sets
+constexpr size_t kAbcSmemBytes = (size_t)kAbcPairs * (6 * 4 + 8 * 4 + 16) + (size_t)kAbcN * 9 * 4 + kAbcInputBytes + 64;
+
+__device__ __forceinline__ void abc_use_shared_small(AbcArgs& b, unsigned char* sm) {
+    int32_t* w = reinterpret_cast<int32_t*>(sm + (size_t)kAbcPairs * 16);   // after the float4 block
+    b.key = reinterpret_cast<float*>(w); w += kAbcPairs;
+    b.first = w; w += kAbcPairs; b.cnt = w; w += kAbcPairs; b.isgrp = w; w += kAbcPairs;
+    b.glist = w; w += kAbcPairs; b.single = w; w += kAbcPairs;
+    b.uniq = w; w += kAbcN; b.offgl = w; w += kAbcN; b.on_used = w; w += kAbcN; b.off_matched = w; w += kAbcN;
+    b.label = w; w += kAbcN; b.rowcnt = w; w += kAbcN; b.rowoff = w; w += kAbcN; b.g_i0 = w; w += kAbcN;
+    b.g_m = w; w += kAbcN;
+}
+__device__ __forceinline__ void abc_use_shared_pairs(AbcArgs& b, unsigned char* sm) {
+    b.mbox = reinterpret_cast<float4*>(sm);
+    int32_t* w = reinterpret_cast<int32_t*>(sm + (size_t)kAbcPairs * 16) + 6 * kAbcPairs + 9 * kAbcN;
+    b.pon[0] = w; w += kAbcPairs; b.pon[1] = w; w += kAbcPairs; b.poff[0] = w; w += kAbcPairs; b.poff[1] = w; w += kAbcPairs;
+    b.flag_a = w; w += kAbcPairs; b.flag_b = w; w += kAbcPairs; b.raw = w; w += kAbcPairs; b.outlist = w; w += kAbcPairs;
+}
+
+__global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a_in) {
+    extern __shared__ __align__(16) unsigned char abc_smem[];
     __shared__ int s_tmp, s_flag[4];
+    AbcArgs a = a_in;   // mutable copy: scratch pointers may be redirected to shared memory
     const int nc = a.nc, nd = a.nd_dev ? min(max(*a.nd_dev, 0), a.nd) : a.nd;
+    const bool small = a.use_smem && nc <= kAbcN && nd <= kAbcN;
+    if (small) {
+        abc_use_shared_small(a, abc_smem);
+        abc_use_shared_pairs(a, abc_smem);   // tentative: undone below if the pair count does not fit
+        // stage both detection sets: every later phase re-reads them many times
+        unsigned char* in = abc_smem + (size_t)kAbcPairs * (6 * 4 + 8 * 4 + 16) + (size_t)kAbcN * 9 * 4;
+        float4* s_onb = reinterpret_cast<float4*>(in);
+        float4* s_offb = s_onb + kAbcN;
+        int64_t* s_oncls = reinterpret_cast<int64_t*>(s_offb + kAbcN);
+        int64_t* s_offcls = s_oncls + kAbcN;
+        float* s_ons = reinterpret_cast<float*>(s_offcls + kAbcN);
+        float* s_offs = s_ons + kAbcN;
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) { s_onb[i] = a.onb[i]; s_oncls[i] = a.oncls[i]; s_ons[i] = a.ons[i]; }
+        for (int j = threadIdx.x; j < nd; j += blockDim.x) { s_offb[j] = a.offb[j]; s_offcls[j] = a.offcls[j]; s_offs[j] = a.offs[j]; }
+        a.onb = s_onb; a.offb = s_offb; a.oncls = s_oncls; a.offcls = s_offcls; a.ons = s_ons; a.offs = s_offs;
+        __syncthreads();
+    }
     int status = 0;
     // In the empty-side branches both members of a pair come from the same detection set.
     const bool on_empty = (nc == 0), off_empty = (nd == 0);
@@ -204,6 +248,12 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a) {
         __syncthreads();
         P = s_tmp;
         __syncthreads();
+        if (small && P + nd > kAbcPairs) {   // too many pairs for shared memory: back to the global workspace
+            a.pon[0] = a_in.pon[0]; a.pon[1] = a_in.pon[1]; a.poff[0] = a_in.poff[0]; a.poff[1] = a_in.poff[1];
+            a.flag_a = a_in.flag_a; a.flag_b = a_in.flag_b; a.raw = a_in.raw; a.outlist = a_in.outlist; a.mbox = a_in.mbox;
+            a.key = a_in.key; a.first = a_in.first; a.cnt = a_in.cnt; a.isgrp = a_in.isgrp; a.glist = a_in.glist;
+            a.single = a_in.single;
+        }
         if (P > a.cap) { status |= 4; }
         for (int i = threadIdx.x; i < nc; i += blockDim.x) {
             const float4 bi = a.onb[i];
@@ -288,11 +338,18 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a) {
             }
             if (!__syncthreads_or(changed)) break;
         }
+        // size and "mixed classes" flag of every cluster, once, in parallel (rowcnt / rowoff are free by now)
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) { a.rowcnt[i] = 0; a.rowoff[i] = 0; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+            const int r = a.label[i];
+            atomicAdd(&a.rowcnt[r], 1);
+            if (a.oncls[i] != a.oncls[r]) atomicOr(&a.rowoff[r], 1);
+        }
+        __syncthreads();
         for (int root = 0; root < nc; ++root) {  // clusters in ascending order of their lowest member
             if (a.label[root] != root) continue;
-            int size = 0, mixed = 0;
-            for (int i = root; i < nc; ++i)
-                if (a.label[i] == root) { ++size; mixed |= (a.oncls[i] != a.oncls[root]); }
+            const int size = a.rowcnt[root], mixed = a.rowoff[root];
             if (size < 2) continue;                     // uniform: every thread evaluates the same data
             if (!mixed) status |= 16;                   // the reference asserts here (util.py:488)
             const float4 broot = a.onb[root];
@@ -310,19 +367,20 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a) {
             }
             any_first = __syncthreads_or(any_first);
             // classes the CLIP detector gave to the pairs of the first cluster box: unanimous?
-            if (threadIdx.x == 0) { s_flag[0] = -1; s_flag[1] = 0; }
+            if (threadIdx.x == 0) { s_flag[0] = -1; s_flag[1] = 0; s_flag[2] = 0x7fffffff; }
             __syncthreads();
             if (any_first) {
-                if (threadIdx.x == 0) {
-                    int cls = -1, multi = 0;
-                    for (int p = 0; p < P; ++p)
-                        if (a.flag_b[p]) {
-                            const int c = (int)a.offcls[a.poff[cur][p]];
-                            if (cls < 0) cls = c; else if (c != cls) multi = 1;
-                        }
-                    s_flag[0] = cls;
-                    s_flag[1] = multi;
-                }
+                int mine = 0x7fffffff;   // lowest flagged pair of this thread
+                for (int p = threadIdx.x; p < P; p += blockDim.x)
+                    if (a.flag_b[p]) { mine = p; break; }
+                if (mine != 0x7fffffff) atomicMin(&s_flag[2], mine);
+                __syncthreads();
+                const int cls = (int)a.offcls[a.poff[cur][s_flag[2]]];
+                int multi = 0;
+                for (int p = threadIdx.x; p < P; p += blockDim.x)
+                    multi |= (a.flag_b[p] && (int)a.offcls[a.poff[cur][p]] != cls);
+                multi = __syncthreads_or(multi);
+                if (threadIdx.x == 0) { s_flag[0] = cls; s_flag[1] = multi; }
                 __syncthreads();
             }
             const int ucls = s_flag[0];
@@ -485,7 +543,8 @@ static int match_abc_impl(const float* on_boxes, const int64_t* on_classes, cons
     a.nc = (int)nc; a.nd = (int)nd; a.nd_dev = nd_dev; a.tag = tag; a.thr = iou_thr; a.w_a = weight_for_box_a; a.cap = (int)cap_pairs;
     a.a_on = a_on; a.a_off = a_off; a.b_on = b_on; a.b_off = b_off; a.c_on = c_on; a.c_off = c_off; a.counts = counts;
     a.a_box = reinterpret_cast<float4*>(a_boxes); a.b_box = reinterpret_cast<float4*>(b_boxes);
-    match_abc_kernel<<<1, 256, 0, s>>>(a);
+    a.use_smem = (nc <= kAbcN && nd <= kAbcN) ? 1 : 0;
+    match_abc_kernel<<<1, 256, a.use_smem ? kAbcSmemBytes : 0, s>>>(a);
     return check_launch("match_abc_kernel");
 }
 
