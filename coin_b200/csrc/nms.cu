@@ -163,7 +163,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ scls,
                 const int32_t* __restrict__ meta, int colblocks, float thr, uint64_t* __restrict__ mask,
-                uint64_t* __restrict__ lower) {
+                uint64_t* __restrict__ lower, uint64_t* __restrict__ rowflags, int fw) {
     const int n = meta[0];
     const bool same_class_only = meta[1] == COIN_NMS_VANILLA;
     const int rt = blockIdx.y;                 // row tile
@@ -210,20 +210,25 @@ nms_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ s
         }
     }
     mask[(size_t)i * colblocks + ct] = word;
+    // rowflags[i]: bitmap of the column blocks with a non-zero word (zero-filled by the host side). Overlap is
+    // sparse, so the sweep reads this bitmap and then only the few non-zero words of a kept row.
+    if (word) atomicOr(reinterpret_cast<unsigned long long*>(rowflags + (size_t)i * fw + (ct >> 6)), 1ull << (ct & 63));
     if (diag) lower[i] = low;
 }
 
 // Single-CTA sweep over 64-row tiles. Warp 0 resolves a tile by FIXED-POINT iteration on the transposed
 // diagonal words: kept = alive & ~any(lower & kept), repeated until stable (the unique solution of the
 // greedy recurrence; a few rounds instead of a 64-step serial chain). The other warps OR the mask rows of
-// the PREVIOUS tile's kept boxes into the `removed` bit-vector one tile behind (each thread owns its
-// columns, no atomics); the one column warp 0 needs immediately (tile t-1 -> column t) is prefetched by
-// warp 0 itself before the kept set is known. 256 threads / ~2 KB of static shared memory: the CTA fits
+// the PREVIOUS tile's kept boxes into the `removed` bit-vector one tile behind: one thread per kept row reads the
+// row's bitmap of non-zero column blocks and fetches only those words (shared-memory atomicOr); the one
+// column warp 0 needs immediately (tile t-1 -> column t) is prefetched by warp 0 itself before the kept set is
+// known. 256 threads / ~2 KB of static shared memory: the CTA fits
 // next to resident HBM-bound kernels of other streams.
 __global__ void __launch_bounds__(256)
 nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__ lower,
-                 const int32_t* __restrict__ order, const int32_t* __restrict__ meta, int stride, int64_t max_keep,
-                 int64_t* __restrict__ keep, int32_t* __restrict__ nkeep) {
+                 const uint64_t* __restrict__ rowflags, int fw, const int32_t* __restrict__ order,
+                 const int32_t* __restrict__ meta, int stride, int64_t max_keep, int64_t* __restrict__ keep,
+                 int32_t* __restrict__ nkeep) {
     extern __shared__ uint64_t removed[];  // colblocks words
     const int n = meta[0];
     const int colblocks = (n + 63) >> 6;   // live column blocks; `stride` is the row pitch of `mask`
@@ -235,6 +240,8 @@ nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__
     __syncthreads();
     int64_t nk = 0;
     const int64_t limit = max_keep >= 0 ? max_keep : (int64_t)n;
+    const bool fast_flags = 64 * fw <= (int)blockDim.x - 32;   // one helper thread per (row, flag word) of a tile
+    uint64_t myflag = 0;                    // helpers: the flag word loaded one iteration earlier
     uint64_t pref0 = 0, pref1 = 0;          // warp 0: mask[(t-1)*64 + lane (+32)][t]
     uint64_t low0 = 0, low1 = 0;            // warp 0: lower words of tile t
     if (warp == 0) {
@@ -284,24 +291,59 @@ nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__
                 keep[nk + pos] = order[t * 64 + lane + 32];
             }
             pref0 = npref0; pref1 = npref1; low0 = nlow0; low1 = nlow1;
+        } else if (fast_flags) {
+            // helpers, n <= 12288 (<= 3 flag words per row): thread h owns flag word (row h / fw, word h % fw) of
+            // the current tile. The flag word of tile t is loaded NOW (independent of the kept set) and used
+            // in the next iteration, when kept(t) is known: one dependent L2 round trip per tile.
+            const int h = tid - 32;
+            uint64_t nflag = 0;
+            if (h < 64 * fw) {
+                const int r = t * 64 + h / fw;
+                if (r < n) nflag = rowflags[(size_t)r * fw + h % fw];
+            }
+            if (t > 0 && h < 64 * fw) {
+                const uint64_t prev = s_kept[buf ^ 1];
+                const int rr = h / fw, f = h - rr * fw;
+                if ((prev >> rr) & 1ull) {
+                    uint64_t bits = myflag;
+                    const int shift = t - f * 64 + 1;          // clear the columns <= t
+                    if (shift >= 64) bits = 0; else if (shift > 0) bits &= ~0ull << shift;
+                    const size_t rowbase = ((size_t)(t - 1) * 64 + rr) * stride + f * 64;
+                    while (bits) {                              // up to 4 loads in flight
+                        int c[4];
+                        uint64_t w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            c[u] = bits ? __ffsll((long long)bits) - 1 : -1;
+                            if (bits) bits &= bits - 1;
+                            w[u] = c[u] >= 0 ? mask[rowbase + c[u]] : 0ull;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c[u] >= 0 && w[u])
+                                atomicOr(reinterpret_cast<unsigned long long*>(&removed[f * 64 + c[u]]), (unsigned long long)w[u]);
+                    }
+                }
+            }
+            myflag = nflag;
         } else if (t > 0) {
-            // helpers: tile t-1's kept rows -> removed[c] for c >= t+1 (column t was warp 0's prefetch)
+            // helpers, generic: tile t-1's kept rows -> removed[c] for c >= t+1 (column t was warp 0's prefetch)
             const uint64_t prev = s_kept[buf ^ 1];
             const int np = __popcll(prev);
-            if (np) {
-                const int* rows = s_krow[buf ^ 1];
-                const size_t base = (size_t)(t - 1) * 64;
-                for (int c = t + 1 + (tid - 32); c < colblocks; c += blockDim.x - 32) {
-                    uint64_t acc = 0;
-                    for (int q = 0; q < np; q += 8) {   // 8 independent loads in flight per thread
-                        uint64_t w[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            w[u] = q + u < np ? mask[(base + rows[q + u]) * stride + c] : 0ull;
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) acc |= w[u];
+            const int* rows = s_krow[buf ^ 1];
+            const size_t base = (size_t)(t - 1) * 64;
+            for (int q = tid - 32; q < np; q += blockDim.x - 32) {
+                const size_t row = base + rows[q];
+                for (int f = t >> 6; f < fw; ++f) {           // flag words that can hold a column > t
+                    uint64_t bits = rowflags[row * fw + f];
+                    const int shift = t - f * 64 + 1;          // clear the columns <= t
+                    if (shift >= 64) bits = 0; else if (shift > 0) bits &= ~0ull << shift;
+                    while (bits) {
+                        const int c = f * 64 + __ffsll((long long)bits) - 1;
+                        bits &= bits - 1;
+                        atomicOr(reinterpret_cast<unsigned long long*>(&removed[c]),
+                                 (unsigned long long)mask[row * stride + c]);
                     }
-                    if (acc) removed[c] |= acc;
                 }
             }
         }
@@ -320,6 +362,7 @@ struct NmsWs {
     float* max_coord;
     uint64_t* mask;
     uint64_t* lower;
+    uint64_t* rowflags;
     size_t total;
 };
 
@@ -353,6 +396,7 @@ static NmsWs carve_nms(void* ws, int64_t n) {
     }
     w.mask = c.take<uint64_t>((size_t)n * colblocks);
     w.lower = c.take<uint64_t>((size_t)n);
+    w.rowflags = c.take<uint64_t>((size_t)n * ceil_div(colblocks, 64));
     w.total = c.used();
     return w;
 }
@@ -400,14 +444,19 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
     }
     dim3 grid((unsigned)ceil_div(colblocks, 4), (unsigned)colblocks), block(64, 4);
     const float thr_f = round_down_to_float(thr);
+    const int fw = (int)ceil_div(colblocks, 64);
+    cudaMemsetAsync(w.rowflags, 0, (size_t)n * fw * sizeof(uint64_t), s);
     if (thr_f >= 0.0f)
-        nms_mask_kernel<true><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower);
+        nms_mask_kernel<true><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower,
+                                                     w.rowflags, fw);
     else
-        nms_mask_kernel<false><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower);
+        nms_mask_kernel<false><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower,
+                                                      w.rowflags, fw);
     if (int rc = check_launch("nms_mask_kernel")) return rc;
     const size_t smem = (size_t)colblocks * sizeof(uint64_t);
     if (smem > 48 * 1024) cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nms_sweep_kernel<<<1, 256, smem, s>>>(w.mask, w.lower, w.order, w.meta, colblocks, max_keep, keep, nkeep);
+    nms_sweep_kernel<<<1, 256, smem, s>>>(w.mask, w.lower, w.rowflags, fw, w.order, w.meta, colblocks, max_keep, keep,
+                                          nkeep);
     return check_launch("nms_sweep_kernel");
 }
 
