@@ -40,12 +40,19 @@ __device__ __forceinline__ int resolve_strategy(int strategy, int n) {
     return strategy;
 }
 
+// Large-n path: 32-bit keys (descending-score order) + 32-bit values (original index). The radix sort is
+// stable and the input is in index order, so exact ties keep the lower index first -- the same order as the
+// 64-bit (key, index) composite of the single-CTA path, in 4 radix passes instead of 8.
 __global__ void make_keys_kernel(const float* __restrict__ scores, int n_cap, const int32_t* __restrict__ n_dev,
-                                 int strategy, uint64_t* __restrict__ keys, int32_t* __restrict__ meta) {
+                                 int strategy, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                 int32_t* __restrict__ meta) {
     const int n = resolve_n(n_cap, n_dev);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { meta[0] = n; meta[1] = resolve_strategy(strategy, n); }
-    if (i < n_cap) keys[i] = i < n ? sort_key(__ldg(scores + i), (uint32_t)i) : ~0ull;
+    if (i < n_cap) {
+        keys[i] = i < n ? (uint32_t)(sort_key(__ldg(scores + i), 0u) >> 32) : 0xffffffffu;
+        vals[i] = (uint32_t)i;
+    }
 }
 
 // max over all 4n coordinates (for the coordinate trick); result as orderable int via atomicMax
@@ -75,14 +82,14 @@ __device__ __forceinline__ float decode_max(const float* p) {
 }
 
 // sorted position -> box (with the class offset when strategy == TRICK), class id, original index
-__global__ void gather_sorted_kernel(const uint64_t* __restrict__ keys, const float4* __restrict__ boxes,
+__global__ void gather_sorted_kernel(const uint32_t* __restrict__ sorted_idx, const float4* __restrict__ boxes,
                                      const int64_t* __restrict__ idxs, const int32_t* __restrict__ meta,
                                      const float* __restrict__ max_coord, float4* __restrict__ sboxes,
                                      int32_t* __restrict__ scls, int32_t* __restrict__ order) {
     const int n = meta[0], strategy = meta[1];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t src = (uint32_t)(keys[i] & 0xffffffffu);
+    const uint32_t src = sorted_idx[i];
     float4 b = __ldg(boxes + src);
     const int64_t cls = idxs ? __ldg(idxs + src) : 0;
     if (strategy == COIN_NMS_TRICK) {
@@ -354,7 +361,7 @@ nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__
 }
 
 struct NmsWs {
-    uint64_t *keys, *keys_alt;
+    uint32_t *keys, *keys_alt, *vals, *vals_alt;
     void* cub_tmp;
     size_t cub_bytes;
     int32_t *order, *scls, *meta;
@@ -368,8 +375,8 @@ struct NmsWs {
 
 static size_t cub_sort_bytes(int64_t n) {
     size_t bytes = 0;
-    cub::DoubleBuffer<uint64_t> db(nullptr, nullptr);
-    if (cub::DeviceRadixSort::SortKeys(nullptr, bytes, db, (int)n) != cudaSuccess) {
+    cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
+    if (cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n) != cudaSuccess) {
         cudaGetLastError();
         bytes = (size_t)n * 16 + (1 << 20);  // conservative when no device can be queried
     }
@@ -385,12 +392,14 @@ static NmsWs carve_nms(void* ws, int64_t n) {
     w.order = c.take<int32_t>((size_t)n);
     w.scls = c.take<int32_t>((size_t)n);
     w.sboxes = c.take<float4>((size_t)n);
-    w.keys = w.keys_alt = nullptr;
+    w.keys = w.keys_alt = w.vals = w.vals_alt = nullptr;
     w.cub_tmp = nullptr;
     w.cub_bytes = 0;
     if (n > kSmallSort) {
-        w.keys = c.take<uint64_t>((size_t)n);
-        w.keys_alt = c.take<uint64_t>((size_t)n);
+        w.keys = c.take<uint32_t>((size_t)n);
+        w.keys_alt = c.take<uint32_t>((size_t)n);
+        w.vals = c.take<uint32_t>((size_t)n);
+        w.vals_alt = c.take<uint32_t>((size_t)n);
         w.cub_bytes = cub_sort_bytes(n);
         w.cub_tmp = c.take<char>(w.cub_bytes);
     }
@@ -426,11 +435,11 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
                                                                           w.scls, w.order, w.meta);
         if (int rc = check_launch("small_sort_gather_kernel")) return rc;
     } else {
-        make_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(scores, n, n_dev, strategy, w.keys, w.meta);
+        make_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(scores, n, n_dev, strategy, w.keys, w.vals, w.meta);
         if (int rc = check_launch("make_keys_kernel")) return rc;
-        cub::DoubleBuffer<uint64_t> db(w.keys, w.keys_alt);
+        cub::DoubleBuffer<uint32_t> dk(w.keys, w.keys_alt), db(w.vals, w.vals_alt);
         size_t bytes = w.cub_bytes;
-        cudaError_t e = cub::DeviceRadixSort::SortKeys(w.cub_tmp, bytes, db, n, 0, 64, s);
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, dk, db, n, 0, 32, s);
         if (e != cudaSuccess) return fail(COIN_ERR_CUDA, "nms: radix sort failed: %s", cudaGetErrorString(e));
         count_launch();
         if (strategy == COIN_NMS_TRICK || strategy == COIN_NMS_AUTO) {
