@@ -396,7 +396,7 @@ static int fill_params(RoiParams& p, const coin_level_t* levels, int nlevels, co
         p.lv[i] = levels[i];
     }
     for (int i = nlevels; i < COIN_MAX_LEVELS; ++i) p.lv[i] = levels[0];
-    p.rois = rois; p.roi_level = nlevels > 1 ? roi_level : nullptr; p.k_dev = nullptr;
+    p.rois = rois; p.roi_level = nlevels > 1 ? roi_level : nullptr; p.k_dev = nullptr; p.flags = 0;
     p.C = C; p.K = K; p.PH = PH; p.PW = PW; p.sampling_ratio = sr; p.aligned = aligned;
     return COIN_OK;
 }

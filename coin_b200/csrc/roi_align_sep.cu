@@ -583,6 +583,7 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
     }
 
     float* __restrict__ Gw = gsm + (size_t)warp * 32 * P;
+    const bool prefetch = p.flags & 1;
     for (int item = warp; item < nunits * nslab; item += nwarps) {
         const int sl = item / nunits, unit = item - sl * nunits;
         const int ph0 = unit * R, nr = min(R, PH - ph0);
@@ -605,6 +606,24 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
             for (; c < cc; ++c) gw_[c] = to_f32(__ldg(gp + (size_t)c * NB));
         }
         __syncwarp();
+        // L2 prefetch of the NEXT item's grad_out rows (this warp's next unit/slab): the rows stream from HBM
+        // exactly once, so without it every staging load pays the full DRAM latency
+        {
+            const int nitem = item + nwarps;
+            if (prefetch && nitem < nunits * nslab) {
+                const int nsl = nitem / nunits, nun = nitem - nsl * nunits;
+                const int nph0 = nun * R, nnr = min(R, PH - nph0);
+                const int nc0 = cg0 + nsl * CC, ncc = min(CC, C - nc0);
+                const int bytes = nnr * PW * (int)sizeof(GT);          // contiguous bytes per channel row
+                const int segs = (bytes + 31) / 32 + 1;                 // 32-byte sectors (+1 for misalignment)
+                const char* base = reinterpret_cast<const char*>(groi + (size_t)nc0 * NB + nph0 * PW);
+                for (int e = lane; e < ncc * segs; e += 32) {
+                    const int ch = e / segs, sg = e - ch * segs;
+                    const int off = min(sg * 32, bytes - 1);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)ch * NB * sizeof(GT) + off));
+                }
+            }
+        }
         float* __restrict__ gb = gimg + c0 + lane;
         if (cc == CC) bwd_walk<CPL, true>(Gw, gb, C, PW, nr, cc, lane, cmin, ncols, colstart, cent, ytab[unit], ne);
         else bwd_walk<CPL, false>(Gw, gb, C, PW, nr, cc, lane, cmin, ncols, colstart, cent, ytab[unit], ne);
@@ -664,7 +683,9 @@ int launch_roi_align_fwd_sep(const RoiParams& p, void* out, int out_dtype, cudaS
 }
 
 
-int launch_roi_align_bwd_sep(const RoiParams& p, const void* grad_out, int grad_dtype, cudaStream_t s) {
+int launch_roi_align_bwd_sep(const RoiParams& p_in, const void* grad_out, int grad_dtype, cudaStream_t s) {
+    RoiParams p = p_in;
+    p.flags = sep_env("COIN_ROI_BWD_PREFETCH", 1) ? 1 : 0;
     const int cpl = p.C <= 32 ? 1 : (sep_env("COIN_ROI_BWD_CPL", 2) == 1 ? 1 : 2);
     const int R = p.PW <= 16 && p.PH >= 2 ? 2 : 1;
     int warps = sep_env("COIN_ROI_BWD_WARPS", (int)std::min<int64_t>(7, std::max<int64_t>(ceil_div(p.PH, R), 4)));

@@ -12,6 +12,7 @@ struct RoiParams {
     const int32_t* roi_level;
     const int32_t* k_dev;   // optional device-side live RoI count (<= K): CTAs of RoIs beyond it exit
     int C, K, PH, PW, sampling_ratio, aligned;
+    int flags;              // bit 0: L2-prefetch the next unit's grad_out rows (backward)
 };
 
 struct RoiGeom {

@@ -131,3 +131,46 @@ def test_pipelined_end_to_end_steps_match_oracle(dev):
         for i, t in enumerate(slot.result_tensors(got)):
             assert torch.equal(pipe.host_cache[s][i][: t.numel()], t.reshape(-1).cpu())
     assert pipe.d2h_bytes > 0
+
+
+def test_distillation_loss_consumers_match_oracle(dev):
+    """Row A14: the reference's distillation losses stay in PyTorch; their INPUTS come from this path.
+    RoI side (fast_rcnn.py:541-545): KLDiv(log(softmax(scores_c) + 1e-7), gt_probs_c) on the C-box ROIAlign features
+    through a fixed head; RPN side (rpn.py:95-98,326-340): teacher_probs = gt_probs_c[:, :-1].sum(1)[matched_idxs]
+    on the anchors with distillation label 1. Identical head weights on both sides; <= 1e-5 relative."""
+    shape = synth.SHAPES["tiny"]
+    batch = synth.image_batch(shape)
+    step = pipeline.RoIPathStep(shape, dev)
+    got = step.finalize(step.run_static(step.to_device(batch), backward=False))
+    want = pipeline_ref.run(batch, backward=False)
+    g = synth.gen(91)
+    k1 = shape.classes + 1
+    w_head = (torch.randn(shape.channels, k1, generator=g) * 0.2).double()
+    obj_logits = torch.randn(want["rpn_labels"][0][0].numel(), generator=g).double()
+    kl = torch.nn.KLDivLoss(reduction="mean")   # as the reference (fast_rcnn.py:273, rpn.py:15)
+
+    def roi_loss(out, to_cpu):
+        feats = to_cpu(out["pooled_c"]).double().mean(dim=(2, 3))                       # [nC, C]
+        p = torch.softmax(feats @ w_head, dim=1)
+        q = torch.cat([to_cpu(out["abc"][i]["RCNN"][2]["gt_probs"]).double() for i in range(shape.images)])
+        return kl(torch.log(p + 1e-7), q)
+
+    def rpn_loss(out, to_cpu, i):
+        gt_labels, matched, didx, dlab = (to_cpu(t) for t in out["rpn_labels"][i])
+        probs_c = to_cpu(out["abc"][i]["RPN"][2]["gt_probs"]).double()
+        if probs_c.shape[0] == 0:
+            return torch.zeros((), dtype=torch.float64)
+        teacher = probs_c[:, :-1].sum(1)[didx.long()].clamp(0.0, 1.0)   # a sum of fp32 probabilities can exceed 1 by an ulp
+        valid = dlab > 0
+        p = torch.sigmoid(obj_logits[valid])
+        p = torch.stack((p, 1 - p), dim=1)
+        q = torch.stack((teacher[valid], 1 - teacher[valid]), dim=1)
+        return kl(torch.log(p + 1e-7), q) if bool(valid.any()) else torch.zeros((), dtype=torch.float64)
+
+    cpu = lambda t: t.cpu()
+    ident = lambda t: t
+    a, b = roi_loss(got, cpu), roi_loss(want, ident)
+    assert abs(float(a - b)) <= 1e-5 * abs(float(b)), (float(a), float(b))
+    for i in range(shape.images):
+        a, b = rpn_loss(got, cpu, i), rpn_loss(want, ident, i)
+        assert abs(float(a - b)) <= 1e-5 * max(abs(float(b)), 1e-12), (i, float(a), float(b))
