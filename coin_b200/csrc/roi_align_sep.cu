@@ -379,15 +379,53 @@ struct YEnt { int off; float w0, w1; int pad; };   // feature-row offset (y*W*C)
 struct CEnt { int bin; float w; };                 // one bin's combined x weight on a feature column
 
 // walk + flush for one unit (lane = channel). FULL: the whole 32*CPL-channel slab is inside C.
-template <int CPL, bool FULL>
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// walk + flush for one unit. FULL: the whole channel slab is inside C.
+// VEC = false: lane owns channels lane + 32*j of the slab (tile pitch 32*CPL + 1, scalar fp32 REDs).
+// VEC = true (CPL == 2, even C): lane owns the ADJACENT channels 2*lane, 2*lane + 1 (tile pitch 66): the tile is
+// read with 64-bit LDS and every flush is ONE vector RED (red.global.add.v2.f32) per lane instead of two - the
+// flush, not the atomic unit, is what the backward spends most of its time issuing.
+template <int CPL, bool FULL, bool VEC>
 __device__ __forceinline__ void bwd_walk(const float* __restrict__ Gw, float* __restrict__ gb, const int C, const int PW,
                                          const int nr, const int cc, const int lane, const int cmin, const int ncols,
                                          const int* __restrict__ colstart, const CEnt* __restrict__ cent,
                                          const YEnt* __restrict__ yt, const int ne) {
-    constexpr int P = 32 * CPL + 1;
+    constexpr int P = VEC ? 32 * CPL + 2 : 32 * CPL + 1;
+    if (VEC) {
+        const float* __restrict__ G0 = Gw + 2 * lane;
+        const float* __restrict__ G1 = Gw + (nr == 2 ? PW * P : 0) + 2 * lane;
+        const float s1 = nr == 2 ? 1.0f : 0.0f;
+        const bool ok0 = FULL || 2 * lane < cc, ok1 = FULL || 2 * lane + 1 < cc;
+        float* __restrict__ gl = gb + 2 * lane;
+        for (int ci = 0; ci < ncols; ++ci) {
+            const int e0 = colstart[ci], e1 = colstart[ci + 1];
+            if (e0 == e1) continue;
+            float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+            for (int e = e0; e < e1; ++e) {
+                const CEnt E = cent[e];
+                const float2 g0 = *reinterpret_cast<const float2*>(G0 + E.bin * P);
+                const float2 g1 = *reinterpret_cast<const float2*>(G1 + E.bin * P);
+                a0.x = __fmaf_rn(E.w, g0.x, a0.x); a0.y = __fmaf_rn(E.w, g0.y, a0.y);
+                a1.x = __fmaf_rn(E.w, g1.x, a1.x); a1.y = __fmaf_rn(E.w, g1.y, a1.y);
+            }
+            float* __restrict__ gc = gl + (size_t)(cmin + ci) * C;
+            for (int e = 0; e < ne; ++e) {
+                const YEnt Y = yt[e];
+                const float w1 = Y.w1 * s1;
+                const float vx = __fmaf_rn(w1, a1.x, Y.w0 * a0.x), vy = __fmaf_rn(w1, a1.y, Y.w0 * a0.y);
+                if (ok1) red_add_v2(gc + Y.off, vx, vy);
+                else if (ok0) atomicAdd(gc + Y.off, vx);
+            }
+        }
+        return;
+    }
     const float* __restrict__ G0 = Gw + lane;
     const float* __restrict__ G1 = Gw + (nr == 2 ? PW * P : 0) + lane;
     const float s1 = nr == 2 ? 1.0f : 0.0f;      // a single-row unit has no second row
+    float* __restrict__ gl = gb + lane;
     for (int ci = 0; ci < ncols; ++ci) {
         const int e0 = colstart[ci], e1 = colstart[ci + 1];
         if (e0 == e1) continue;
@@ -405,7 +443,7 @@ __device__ __forceinline__ void bwd_walk(const float* __restrict__ Gw, float* __
                 a1[j] = __fmaf_rn(E.w, g1, a1[j]);
             }
         }
-        float* __restrict__ gc = gb + (size_t)(cmin + ci) * C;
+        float* __restrict__ gc = gl + (size_t)(cmin + ci) * C;
         for (int e = 0; e < ne; ++e) {
             const YEnt Y = yt[e];
             const float w1 = Y.w1 * s1;
@@ -416,10 +454,10 @@ __device__ __forceinline__ void bwd_walk(const float* __restrict__ Gw, float* __
     }
 }
 
-template <typename GT, int CPL, int CS, int PHT, int PWT, int SB>
+template <typename GT, int CPL, int CS, int PHT, int PWT, int SB, bool VEC>
 __global__ void __launch_bounds__(224, 3)
 roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int cgroups, const int slabs) {
-    constexpr int CC = 32 * CPL, P = CC + 1;
+    constexpr int CC = 32 * CPL, P = VEC ? CC + 2 : CC + 1;
     extern __shared__ float gsm[];                 // [nwarps][32][P]
     __shared__ XTap xs[kSepTap];
     __shared__ Tap ys[kSepTap];
@@ -624,18 +662,18 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
                 }
             }
         }
-        float* __restrict__ gb = gimg + c0 + lane;
-        if (cc == CC) bwd_walk<CPL, true>(Gw, gb, C, PW, nr, cc, lane, cmin, ncols, colstart, cent, ytab[unit], ne);
-        else bwd_walk<CPL, false>(Gw, gb, C, PW, nr, cc, lane, cmin, ncols, colstart, cent, ytab[unit], ne);
+        float* __restrict__ gb = gimg + c0;
+        if (cc == CC) bwd_walk<CPL, true, VEC>(Gw, gb, C, PW, nr, cc, lane, cmin, ncols, colstart, cent, ytab[unit], ne);
+        else bwd_walk<CPL, false, VEC>(Gw, gb, C, PW, nr, cc, lane, cmin, ncols, colstart, cent, ytab[unit], ne);
         __syncwarp();
     }
 }
 
-template <typename GT, int CPL, int CS, int PHT, int PWT, int SB>
+template <typename GT, int CPL, int CS, int PHT, int PWT, int SB, bool VEC = false>
 static int launch_bwd_sep(const RoiParams& p, const GT* go, int warps, int slabs, cudaStream_t s) {
     constexpr int CC = 32 * CPL;
-    auto kern = roi_align_bwd_sep_kernel<GT, CPL, CS, PHT, PWT, SB>;
-    const size_t smem = (size_t)warps * 32 * (CC + 1) * sizeof(float);
+    auto kern = roi_align_bwd_sep_kernel<GT, CPL, CS, PHT, PWT, SB, VEC>;
+    const size_t smem = (size_t)warps * 32 * (CC + (VEC ? 2 : 1)) * sizeof(float);
     if (smem > 24 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int cgroups = (int)ceil_div(p.C, CC * slabs);
     kern<<<(unsigned)(p.K * cgroups), 32 * warps, smem, s>>>(p, go, cgroups, slabs);
@@ -645,13 +683,20 @@ static int launch_bwd_sep(const RoiParams& p, const GT* go, int warps, int slabs
 template <typename GT>
 static int dispatch_bwd_sep(const RoiParams& p, const GT* g, int cpl, int warps, int slabs, cudaStream_t s) {
     const int sb = sep_env("COIN_ROI_BWD_SB", 16);
+    // vector REDs need 8-byte aligned channel pairs: even C (slab starts are multiples of 64)
+    const bool vec = cpl == 2 && p.C % 2 == 0 && sep_env("COIN_ROI_BWD_VEC", 1) != 0;
     if (p.C == 1024 && p.PH == 14 && p.PW == 14) {
         if (cpl == 1) return launch_bwd_sep<GT, 1, 1024, 14, 14, 16>(p, g, warps, slabs, s);
         if (sb == 32) return launch_bwd_sep<GT, 2, 1024, 14, 14, 32>(p, g, warps, slabs, s);
+        if (vec) return launch_bwd_sep<GT, 2, 1024, 14, 14, 16, true>(p, g, warps, slabs, s);
         return launch_bwd_sep<GT, 2, 1024, 14, 14, 16>(p, g, warps, slabs, s);
     }
     if (cpl == 1) return launch_bwd_sep<GT, 1, 0, 0, 0, 16>(p, g, warps, slabs, s);
-    if (p.C == 1024 && p.PH == 7 && p.PW == 7) return launch_bwd_sep<GT, 2, 1024, 7, 7, 16>(p, g, warps, slabs, s);
+    if (p.C == 1024 && p.PH == 7 && p.PW == 7) {
+        if (vec) return launch_bwd_sep<GT, 2, 1024, 7, 7, 16, true>(p, g, warps, slabs, s);
+        return launch_bwd_sep<GT, 2, 1024, 7, 7, 16>(p, g, warps, slabs, s);
+    }
+    if (vec) return launch_bwd_sep<GT, 2, 0, 0, 0, 16, true>(p, g, warps, slabs, s);
     return launch_bwd_sep<GT, 2, 0, 0, 0, 16>(p, g, warps, slabs, s);
 }
 
