@@ -370,10 +370,10 @@ static int launch_sep(const RoiParams& p, OutT* out, int warps, int slabs, cudaS
 //           its rows merged into a table once per CTA), ONE fp32 RED of Wy-weighted window values -
 //           rows of the unit that share a feature row share the atomic.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBwdYEnt = 16;    // merged y-table entries per unit
-constexpr int kBwdUnits = 16;   // units per RoI handled by the tables (PH <= 32 with two rows per unit)
+constexpr int kBwdYEnt = 16;    // merged y-table entries per unit (7x7 outputs of large RoIs reach grid_h = 5)
+constexpr int kBwdUnits = 8;    // units per RoI handled by the tables (PH <= 16 with two rows per unit)
 constexpr int kBwdCols = 128;   // feature columns of one RoI handled by the column program
-constexpr int kBwdEnt = 2 * kSepTap;   // (bin, weight) entries of the column program
+constexpr int kBwdEnt = 192;    // (bin, weight) entries of the column program
 
 struct YEnt { int off; float w0, w1; int pad; };   // feature-row offset (y*W*C), weights of unit rows 0 and 1
 struct CEnt { int bin; float w; };                 // one bin's combined x weight on a feature column
@@ -455,12 +455,15 @@ __device__ __forceinline__ void bwd_walk(const float* __restrict__ Gw, float* __
 }
 
 template <typename GT, int CPL, int CS, int PHT, int PWT, int SB, bool VEC>
-__global__ void __launch_bounds__(224, 3)
-roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int cgroups, const int slabs) {
+__global__ void __launch_bounds__(224, 4)
+roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int cgroups, const int slabs,
+                         const int trows) {
     constexpr int CC = 32 * CPL, P = VEC ? CC + 2 : CC + 1;
-    extern __shared__ float gsm[];                 // [nwarps][32][P]
-    __shared__ XTap xs[kSepTap];
-    __shared__ Tap ys[kSepTap];
+    extern __shared__ __align__(16) float gsm[];   // [nwarps][32][P]; its head doubles as the tap tables below
+    // the x / y tap tables are only needed while the column program and the y tables are built: they live in
+    // the (not yet used) per-warp tile region, which keeps the static footprint at ~4 KB -> 4 CTAs per SM
+    XTap* xs = reinterpret_cast<XTap*>(gsm);
+    Tap* ys = reinterpret_cast<Tap*>(gsm) + kSepTap;
     __shared__ YEnt ytab[kBwdUnits][kBwdYEnt];
     __shared__ int ycnt[kBwdUnits];
     __shared__ int colstart[kBwdCols + 1];
@@ -620,7 +623,7 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
         return;
     }
 
-    float* __restrict__ Gw = gsm + (size_t)warp * 32 * P;
+    float* __restrict__ Gw = gsm + (size_t)warp * trows * P;   // trows = bins per unit (R * PW <= 32)
     const bool prefetch = p.flags & 1;
     for (int item = warp; item < nunits * nslab; item += nwarps) {
         const int sl = item / nunits, unit = item - sl * nunits;
@@ -673,10 +676,12 @@ template <typename GT, int CPL, int CS, int PHT, int PWT, int SB, bool VEC = fal
 static int launch_bwd_sep(const RoiParams& p, const GT* go, int warps, int slabs, cudaStream_t s) {
     constexpr int CC = 32 * CPL;
     auto kern = roi_align_bwd_sep_kernel<GT, CPL, CS, PHT, PWT, SB, VEC>;
-    const size_t smem = (size_t)warps * 32 * (CC + (VEC ? 2 : 1)) * sizeof(float);
+    const int R = p.PW <= 16 && p.PH >= 2 ? 2 : 1;
+    const int trows = std::min(32, R * p.PW);
+    const size_t smem = std::max<size_t>((size_t)warps * trows * (CC + (VEC ? 2 : 1)) * sizeof(float), 2 * kSepTap * 16);
     if (smem > 24 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int cgroups = (int)ceil_div(p.C, CC * slabs);
-    kern<<<(unsigned)(p.K * cgroups), 32 * warps, smem, s>>>(p, go, cgroups, slabs);
+    kern<<<(unsigned)(p.K * cgroups), 32 * warps, smem, s>>>(p, go, cgroups, slabs, trows);
     return check_launch("roi_align_bwd_sep_kernel");
 }
 
