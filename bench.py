@@ -175,7 +175,8 @@ def main():
         torch.cuda.synchronize()
 
     shape = synth.SHAPES[args.workload]
-    batch = synth.image_batch(shape, seed=synth.SEED + rank)   # every rank owns different images
+    # every rank owns different images (COIN_BENCH_SEED_OFFSET: reproduce another rank's data on one GPU)
+    batch = synth.image_batch(shape, seed=synth.SEED + rank + int(os.environ.get("COIN_BENCH_SEED_OFFSET", "0")))
     step = pipeline.RoIPathStep(shape, dev)
     pinned = step.host_inputs(batch)
     d = step.h2d(pinned)

@@ -331,7 +331,37 @@ roi_align_fwd_sep_kernel(const RoiParams p, OutT* __restrict__ out, const int cg
             } else if (active) {   // no valid x sample for this bin
                 for (int c = 0; c < nch; ++c) ob[(size_t)c * NB] = from_f32<OutT>(0.0f);
             }
-        } else if (active) {   // wide bins (fixed sampling_ratio with large RoIs): per-sample evaluation
+        } else if (maxspan <= 8) {
+            // bins spanning 5..8 feature columns (RoIs wider than ~42 cells, e.g. the whole 75-cell map): the
+            // same scheme with 8 combined column weights (recomputed here so the common path keeps 4 registers)
+            float w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) w[q] = 0.0f;
+            if (active) {
+                const XTap* xt = xs + (ch.pa + pwl) * gw;
+                for (int ix = 0; ix < gw; ++ix) {
+                    const XTap X = xt[ix];
+                    if (X.lo < 0) continue;
+                    const int d = X.lo - first, e = X.hi - first;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) w[q] += (d == q ? X.h : 0.0f) + (e == q ? X.l : 0.0f);
+                }
+            }
+            const int last = max(span - 1, 0);
+            int o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { w[q] *= rcount; o[q] = min(q, last) * P; }
+            if (active) {
+                for (int c = 0; c < nch; ++c) {
+                    float acc = first >= 0 ? w[0] * tb[c] : 0.0f;
+                    if (first >= 0) {
+#pragma unroll
+                        for (int q = 1; q < 8; ++q) acc = __fmaf_rn(w[q], tb[o[q] + c], acc);
+                    }
+                    ob[(size_t)c * NB] = from_f32<OutT>(acc);
+                }
+            }
+        } else if (active) {   // still wider bins (fixed sampling_ratio with huge RoIs): per-sample evaluation
             const XTap* xt = xs + (ch.pa + pwl) * gw;
             const float* __restrict__ trow = Tw + (lr * ch.ncol - ch.ca) * P + half;
             for (int c = 0; c < nch; ++c) {
@@ -726,7 +756,9 @@ int launch_roi_align_fwd_sep(const RoiParams& p, void* out, int out_dtype, cudaS
     const bool small = p.PH * p.PW <= 64;
     int warps = sep_env("COIN_ROI_SEP_WARPS", small ? 8 : (int)std::min<int64_t>(8, std::max<int64_t>(ceil_div(p.PH, rows), 4)));
     warps = std::max(1, std::min(warps, 8));
-    int slabs = sep_env("COIN_ROI_SEP_SLABS", small ? 2 : 4);
+    // few RoIs (e.g. the private-box call of the step): one slab per CTA, so a single very large RoI is spread
+    // over C/64 CTAs instead of leaving a long tail on C/256 of them
+    int slabs = sep_env("COIN_ROI_SEP_SLABS", small ? 2 : (p.K < 1024 ? 1 : 4));
     slabs = std::max(1, std::min(slabs, (int)ceil_div(p.C, cc)));
     if (out_dtype == COIN_F32) return dispatch_sep<float>(p, static_cast<float*>(out), cpl, warps, slabs, s);
     return dispatch_sep<__half>(p, static_cast<__half*>(out), cpl, warps, slabs, s);

@@ -11,7 +11,7 @@ from coin_b200 import pipeline, synth  # noqa: E402
 dev = torch.device("cuda:0")
 shape = synth.SHAPES[sys.argv[1] if len(sys.argv) > 1 else "foggy_roi_head"]
 step = pipeline.RoIPathStep(shape, dev)
-d = step.to_device(synth.image_batch(shape))
+d = step.to_device(synth.image_batch(shape, seed=synth.SEED + int(os.environ.get("COIN_BENCH_SEED_OFFSET", "0"))))
 step.timeline = {}
 step.capture(d, backward=True)
 tl = step.timeline
