@@ -206,7 +206,6 @@ def main():
         out = step.replay()
     t1.record()
     barrier()
-    clocks = sampler.stop()
     ms = t0.elapsed_time(t1)
     launches = launches_per_step * args.steps
     # kernel durations inside the graph: replay, then read the external event pairs (one sample per replay)
@@ -247,6 +246,7 @@ def main():
     l1.record()
     barrier()
     ms_e2e_latency = l0.elapsed_time(l1) / 5
+    clocks = sampler.stop()   # sampled from the start of the timed region to the end of the end-to-end region
 
     ms, ms_e2e, k_fwd, k_bwd, k_fwd_step, k_bwd_step = sharding.max_over_ranks(
         [ms, ms_e2e, k_fwd, k_bwd, k_fwd_step, k_bwd_step], device=dev)
