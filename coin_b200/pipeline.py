@@ -529,6 +529,7 @@ class PipelinedSteps:
         self.compute_done = [None, None]
         self.d2h_done = [None, None]
         self.host_cache = [{}, {}]
+        self.host_views = [None, None]   # per slot: host tensors (views into pinned buffers), order of result_tensors
         self.d2h_bytes = 0
 
     def _h2d(self, n, pinned):
@@ -555,14 +556,33 @@ class PipelinedSteps:
         step = self.slots[s]
         res = step.result_tensors(step.finalize(step._graph_out, counts_host=self.counts_host[s]))
         cache, nbytes = self.host_cache[s], self.counts_host[s].numel() * 4
+        views = [None] * len(res)
         with torch.cuda.stream(self.s_out):
+            # the ~100 small result tensors are packed per dtype on the device (one torch.cat each) and leave
+            # in one copy per dtype; large tensors (the feature-map gradient) are copied directly
+            groups: Dict[torch.dtype, list] = {}
             for i, t in enumerate(res):
-                h = cache.get(i)
-                if h is None or h.numel() < t.numel() or h.dtype != t.dtype:
-                    h = cache[i] = torch.empty((max(t.numel(), 1),), dtype=t.dtype).pin_memory()
-                h[: t.numel()].copy_(t.reshape(-1), non_blocking=True)
                 nbytes += t.numel() * t.element_size()
+                if t.numel() * t.element_size() >= (1 << 20):
+                    h = cache.get(("big", i))
+                    if h is None or h.numel() < t.numel():
+                        h = cache[("big", i)] = torch.empty((t.numel(),), dtype=t.dtype).pin_memory()
+                    h[: t.numel()].copy_(t.reshape(-1), non_blocking=True)
+                    views[i] = h[: t.numel()]
+                else:
+                    groups.setdefault(t.dtype, []).append((i, t.reshape(-1)))
+            for dt, items in groups.items():
+                flat = torch.cat([t for _, t in items]) if len(items) > 1 else items[0][1]
+                h = cache.get(dt)
+                if h is None or h.numel() < flat.numel():
+                    h = cache[dt] = torch.empty((max(2 * flat.numel(), 1),), dtype=dt).pin_memory()
+                h[: flat.numel()].copy_(flat, non_blocking=True)
+                off = 0
+                for i, t in items:
+                    views[i] = h[off: off + t.numel()]
+                    off += t.numel()
             self.d2h_done[s] = self.s_out.record_event()
+        self.host_views[s] = views
         self.d2h_bytes = nbytes
 
     def run(self, pinned: Dict[str, torch.Tensor], steps: int) -> None:
