@@ -229,6 +229,8 @@ def main():
     #      buffered (H2D of step n+1 and D2H of step n-1 overlap the graph of step n)
     h2d_bytes = step.input_bytes(pinned)
     pipe = pipeline.PipelinedSteps(step, d, backward=True)
+    pipe.load_inputs(pinned)          # the step's inputs sit in the pinned staging buffers (a loader's output)
+    pinned = None                     # every step below H2D-copies those pinned buffers
     pipe.run(pinned, 4)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
