@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcoinops.so")
-SOURCES = ["capi.cu", "roi_align.cu", "roi_align_sep.cu", "box_codec.cu", "iou_match.cu", "nms.cu", "fusion_nms.cu",
+SOURCES = ["capi.cu", "roi_align.cu", "roi_align_sep.cu", "roi_align_reg.cu", "box_codec.cu", "iou_match.cu", "nms.cu", "fusion_nms.cu",
            "det_postprocess.cu", "match_abc.cu", "step_dev.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -471,7 +471,10 @@ extern "C" int coin_roi_align_fwd(const coin_level_t* levels_host, int nlevels, 
     COIN_REQUIRE(out, "roi_align_fwd: out is null");
     // COIN_ROI_EXACT: 0 (default) separable fast kernel; 1 bit-exact parity kernel; 2 the parity kernel's FMA variant
     const int mode = env_int("COIN_ROI_EXACT", 0);
-    if (mode == 0) return launch_roi_align_fwd_sep(p, out, out_dtype, as_stream(stream));
+    if (mode == 0) {
+        if (roi_align_fwd_reg_supported(p, out_dtype)) return launch_roi_align_fwd_reg(p, out, as_stream(stream));
+        return launch_roi_align_fwd_sep(p, out, out_dtype, as_stream(stream));
+    }
     LaunchCfg cfg;
     if (int rc = pick_cfg(cfg, C, PH, PW, out_dtype == COIN_F32 ? 4 : 2, "COIN_ROI_FWD")) return rc;
     cudaStream_t s = as_stream(stream);
@@ -490,7 +493,10 @@ extern "C" int coin_roi_align_fwd_dev(const coin_level_t* levels_host, int nleve
     COIN_REQUIRE(out, "roi_align_fwd: out is null");
     p.k_dev = k_dev;
     const int mode = env_int("COIN_ROI_EXACT", 0);
-    if (mode == 0) return launch_roi_align_fwd_sep(p, out, out_dtype, as_stream(stream));
+    if (mode == 0) {
+        if (roi_align_fwd_reg_supported(p, out_dtype)) return launch_roi_align_fwd_reg(p, out, as_stream(stream));
+        return launch_roi_align_fwd_sep(p, out, out_dtype, as_stream(stream));
+    }
     LaunchCfg cfg;
     if (int rc = pick_cfg(cfg, C, PH, PW, out_dtype == COIN_F32 ? 4 : 2, "COIN_ROI_FWD")) return rc;
     cudaStream_t s = as_stream(stream);

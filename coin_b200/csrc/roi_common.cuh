@@ -99,4 +99,8 @@ int launch_roi_align_fwd_sep(const RoiParams& p, void* out, int out_dtype, cudaS
 // host-side launch of the separable backward kernel (roi_align_sep.cu); PW <= 32 only
 int launch_roi_align_bwd_sep(const RoiParams& p, const void* grad_out, int grad_dtype, cudaStream_t s);
 
+// register-tile kernels (roi_align_reg.cu): 14x14 / 7x7 outputs, C % 32 == 0, fp32
+bool roi_align_fwd_reg_supported(const RoiParams& p, int out_dtype);
+int launch_roi_align_fwd_reg(const RoiParams& p, void* out, cudaStream_t s);
+
 }  // namespace coin

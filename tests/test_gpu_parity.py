@@ -78,7 +78,10 @@ def test_roi_align_default_fma_mode_within_tolerance(dev, monkeypatch):
 
 @pytest.mark.parametrize("c,ph,pw,sr,aligned", [(3, 7, 7, 0, True), (40, 14, 14, 0, True), (96, 5, 9, 0, True),
                                                   (64, 7, 7, 2, True), (33, 14, 14, 0, False), (64, 3, 20, 4, True),
-                                                  (32, 1, 1, 0, True), (70, 14, 14, 1, True)])
+                                                  (32, 1, 1, 0, True), (70, 14, 14, 1, True),
+                                                  # the register-tile kernels (C % 32 == 0, 14x14 / 7x7)
+                                                  (64, 14, 14, 0, True), (96, 14, 14, 2, False), (32, 7, 7, 0, True),
+                                                  (128, 14, 14, 1, True), (160, 7, 7, 3, False)])
 def test_roi_align_separable_kernel_cases(dev, monkeypatch, c, ph, pw, sr, aligned):
     """The default (separable) forward kernel against torchvision CPU over geometry edge cases: channel
     tails, non-square outputs, fixed sampling ratios (sample spacing > 1 cell), RoIs outside / larger
