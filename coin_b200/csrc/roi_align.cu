@@ -513,6 +513,8 @@ extern "C" int coin_roi_align_bwd(const coin_level_t* grad_levels_host, int nlev
     if (K == 0) return COIN_OK;
     COIN_REQUIRE(grad_out, "roi_align_bwd: grad_out is null");
     // COIN_ROI_BWD_SEP: 1 (default) the separable kernel of roi_align_sep.cu; 0 the per-sample kernel below
+    if (env_int("COIN_ROI_BWD_SEP", 1) != 0 && roi_align_bwd_reg_supported(p, grad_dtype))
+        return launch_roi_align_bwd_reg(p, grad_out, as_stream(stream));
     if (PW <= 32 && env_int("COIN_ROI_BWD_SEP", 1) != 0) return launch_roi_align_bwd_sep(p, grad_out, grad_dtype, as_stream(stream));
     LaunchCfg cfg;
     if (int rc = pick_cfg(cfg, C, PH, PW, grad_dtype == COIN_F32 ? 4 : 2, "COIN_ROI_BWD")) return rc;

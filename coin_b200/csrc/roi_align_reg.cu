@@ -60,6 +60,20 @@ __device__ __forceinline__ void reg_bulk_store(void* gdst, const void* ssrc, uin
 __device__ __forceinline__ void reg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void reg_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void reg_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(reg_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void reg_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(reg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void reg_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(
+            reg_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // Packed fp32 FMA of Blackwell (FFMA2): d = a * b + c on register pairs, b broadcast to both halves (the
 // compiler folds the {b, b} pair into the instruction's scalar-operand form: no MOV).
 __device__ __forceinline__ float2 ffma2(const float2 a, const float b, const float2 c) {
@@ -73,60 +87,43 @@ __device__ __forceinline__ float2 ffma2(const float2 a, const float b, const flo
     return r;
 }
 
-struct __align__(16) ColWin { float w[6]; int p0h; int pad; };   // the <= 6 non-zero weights of a column, bins [2*p0h, 2*p0h + 6)
-
-// acc[r][H + i] += w[2i .. 2i+1] * t[r] for the 6-bin window starting at the compile-time bin pair H
-template <int R, int NP, int H>
-__device__ __forceinline__ void win6_apply(float2 (&acc)[R][NP], const float4 wa, const float2 wb, const float (&t)[R]) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        acc[r][H + 0] = ffma2(make_float2(wa.x, wa.y), t[r], acc[r][H + 0]);
-        acc[r][H + 1] = ffma2(make_float2(wa.z, wa.w), t[r], acc[r][H + 1]);
-        acc[r][H + 2] = ffma2(wb, t[r], acc[r][H + 2]);
-    }
-}
-
-// the window start is warp-uniform: a jump table over statically indexed accumulators
-template <int R, int NP>
-__device__ __forceinline__ void win6_switch(float2 (&acc)[R][NP], const int p0h, const float4 wa, const float2 wb,
-                                            const float (&t)[R]) {
-    static_assert(NP >= 3 && NP <= 8, "window switch covers 6 <= PW <= 16");
-    switch (p0h) {
-#define COIN_WIN_CASE(H) \
-    case H:              \
-        if constexpr (H + 3 <= NP) win6_apply<R, NP, (H + 3 <= NP ? H : 0)>(acc, wa, wb, t); \
-        break;
-        COIN_WIN_CASE(0) COIN_WIN_CASE(1) COIN_WIN_CASE(2) COIN_WIN_CASE(3) COIN_WIN_CASE(4) COIN_WIN_CASE(5)
-#undef COIN_WIN_CASE
-        default: break;
-    }
+__device__ __forceinline__ float2 ffma2v(const float2 a, const float2 b, const float2 c) {   // a * b + c, pairwise
+    unsigned long long xa, xb, xc, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(xa), "l"(xb), "l"(xc));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(d));
+    return r;
 }
 
 // shared tables of one RoI (built once per CTA); units are pairs of output rows
 template <int NU>
 struct RegTables {
     float wxd[kRegCols + 2][16];          // combined x weight (already / count) of every bin on every column
-    ColWin win[kRegCols + 2];             // the same weights as a 6-bin window (valid when maxspan <= 6)
-    int yoff[NU][kRegYEnt];               // merged y table of every unit: feature-row offset (y*W*C) ...
-    float2 yw[NU][kRegYEnt];              // ... and its weights on the unit's two output rows
-    int ycnt[NU];
-    int mode, cmin, cmax, maxspan;        // mode 0: tables, 1: direct evaluation, 2: the RoI pools to zeros
+    float2 yw[NU][kRegYEnt];              // merged y table of a unit: weights of feature row ymin[u] + e on its two rows
+    int ymin[NU], ycnt[NU];
+    int mode;                             // 0: tables, 1: direct evaluation, 2: the RoI pools to zeros
 };
 
-// Builds the tables; every thread of the CTA must call it. `scratch` (>= 2*kRegTap*16 bytes, 16-byte aligned) holds
-// the per-sample tap tables while the merged tables are built and is free again on return.
+// Builds the tables (two CTA barriers); every thread of the CTA must call it. `scratch` (>= 2*kRegTap*16 bytes,
+// 16-byte aligned) holds the per-sample tap tables meanwhile and is free again on return. Returns the RoI's
+// feature-column range [cmin, cmin + ncols), ncols even (padded with a zero-weight column).
 template <int PH, int PW, int NT>
 __device__ __forceinline__ void reg_build_tables(RegTables<(PH + 1) / 2>& tb, void* scratch, const RoiGeom& g,
-                                                 const int H, const int W, const int C) {
+                                                 const int H, const int W, int& cmin, int& ncols, int& creal0,
+                                                 int& creal1) {
     constexpr int NU = (PH + 1) / 2;
     RXTap* xs = reinterpret_cast<RXTap*>(scratch);
-    Tap* ys = reinterpret_cast<Tap*>(scratch) + kRegTap;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    RXTap* ys = xs + kRegTap;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int gh = g.grid_h, gw = g.grid_w;
     const bool empty = gh <= 0 || gw <= 0;
     const bool tables = !empty && (long long)PW * gw <= kRegTap && (long long)PH * gh <= kRegTap;
     const float rcount = 1.0f / g.count;
-    if (tid == 0) { tb.mode = empty ? 2 : (tables ? 0 : 1); tb.cmin = INT_MAX; tb.cmax = -1; tb.maxspan = 0; }
+    cmin = 0; ncols = 0; creal0 = 0; creal1 = 0;
+    if (tid == 0) tb.mode = empty ? 2 : (tables ? 0 : 1);
     if (tables) {
         const int nx = PW * gw, ny = PH * gh;
         for (int s = tid; s < nx; s += NT) {
@@ -135,79 +132,70 @@ __device__ __forceinline__ void reg_build_tables(RegTables<(PH + 1) / 2>& tb, vo
         }
         for (int s = NT - 1 - tid; s < ny; s += NT) {
             const int ph = s / gh;
-            ys[s] = make_tap(g.start_h, g.bin_h, ph, s - ph * gh, gh, H, W * C);
+            ys[s] = reg_xtap(g.start_h, g.bin_h, ph, s - ph * gh, gh, H);
         }
     }
     __syncthreads();
-    if (tables) {
-        for (int u = NT - 1 - tid; u < NU; u += NT) {   // merged y table: one thread per unit
-            int n = 0;
-            bool overflow = false;
-            for (int r = 0; r < 2 && u * 2 + r < PH && !overflow; ++r)
-                for (int iy = 0; iy < gh && !overflow; ++iy) {
-                    const Tap Y = ys[(u * 2 + r) * gh + iy];
-                    if (Y.lo < 0) continue;
-                    for (int t = 0; t < 2; ++t) {
-                        const int off = t ? Y.hi : Y.lo;
-                        const float w = t ? Y.l : Y.h;
-                        int e = 0;
-                        while (e < n && tb.yoff[u][e] != off) ++e;
-                        if (e == n) {
-                            if (n == kRegYEnt) { overflow = true; break; }
-                            tb.yoff[u][e] = off;
-                            tb.yw[u][e] = make_float2(0.0f, 0.0f);
-                            ++n;
-                        }
-                        if (r == 0) tb.yw[u][e].x += w; else tb.yw[u][e].y += w;
-                    }
-                }
-            tb.ycnt[u] = n;
-            if (overflow) tb.mode = 1;
+    if (!tables) return;
+    // merged y tables: thread (unit, entry e, row r) sums the weights of row 2u + r's samples on feature row ymin + e.
+    // The rows a unit touches are consecutive (sample positions are monotone), so the table is just [ymin, ymin + n).
+    for (int idx = tid; idx < NU * kRegYEnt * 2; idx += NT) {
+        const int r = idx & 1, e = (idx >> 1) % kRegYEnt, u = idx / (2 * kRegYEnt);
+        const int s0 = u * 2 * gh, s1 = min(PH, u * 2 + 2) * gh;
+        int ylo = INT_MAX, yhi = -1;
+        for (int sidx = s0; sidx < s1; ++sidx) {
+            const RXTap Y = ys[sidx];
+            if (Y.lo >= 0) { ylo = min(ylo, Y.lo); yhi = max(yhi, Y.hi); }
         }
-        if (warp == 0) {   // feature-column range of the RoI
-            int lo = INT_MAX, hi = -1;
-            for (int s = lane; s < PW * gw; s += 32) {
-                const RXTap X = xs[s];
-                if (X.lo >= 0) { lo = min(lo, X.lo); hi = max(hi, X.hi); }
-            }
-            lo = __reduce_min_sync(0xffffffffu, lo);
-            hi = __reduce_max_sync(0xffffffffu, hi);
-            if (lane == 0) {
-                tb.cmin = lo; tb.cmax = hi;
-                if (hi < 0) tb.mode = 2;                          // every x sample lies outside the map
-                else if (hi - lo + 1 > kRegCols) tb.mode = 1;
-            }
-        }
-    }
-    __syncthreads();
-    if (tb.mode != 0) return;
-    const int cmin = tb.cmin, ncols = tb.cmax - cmin + 1;
-    for (int idx = tid; idx < (ncols + 2) * 16; idx += NT) {   // dense weights (+ two all-zero padding columns)
-        const int ci = idx >> 4, pw = idx & 15, col = cmin + ci;
+        const int n = yhi < 0 ? 0 : yhi - ylo + 1;
         float w = 0.0f;
-        if (pw < PW && ci < ncols)
-            for (int ix = 0; ix < gw; ++ix) {
-                const RXTap X = xs[pw * gw + ix];
-                if (X.lo < 0) continue;
-                if (X.lo == col) w += X.h;
-                if (X.hi == col) w += X.l;
+        if (e < n && u * 2 + r < PH) {
+            const int y = ylo + e;
+            for (int iy = 0; iy < gh; ++iy) {
+                const RXTap Y = ys[(u * 2 + r) * gh + iy];
+                if (Y.lo < 0) continue;
+                if (Y.lo == y) w += Y.h;
+                if (Y.hi == y) w += Y.l;
             }
-        tb.wxd[ci][pw] = w * rcount;
+        }
+        if (r == 0) tb.yw[u][e].x = w; else tb.yw[u][e].y = w;
+        if (e == 0 && r == 0) {
+            tb.ymin[u] = yhi < 0 ? 0 : ylo;
+            tb.ycnt[u] = n;
+            if (n > kRegYEnt) tb.mode = 1;
+        }
     }
-    __syncthreads();
-    for (int ci = tid; ci < ncols + 2; ci += NT) {             // window of non-zero bins per column
-        int first = -1, last = -1;
-#pragma unroll
-        for (int pw = 0; pw < PW; ++pw)
-            if (tb.wxd[ci][pw] != 0.0f) { if (first < 0) first = pw; last = pw; }
-        constexpr int kMaxH = (PW + 1) / 2 >= 3 ? (PW + 1) / 2 - 3 : 0;      // last window start (in bin pairs)
-        const int p0h = first < 0 ? 0 : min(first >> 1, kMaxH);
-        ColWin cw;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) cw.w[i] = tb.wxd[ci][2 * p0h + i];       // columns >= PW of wxd are zero
-        cw.p0h = p0h; cw.pad = 0;
-        tb.win[ci] = cw;
-        if (first >= 0) atomicMax(&tb.maxspan, last - 2 * p0h + 1);
+    // feature-column range of the RoI (every warp computes it for itself)
+    int lo = INT_MAX, hi = -1;
+    for (int s = lane; s < PW * gw; s += 32) {
+        const RXTap X = xs[s];
+        if (X.lo >= 0) { lo = min(lo, X.lo); hi = max(hi, X.hi); }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    const int rlo = lo, rhi = hi;                     // the columns that carry weight
+    if (hi >= 0 && ((hi - lo + 1) & 1)) {             // even column count: the forward walks two columns per step
+        if (hi + 1 < W) ++hi; else if (lo > 0) --lo;  // (the added column has zero weights; W == 1: mode 1)
+    }
+    if (hi < 0) {
+        if (tid == 0) tb.mode = 2;                    // every x sample lies outside the map
+    } else if (hi - lo + 1 > kRegCols || ((hi - lo + 1) & 1)) {
+        if (tid == 0) tb.mode = 1;
+    } else {
+        cmin = lo; ncols = hi - lo + 1;
+        creal0 = rlo - lo; creal1 = rhi - lo + 1;
+        for (int idx = tid; idx < ncols * 16; idx += NT) {   // dense x weights
+            const int ci = idx >> 4, pw = idx & 15, col = cmin + ci;
+            float w = 0.0f;
+            if (pw < PW)
+                for (int ix = 0; ix < gw; ++ix) {
+                    const RXTap X = xs[pw * gw + ix];
+                    if (X.lo < 0) continue;
+                    if (X.lo == col) w += X.h;
+                    if (X.hi == col) w += X.l;
+                }
+            tb.wxd[ci][pw] = w * rcount;
+        }
     }
     __syncthreads();
 }
@@ -215,89 +203,60 @@ __device__ __forceinline__ void reg_build_tables(RegTables<(PH + 1) / 2>& tb, vo
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-// x phase of one feature column: acc[r][pw] += Wx[col][pw] * t[r]
-template <int PW, bool DENSE, typename TB>
-__device__ __forceinline__ void fwd_xphase(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const int ci, const float (&t)[2]) {
+// x phase of one feature column: acc[r][pw] += Wx[col][pw] * t[r] over all PW bins (the weight row is mostly zeros
+// for wide RoIs, but a branch-free body with statically indexed accumulators beats a warp-uniform window switch)
+template <int PW, typename TB>
+__device__ __forceinline__ void fwd_xphase(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const int ci, const float2 t2) {
     constexpr int NP = (PW + 1) / 2;
-    if (DENSE) {
-        const float4* wrow = reinterpret_cast<const float4*>(tb.wxd[ci]);
+    const float4* wrow = reinterpret_cast<const float4*>(tb.wxd[ci]);
 #pragma unroll
-        for (int i = 0; i < (NP + 1) / 2; ++i) {
-            const float4 x = wrow[i];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                acc[r][2 * i] = ffma2(make_float2(x.x, x.y), t[r], acc[r][2 * i]);
-                if (2 * i + 1 < NP) acc[r][2 * i + 1] = ffma2(make_float2(x.z, x.w), t[r], acc[r][2 * i + 1]);
-            }
-        }
-    } else {
-        const float4* cw = reinterpret_cast<const float4*>(&tb.win[ci]);
-        const float4 wa = cw[0], wb = cw[1];
-        win6_switch<2, NP>(acc, __float_as_int(wb.z), wa, make_float2(wb.x, wb.y), t);
-    }
-}
-
-// NQ feature columns at pj[.] (+ q * cstride): all NJ * NQ loads first, then the y and x phases
-template <int PW, int CS, bool DENSE, int NJ, int NQ, typename TB>
-__device__ __forceinline__ void fwd_step(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const int ci,
-                                         const float* const (&pj)[NJ], const float2 (&yw)[NJ], const int C) {
-    const int cstride = CS ? CS : C;
-    float v[NQ][NJ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) v[q][j] = __ldg(pj[j] + q * cstride);
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        float2 t2 = make_float2(yw[0].x * v[q][0], yw[0].y * v[q][0]);
-#pragma unroll
-        for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j], t2);
-        const float t[2] = {t2.x, t2.y};
-        fwd_xphase<PW, DENSE>(acc, tb, ci + q, t);
-    }
-}
-
-// One pass over the RoI's feature columns for one unit and NJ merged y entries starting at e0.
-template <int PW, int CS, bool DENSE, int NJ, typename TB>
-__device__ __forceinline__ void fwd_columns(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const int u, const int e0,
-                                            const float* __restrict__ fcol, const int ncols, const int C) {
-    const float* pj[NJ];
-    float2 yw[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        pj[j] = fcol + tb.yoff[u][e0 + j];
-        yw[j] = tb.yw[u][e0 + j];
-    }
-    const int cstride = CS ? CS : C;
-    constexpr int NQ = NJ <= 2 ? 4 : 2;       // columns per step: 8 independent loads in flight
-    int ci = 0;
-    for (; ci + NQ <= ncols; ci += NQ) {
-        fwd_step<PW, CS, DENSE, NJ, NQ>(acc, tb, ci, pj, yw, C);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) pj[j] += NQ * cstride;
-    }
-    for (; ci < ncols; ++ci) {
-        fwd_step<PW, CS, DENSE, NJ, 1>(acc, tb, ci, pj, yw, C);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) pj[j] += cstride;
-    }
-}
-
-template <int PW, int CS, bool DENSE, typename TB>
-__device__ __forceinline__ void fwd_unit(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const int u, const int ne,
-                                         const float* __restrict__ fcol, const int ncols, const int C) {
-    for (int e0 = 0; e0 < ne; e0 += 4) {
-        switch (min(4, ne - e0)) {   // warp-uniform
-            case 1: fwd_columns<PW, CS, DENSE, 1>(acc, tb, u, e0, fcol, ncols, C); break;
-            case 2: fwd_columns<PW, CS, DENSE, 2>(acc, tb, u, e0, fcol, ncols, C); break;
-            case 3: fwd_columns<PW, CS, DENSE, 3>(acc, tb, u, e0, fcol, ncols, C); break;
-            default: fwd_columns<PW, CS, DENSE, 4>(acc, tb, u, e0, fcol, ncols, C); break;
+    for (int i = 0; i < (NP + 1) / 2; ++i) {
+        const float4 x = wrow[i];
+        acc[0][2 * i] = ffma2(make_float2(x.x, x.y), t2.x, acc[0][2 * i]);
+        acc[1][2 * i] = ffma2(make_float2(x.x, x.y), t2.y, acc[1][2 * i]);
+        if (2 * i + 1 < NP) {
+            acc[0][2 * i + 1] = ffma2(make_float2(x.z, x.w), t2.x, acc[0][2 * i + 1]);
+            acc[1][2 * i + 1] = ffma2(make_float2(x.z, x.w), t2.y, acc[1][2 * i + 1]);
         }
     }
 }
 
-template <int PH, int PW, int CS>
-__global__ void __launch_bounds__(32 * ((PH + 1) / 2), (PH * PW > 64 ? 4 : 8))
+// One pass over the RoI's feature columns for one unit and NJ consecutive feature rows starting at p0 (row stride rs).
+template <int PW, int CS, int NJ, typename TB>
+__device__ __forceinline__ void fwd_columns(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const float2 (&yw)[4],
+                                            const float* __restrict__ p0, const int rs, const int ncols, const int C) {
+    const int cstride = CS ? CS : C;
+#pragma unroll 1
+    for (int ci = 0; ci < ncols; ci += 2) {   // two columns per step: 2 * NJ independent 128-byte loads in flight
+        float v[2][NJ];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) v[q][j] = __ldg(p0 + j * rs + q * cstride);
+        p0 += 2 * cstride;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float2 t2 = make_float2(yw[0].x * v[q][0], yw[0].y * v[q][0]);
+#pragma unroll
+            for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j], t2);
+            fwd_xphase<PW>(acc, tb, ci + q, t2);
+        }
+    }
+}
+
+template <int PW, int CS, typename TB>
+__device__ __forceinline__ void fwd_chunk(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const int nj, const float2 (&yw)[4],
+                                          const float* __restrict__ p0, const int rs, const int ncols, const int C) {
+    switch (nj) {   // warp-uniform
+        case 1: fwd_columns<PW, CS, 1>(acc, tb, yw, p0, rs, ncols, C); break;
+        case 2: fwd_columns<PW, CS, 2>(acc, tb, yw, p0, rs, ncols, C); break;
+        case 3: fwd_columns<PW, CS, 3>(acc, tb, yw, p0, rs, ncols, C); break;
+        default: fwd_columns<PW, CS, 4>(acc, tb, yw, p0, rs, ncols, C); break;
+    }
+}
+
+template <int PH, int PW, int CS, int OCC>
+__global__ void __launch_bounds__(32 * ((PH + 1) / 2), OCC)
 roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int cgroups, const int slabs) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW, NT = 32 * NU, NP = (PW + 1) / 2;
     constexpr bool VEC = PW % 2 == 0 && (2 * PW) % 4 == 0 && NB % 4 == 0;
@@ -318,7 +277,8 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
     const int nslab = min(slabs, (C - cg0) / 32);
     float* __restrict__ oroi = out + (size_t)k * C * NB;
 
-    reg_build_tables<PH, PW, NT>(tb, tile, g, H, W, C);
+    int cmin, ncols, creal0, creal1;
+    reg_build_tables<PH, PW, NT>(tb, tile, g, H, W, cmin, ncols, creal0, creal1);
     const int mode = tb.mode;
 
     if (mode == 2) {   // no sample inside the map: the RoI pools to zeros
@@ -350,26 +310,35 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
         return;
     }
 
-    const int cmin = tb.cmin, ncols = tb.cmax - cmin + 1;
-    const bool dense = PW < 6 || tb.maxspan > 6;
-    const int ne = tb.ycnt[u];
+    // the unit's merged y table stays in registers across the CTA's channel slabs (first <= 4 feature rows)
+    const int ne = tb.ycnt[u], rs = W * C;
+    float2 yw0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) yw0[j] = j < ne ? tb.yw[u][j] : make_float2(0.0f, 0.0f);
+    const float* __restrict__ funit = fimg + (size_t)tb.ymin[u] * rs + (size_t)cmin * C + cg0 + lane;
     const int nr = min(2, PH - u * 2);
     const uint64_t pol = l2_evict_first_policy();
+    float* __restrict__ tp = tile + lane * NB + u * (2 * PW);
 
     for (int sl = 0; sl < nslab; ++sl) {
-        const int c0 = cg0 + sl * 32;
-        const float* __restrict__ fcol = fimg + c0 + lane + (size_t)cmin * C;
+        const float* __restrict__ fcol = funit + sl * 32;
         float2 acc[2][NP];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int i = 0; i < NP; ++i) acc[r][i] = make_float2(0.0f, 0.0f);
-        if (dense) fwd_unit<PW, CS, true>(acc, tb, u, ne, fcol, ncols, C);
-        else fwd_unit<PW, CS, false>(acc, tb, u, ne, fcol, ncols, C);
+        if (ne > 0) {
+            fwd_chunk<PW, CS>(acc, tb, min(ne, 4), yw0, fcol, rs, ncols, C);
+            for (int e0 = 4; e0 < ne; e0 += 4) {   // tall RoIs: further chunks of <= 4 feature rows
+                float2 yw[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) yw[j] = e0 + j < ne ? tb.yw[u][e0 + j] : make_float2(0.0f, 0.0f);
+                fwd_chunk<PW, CS>(acc, tb, min(ne - e0, 4), yw, fcol + (size_t)e0 * rs, rs, ncols, C);
+            }
+        }
         // the previous slab's bulk store must have read the tile before it is overwritten
         if (sl > 0 && threadIdx.x == 0) reg_bulk_wait_read();
         __syncthreads();
-        float* __restrict__ tp = tile + lane * NB + u * (2 * PW);
         if (VEC) {   // rows 2u, 2u+1 are 2*PW consecutive floats of the channel's plane
             float4* tp4 = reinterpret_cast<float4*>(tp);
 #pragma unroll
@@ -387,19 +356,204 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
         }
         reg_fence_async();
         __syncthreads();
-        if (threadIdx.x == 0) reg_bulk_store(oroi + (size_t)c0 * NB, tile, 32 * NB * sizeof(float), pol);
+        if (threadIdx.x == 0) reg_bulk_store(oroi + (size_t)(cg0 + sl * 32) * NB, tile, 32 * NB * sizeof(float), pol);
     }
     if (threadIdx.x == 0) reg_bulk_wait_read();
 }
 
-template <int PH, int PW, int CS>
+template <int PH, int PW, int CS, int OCC>
 static int launch_fwd_reg(const RoiParams& p, float* out, int slabs, cudaStream_t s) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW;
-    auto kern = roi_align_fwd_reg_kernel<PH, PW, CS>;
+    auto kern = roi_align_fwd_reg_kernel<PH, PW, CS, OCC>;
     const size_t smem = (size_t)32 * NB * sizeof(float);
     const int cgroups = (int)ceil_div(p.C, 32 * slabs);
     kern<<<(unsigned)(p.K * cgroups), 32 * NU, smem, s>>>(p, out, cgroups, slabs);
     return check_launch("roi_align_fwd_reg_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: grad_in[y][x][c] += sum_{ph,pw} Wy[ph][y] * Wx[pw][x] / count * g[c][ph][pw]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reg_bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(reg_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            reg_smem_u32(sdst)),
+        "l"(gsrc), "r"(bytes), "r"(reg_smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+
+// One pass over the RoI's feature columns for one unit: u_r = sum_pw Wx[col][pw] * g[r][pw], then one fp32 RED per
+// merged feature row. The first NJ (<= 4) rows' weights are in registers; taller units read the rest from the table.
+template <int PW, int CS, int NJ, typename TB>
+__device__ __forceinline__ void bwd_columns(const float2 (&gr)[2][(PW + 1) / 2], const TB& tb, const int u, const int ne,
+                                            const float2 (&yw)[4], float* __restrict__ p0, const int rs, const int c0,
+                                            const int c1, const int C) {
+    constexpr int NP = (PW + 1) / 2;
+    const int cstride = CS ? CS : C;
+    p0 += (size_t)c0 * cstride;
+    for (int ci = c0; ci < c1; ++ci) {
+        const float4* wrow = reinterpret_cast<const float4*>(tb.wxd[ci]);
+        float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int i = 0; i < (NP + 1) / 2; ++i) {
+            const float4 x = wrow[i];
+            s0 = ffma2v(gr[0][2 * i], make_float2(x.x, x.y), s0);
+            s1 = ffma2v(gr[1][2 * i], make_float2(x.x, x.y), s1);
+            if (2 * i + 1 < NP) {
+                s0 = ffma2v(gr[0][2 * i + 1], make_float2(x.z, x.w), s0);
+                s1 = ffma2v(gr[1][2 * i + 1], make_float2(x.z, x.w), s1);
+            }
+        }
+        const float u0 = s0.x + s0.y, u1 = s1.x + s1.y;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) atomicAdd(p0 + j * rs, __fmaf_rn(yw[j].y, u1, yw[j].x * u0));
+        for (int j = 4; j < ne; ++j) {   // tall RoIs (warp-uniform, rare)
+            const float2 w = tb.yw[u][j];
+            atomicAdd(p0 + (size_t)j * rs, __fmaf_rn(w.y, u1, w.x * u0));
+        }
+        p0 += cstride;
+    }
+}
+
+template <int PH, int PW, int CS, int OCC>
+__global__ void __launch_bounds__(32 * ((PH + 1) / 2), OCC)
+roi_align_bwd_reg_kernel(const RoiParams p, const float* __restrict__ go, const int cgroups, const int slabs) {
+    constexpr int NU = (PH + 1) / 2, NB = PH * PW, NT = 32 * NU, NP = (PW + 1) / 2;
+    constexpr bool VEC = PW % 2 == 0 && (2 * PW) % 4 == 0 && NB % 4 == 0;
+    constexpr uint32_t kTileBytes = 32 * NB * sizeof(float);
+    extern __shared__ __align__(128) float tile[];   // [32 channels][NB] grad_out tile, then 4 KB of tap-table scratch
+    __shared__ RegTables<NU> tb;
+    __shared__ __align__(8) uint64_t bar_full;
+
+    const int k = blockIdx.x / cgroups;
+    if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
+    const int cg0 = (blockIdx.x - k * cgroups) * (32 * slabs);
+    const int lane = threadIdx.x & 31, u = threadIdx.x >> 5;
+    const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
+    const coin_level_t L = p.lv[lvl];
+    const int H = L.H, W = L.W;
+    const int C = CS ? CS : p.C;
+    const RoiGeom g = roi_geometry(p.rois + 5 * (size_t)k, L.spatial_scale, PH, PW, p.sampling_ratio, p.aligned);
+    if (g.grid_h <= 0 || g.grid_w <= 0) return;    // no samples: no gradient
+    float* __restrict__ gimg = const_cast<float*>(L.feat_nhwc) + (size_t)g.batch * H * W * C;
+    const int nslab = min(slabs, (C - cg0) / 32);
+    const float* __restrict__ groi = go + ((size_t)k * C + cg0) * NB;
+    const uint64_t pol = l2_evict_first_policy();
+
+    if (threadIdx.x == 0) {   // the first tile streams in while the tables are built
+        reg_mbar_init(&bar_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        reg_bulk_load(tile, groi, kTileBytes, &bar_full, pol);
+    }
+    int cmin, ncols, creal0, creal1;
+    reg_build_tables<PH, PW, NT>(tb, tile + 32 * NB, g, H, W, cmin, ncols, creal0, creal1);
+    const int mode = tb.mode;
+
+    if (mode == 2) {   // no sample inside the map: no gradient (the tile in flight must land before the CTA may exit)
+        reg_mbar_wait(&bar_full, 0);
+        return;
+    }
+    if (mode == 1) {   // exotic geometry: direct 4-tap scatter
+        reg_mbar_wait(&bar_full, 0);
+        const float rcount = 1.0f / g.count;
+        for (int sl = 0; sl < nslab; ++sl) {
+            const int c = cg0 + sl * 32 + lane;
+            for (int b = u; b < NB; b += NU) {
+                const int ph = b / PW, pw = b - ph * PW;
+                const float gv = __ldg(groi + (size_t)(sl * 32 + lane) * NB + b) * rcount;
+                for (int iy = 0; iy < g.grid_h; ++iy) {
+                    const Tap Y = make_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H, W * C);
+                    if (Y.lo < 0) continue;
+                    for (int ix = 0; ix < g.grid_w; ++ix) {
+                        const Tap X = make_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W, C);
+                        if (X.lo < 0) continue;
+                        float* f = gimg + c;
+                        atomicAdd(f + Y.lo + X.lo, Y.h * X.h * gv);
+                        atomicAdd(f + Y.lo + X.hi, Y.h * X.l * gv);
+                        atomicAdd(f + Y.hi + X.lo, Y.l * X.h * gv);
+                        atomicAdd(f + Y.hi + X.hi, Y.l * X.l * gv);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    const int ne = tb.ycnt[u], rs = W * C;
+    float2 yw0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) yw0[j] = j < ne ? tb.yw[u][j] : make_float2(0.0f, 0.0f);
+    float* __restrict__ gunit = gimg + (size_t)tb.ymin[u] * rs + (size_t)cmin * C + cg0 + lane;
+    const int nr = min(2, PH - u * 2);
+    const float* __restrict__ tp = tile + lane * NB + u * (2 * PW);
+
+    for (int sl = 0; sl < nslab; ++sl) {
+        reg_mbar_wait(&bar_full, sl & 1);          // the slab's [32][NB] grad_out tile has landed
+        float2 gr[2][NP];
+        if (VEC) {   // rows 2u, 2u+1 are 2*PW consecutive floats of the channel's plane
+            const float4* tp4 = reinterpret_cast<const float4*>(tp);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const float4 x = tp4[i];
+                const int r = (2 * i) / NP, a = 2 * i - r * NP;
+                const int r2 = (2 * i + 1) / NP, b = 2 * i + 1 - r2 * NP;
+                gr[r][a] = make_float2(x.x, x.y);
+                gr[r2][b] = make_float2(x.z, x.w);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const int b0 = 2 * i, b1 = 2 * i + 1;
+                    gr[r][i].x = (r < nr && b0 < PW) ? tp[r * PW + b0] : 0.0f;
+                    gr[r][i].y = (r < nr && b1 < PW) ? tp[r * PW + b1] : 0.0f;
+                }
+        }
+        __syncthreads();                            // every warp holds its rows in registers: the tile is free
+        if (threadIdx.x == 0 && sl + 1 < nslab)     // the next tile streams in under this slab's arithmetic
+            reg_bulk_load(tile, groi + (size_t)(sl + 1) * 32 * NB, kTileBytes, &bar_full, pol);
+        if (ne > 0) {
+            float* __restrict__ gcol = gunit + sl * 32;
+            switch (min(ne, 4)) {   // warp-uniform
+                case 1: bwd_columns<PW, CS, 1>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
+                case 2: bwd_columns<PW, CS, 2>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
+                case 3: bwd_columns<PW, CS, 3>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
+                default: bwd_columns<PW, CS, 4>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
+            }
+        }
+    }
+}
+
+template <int PH, int PW, int CS, int OCC>
+static int launch_bwd_reg(const RoiParams& p, const float* go, int slabs, cudaStream_t s) {
+    constexpr int NU = (PH + 1) / 2, NB = PH * PW;
+    auto kern = roi_align_bwd_reg_kernel<PH, PW, CS, OCC>;
+    const size_t smem = (size_t)32 * NB * sizeof(float) + 2 * kRegTap * sizeof(RXTap);
+    const int cgroups = (int)ceil_div(p.C, 32 * slabs);
+    kern<<<(unsigned)(p.K * cgroups), 32 * NU, smem, s>>>(p, go, cgroups, slabs);
+    return check_launch("roi_align_bwd_reg_kernel");
+}
+
+bool roi_align_bwd_reg_supported(const RoiParams& p, int grad_dtype) {
+    if (reg_env("COIN_ROI_REG", 1) == 0 || reg_env("COIN_ROI_BWD_REG", 1) == 0) return false;
+    if (grad_dtype != COIN_F32 || p.C % 32 != 0) return false;
+    return (p.PH == 14 && p.PW == 14) || (p.PH == 7 && p.PW == 7);
+}
+
+int launch_roi_align_bwd_reg(const RoiParams& p, const void* grad_out, cudaStream_t s) {
+    if (reinterpret_cast<uintptr_t>(grad_out) & 15) return fail(COIN_ERR_INVALID, "roi_align_bwd: grad_out must be 16-byte aligned");
+    const float* g = static_cast<const float*>(grad_out);
+    const int nsl = (int)(p.C / 32);
+    int slabs = reg_env("COIN_ROI_BWD_REG_SLABS", p.K < 1024 ? 2 : 8);
+    slabs = std::max(1, std::min(slabs, nsl));
+    if (p.PH == 14) {
+        if (p.C == 1024) return launch_bwd_reg<14, 14, 1024, 4>(p, g, slabs, s);
+        return launch_bwd_reg<14, 14, 0, 4>(p, g, slabs, s);
+    }
+    if (p.C == 1024) return launch_bwd_reg<7, 7, 1024, 8>(p, g, slabs, s);
+    return launch_bwd_reg<7, 7, 0, 8>(p, g, slabs, s);
 }
 
 bool roi_align_fwd_reg_supported(const RoiParams& p, int out_dtype) {
@@ -416,11 +570,14 @@ int launch_roi_align_fwd_reg(const RoiParams& p, void* out, cudaStream_t s) {
     int slabs = reg_env("COIN_ROI_REG_SLABS", p.K < 1024 ? 2 : 8);
     slabs = std::max(1, std::min(slabs, nsl));
     if (p.PH == 14) {
-        if (p.C == 1024) return launch_fwd_reg<14, 14, 1024>(p, o, slabs, s);
-        return launch_fwd_reg<14, 14, 0>(p, o, slabs, s);
+        if (p.C == 1024) {
+            if (reg_env("COIN_ROI_REG_OCC", 4) == 3) return launch_fwd_reg<14, 14, 1024, 3>(p, o, slabs, s);
+            return launch_fwd_reg<14, 14, 1024, 4>(p, o, slabs, s);
+        }
+        return launch_fwd_reg<14, 14, 0, 4>(p, o, slabs, s);
     }
-    if (p.C == 1024) return launch_fwd_reg<7, 7, 1024>(p, o, slabs, s);
-    return launch_fwd_reg<7, 7, 0>(p, o, slabs, s);
+    if (p.C == 1024) return launch_fwd_reg<7, 7, 1024, 8>(p, o, slabs, s);
+    return launch_fwd_reg<7, 7, 0, 8>(p, o, slabs, s);
 }
 
 }  // namespace coin

@@ -123,6 +123,27 @@ def test_roi_align_backward_foggy_shape(dev):
     close(xx.grad, clib.roi_align_bwd(go, rois, 1.0 / 16, 14, 14, 2, 64, h, w, 0, True), scale=float(xr.grad.abs().max()))
 
 
+@pytest.mark.parametrize("c,pooled,sr,aligned", [(64, 7, 0, True), (96, 14, 2, False), (32, 14, 0, True), (160, 7, 3, True)])
+def test_roi_align_backward_register_tile_cases(dev, c, pooled, sr, aligned):
+    """The register-tile backward kernel (C % 32 == 0, 14x14 / 7x7) against torchvision CPU over the geometry edge
+    cases of the forward test: RoIs outside / larger than / much smaller than the map, inverted RoIs."""
+    g = synth.gen(91 + c)
+    h, w = 37, 75
+    x = torch.randn(2, c, h, w, generator=g)
+    boxes = synth.random_boxes(g, 70, 600, 1200, lo=4.0, hi=1100.0, min_side=0.5)
+    extra = torch.tensor([[-100.0, -100.0, -50.0, -50.0], [0.0, 0.0, 1200.0, 600.0], [64.0, 64.0, 64.2, 64.1],
+                          [160.0, 128.0, 32.0, 16.0], [0.0, 0.0, 6400.0, 4800.0], [-300.0, 100.0, 500.0, 130.0],
+                          [1100.0, 500.0, 1500.0, 900.0], [5.0, 5.0, 5.0, 5.0], [1199.0, 0.0, 1200.0, 600.0]])
+    boxes = torch.cat((boxes, extra))
+    rois = torch.cat((torch.randint(0, 2, (boxes.shape[0], 1), generator=g).float(), boxes), dim=1)
+    go = torch.randn(rois.shape[0], c, pooled, pooled, generator=g)
+    xr = x.clone().requires_grad_(True)
+    torchvision.ops.roi_align(xr, rois, (pooled, pooled), 1.0 / 16, sr, aligned).backward(go)
+    xx = x.to(dev).requires_grad_(True)
+    coin_b200.ROIAlign(pooled, 1.0 / 16, sr, aligned)(xx, rois.to(dev)).backward(go.to(dev))
+    close(xx.grad, xr.grad, scale=float(xr.grad.abs().max()))
+
+
 def test_roi_align_edge_cases(dev):
     x = torch.arange(2 * 3 * 6 * 9, dtype=torch.float32).reshape(2, 3, 6, 9)
     layer = coin_b200.ROIAlign(7, 0.5, 0, True)
