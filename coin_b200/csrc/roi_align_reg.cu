@@ -222,10 +222,39 @@ __device__ __forceinline__ void fwd_xphase(float2 (&acc)[2][(PW + 1) / 2], const
 }
 
 // One pass over the RoI's feature columns for one unit and NJ consecutive feature rows starting at p0 (row stride rs).
-template <int PW, int CS, int NJ, typename TB>
+template <int PW, int CS, int NJ, bool PIPE, typename TB>
 __device__ __forceinline__ void fwd_columns(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const float2 (&yw)[4],
                                             const float* __restrict__ p0, const int rs, const int ncols, const int C) {
     const int cstride = CS ? CS : C;
+    if (PIPE) {   // the loads of step s + 1 are issued before the arithmetic of step s
+        float v[2][NJ];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) v[q][j] = __ldg(p0 + j * rs + q * cstride);
+#pragma unroll 1
+        for (int ci = 0; ci < ncols; ci += 2) {
+            p0 += 2 * cstride;
+            float vn[2][NJ];
+            const bool more = ci + 2 < ncols;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) vn[q][j] = more ? __ldg(p0 + j * rs + q * cstride) : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float2 t2 = make_float2(yw[0].x * v[q][0], yw[0].y * v[q][0]);
+#pragma unroll
+                for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j], t2);
+                fwd_xphase<PW>(acc, tb, ci + q, t2);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) v[q][j] = vn[q][j];
+        }
+        return;
+    }
 #pragma unroll 1
     for (int ci = 0; ci < ncols; ci += 2) {   // two columns per step: 2 * NJ independent 128-byte loads in flight
         float v[2][NJ];
@@ -244,18 +273,18 @@ __device__ __forceinline__ void fwd_columns(float2 (&acc)[2][(PW + 1) / 2], cons
     }
 }
 
-template <int PW, int CS, typename TB>
+template <int PW, int CS, bool PIPE, typename TB>
 __device__ __forceinline__ void fwd_chunk(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const int nj, const float2 (&yw)[4],
                                           const float* __restrict__ p0, const int rs, const int ncols, const int C) {
     switch (nj) {   // warp-uniform
-        case 1: fwd_columns<PW, CS, 1>(acc, tb, yw, p0, rs, ncols, C); break;
-        case 2: fwd_columns<PW, CS, 2>(acc, tb, yw, p0, rs, ncols, C); break;
-        case 3: fwd_columns<PW, CS, 3>(acc, tb, yw, p0, rs, ncols, C); break;
-        default: fwd_columns<PW, CS, 4>(acc, tb, yw, p0, rs, ncols, C); break;
+        case 1: fwd_columns<PW, CS, 1, PIPE>(acc, tb, yw, p0, rs, ncols, C); break;
+        case 2: fwd_columns<PW, CS, 2, PIPE>(acc, tb, yw, p0, rs, ncols, C); break;
+        case 3: fwd_columns<PW, CS, 3, PIPE>(acc, tb, yw, p0, rs, ncols, C); break;
+        default: fwd_columns<PW, CS, 4, PIPE>(acc, tb, yw, p0, rs, ncols, C); break;
     }
 }
 
-template <int PH, int PW, int CS, int OCC>
+template <int PH, int PW, int CS, int OCC, bool PIPE>
 __global__ void __launch_bounds__(32 * ((PH + 1) / 2), OCC)
 roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int cgroups, const int slabs) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW, NT = 32 * NU, NP = (PW + 1) / 2;
@@ -328,12 +357,12 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
 #pragma unroll
             for (int i = 0; i < NP; ++i) acc[r][i] = make_float2(0.0f, 0.0f);
         if (ne > 0) {
-            fwd_chunk<PW, CS>(acc, tb, min(ne, 4), yw0, fcol, rs, ncols, C);
+            fwd_chunk<PW, CS, PIPE>(acc, tb, min(ne, 4), yw0, fcol, rs, ncols, C);
             for (int e0 = 4; e0 < ne; e0 += 4) {   // tall RoIs: further chunks of <= 4 feature rows
                 float2 yw[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) yw[j] = e0 + j < ne ? tb.yw[u][e0 + j] : make_float2(0.0f, 0.0f);
-                fwd_chunk<PW, CS>(acc, tb, min(ne - e0, 4), yw, fcol + (size_t)e0 * rs, rs, ncols, C);
+                fwd_chunk<PW, CS, PIPE>(acc, tb, min(ne - e0, 4), yw, fcol + (size_t)e0 * rs, rs, ncols, C);
             }
         }
         // the previous slab's bulk store must have read the tile before it is overwritten
@@ -361,10 +390,10 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
     if (threadIdx.x == 0) reg_bulk_wait_read();
 }
 
-template <int PH, int PW, int CS, int OCC>
+template <int PH, int PW, int CS, int OCC, bool PIPE = false>
 static int launch_fwd_reg(const RoiParams& p, float* out, int slabs, cudaStream_t s) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW;
-    auto kern = roi_align_fwd_reg_kernel<PH, PW, CS, OCC>;
+    auto kern = roi_align_fwd_reg_kernel<PH, PW, CS, OCC, PIPE>;
     const size_t smem = (size_t)32 * NB * sizeof(float);
     const int cgroups = (int)ceil_div(p.C, 32 * slabs);
     kern<<<(unsigned)(p.K * cgroups), 32 * NU, smem, s>>>(p, out, cgroups, slabs);
@@ -383,36 +412,66 @@ __device__ __forceinline__ void reg_bulk_load(void* sdst, const void* gsrc, uint
         : "memory");
 }
 
-// One pass over the RoI's feature columns for one unit: u_r = sum_pw Wx[col][pw] * g[r][pw], then one fp32 RED per
-// merged feature row. The first NJ (<= 4) rows' weights are in registers; taller units read the rest from the table.
-template <int PW, int CS, int NJ, typename TB>
+// x phase of the backward for one feature column: u_r = sum_pw Wx[col][pw] * g[r][pw]
+template <int PW, typename TB>
+__device__ __forceinline__ void bwd_xphase(const float2 (&gr)[2][(PW + 1) / 2], const TB& tb, const int ci, float& u0, float& u1) {
+    constexpr int NP = (PW + 1) / 2;
+    const float4* wrow = reinterpret_cast<const float4*>(tb.wxd[ci]);
+    float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < (NP + 1) / 2; ++i) {
+        const float4 x = wrow[i];
+        s0 = ffma2v(gr[0][2 * i], make_float2(x.x, x.y), s0);
+        s1 = ffma2v(gr[1][2 * i], make_float2(x.x, x.y), s1);
+        if (2 * i + 1 < NP) {
+            s0 = ffma2v(gr[0][2 * i + 1], make_float2(x.z, x.w), s0);
+            s1 = ffma2v(gr[1][2 * i + 1], make_float2(x.z, x.w), s1);
+        }
+    }
+    u0 = s0.x + s0.y;
+    u1 = s1.x + s1.y;
+}
+
+// One pass over the RoI's feature columns [c0, c1) for one unit: per column the x phase, then one fp32 RED per merged
+// feature row. The first NJ (<= 4) rows' weights are in registers; TALL units read the rest from the table. Two
+// columns per iteration share the RED address arithmetic (the second column is an immediate offset).
+template <int PW, int CS, int NJ, bool TALL, typename TB>
 __device__ __forceinline__ void bwd_columns(const float2 (&gr)[2][(PW + 1) / 2], const TB& tb, const int u, const int ne,
                                             const float2 (&yw)[4], float* __restrict__ p0, const int rs, const int c0,
                                             const int c1, const int C) {
-    constexpr int NP = (PW + 1) / 2;
     const int cstride = CS ? CS : C;
     p0 += (size_t)c0 * cstride;
-    for (int ci = c0; ci < c1; ++ci) {
-        const float4* wrow = reinterpret_cast<const float4*>(tb.wxd[ci]);
-        float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
+    int ci = c0;
+#pragma unroll 1
+    for (; ci + 2 <= c1; ci += 2) {
+        float a0, a1, b0, b1;
+        bwd_xphase<PW>(gr, tb, ci, a0, a1);
+        bwd_xphase<PW>(gr, tb, ci + 1, b0, b1);
 #pragma unroll
-        for (int i = 0; i < (NP + 1) / 2; ++i) {
-            const float4 x = wrow[i];
-            s0 = ffma2v(gr[0][2 * i], make_float2(x.x, x.y), s0);
-            s1 = ffma2v(gr[1][2 * i], make_float2(x.x, x.y), s1);
-            if (2 * i + 1 < NP) {
-                s0 = ffma2v(gr[0][2 * i + 1], make_float2(x.z, x.w), s0);
-                s1 = ffma2v(gr[1][2 * i + 1], make_float2(x.z, x.w), s1);
+        for (int j = 0; j < NJ; ++j) {
+            float* q = p0 + j * rs;
+            atomicAdd(q, __fmaf_rn(yw[j].y, a1, yw[j].x * a0));
+            atomicAdd(q + cstride, __fmaf_rn(yw[j].y, b1, yw[j].x * b0));
+        }
+        if (TALL)
+            for (int j = 4; j < ne; ++j) {   // warp-uniform, rare
+                const float2 w = tb.yw[u][j];
+                float* q = p0 + (size_t)j * rs;
+                atomicAdd(q, __fmaf_rn(w.y, a1, w.x * a0));
+                atomicAdd(q + cstride, __fmaf_rn(w.y, b1, w.x * b0));
             }
-        }
-        const float u0 = s0.x + s0.y, u1 = s1.x + s1.y;
+        p0 += 2 * cstride;
+    }
+    if (ci < c1) {
+        float a0, a1;
+        bwd_xphase<PW>(gr, tb, ci, a0, a1);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) atomicAdd(p0 + j * rs, __fmaf_rn(yw[j].y, u1, yw[j].x * u0));
-        for (int j = 4; j < ne; ++j) {   // tall RoIs (warp-uniform, rare)
-            const float2 w = tb.yw[u][j];
-            atomicAdd(p0 + (size_t)j * rs, __fmaf_rn(w.y, u1, w.x * u0));
-        }
-        p0 += cstride;
+        for (int j = 0; j < NJ; ++j) atomicAdd(p0 + j * rs, __fmaf_rn(yw[j].y, a1, yw[j].x * a0));
+        if (TALL)
+            for (int j = 4; j < ne; ++j) {
+                const float2 w = tb.yw[u][j];
+                atomicAdd(p0 + (size_t)j * rs, __fmaf_rn(w.y, a1, w.x * a0));
+            }
     }
 }
 
@@ -516,11 +575,12 @@ roi_align_bwd_reg_kernel(const RoiParams p, const float* __restrict__ go, const 
             reg_bulk_load(tile, groi + (size_t)(sl + 1) * 32 * NB, kTileBytes, &bar_full, pol);
         if (ne > 0) {
             float* __restrict__ gcol = gunit + sl * 32;
-            switch (min(ne, 4)) {   // warp-uniform
-                case 1: bwd_columns<PW, CS, 1>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
-                case 2: bwd_columns<PW, CS, 2>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
-                case 3: bwd_columns<PW, CS, 3>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
-                default: bwd_columns<PW, CS, 4>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
+            switch (min(ne, 5)) {   // warp-uniform
+                case 1: bwd_columns<PW, CS, 1, false>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
+                case 2: bwd_columns<PW, CS, 2, false>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
+                case 3: bwd_columns<PW, CS, 3, false>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
+                case 4: bwd_columns<PW, CS, 4, false>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
+                default: bwd_columns<PW, CS, 4, true>(gr, tb, u, ne, yw0, gcol, rs, creal0, creal1, C); break;
             }
         }
     }
@@ -571,7 +631,10 @@ int launch_roi_align_fwd_reg(const RoiParams& p, void* out, cudaStream_t s) {
     slabs = std::max(1, std::min(slabs, nsl));
     if (p.PH == 14) {
         if (p.C == 1024) {
-            if (reg_env("COIN_ROI_REG_OCC", 4) == 3) return launch_fwd_reg<14, 14, 1024, 3>(p, o, slabs, s);
+            const int occ = reg_env("COIN_ROI_REG_OCC", 4), pipe = reg_env("COIN_ROI_REG_PIPE", 0);
+            if (occ == 3 && pipe) return launch_fwd_reg<14, 14, 1024, 3, true>(p, o, slabs, s);
+            if (occ == 3) return launch_fwd_reg<14, 14, 1024, 3>(p, o, slabs, s);
+            if (pipe) return launch_fwd_reg<14, 14, 1024, 4, true>(p, o, slabs, s);
             return launch_fwd_reg<14, 14, 1024, 4>(p, o, slabs, s);
         }
         return launch_fwd_reg<14, 14, 0, 4>(p, o, slabs, s);
