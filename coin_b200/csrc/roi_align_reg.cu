@@ -113,7 +113,7 @@ struct RegTables {
 template <int PH, int PW, int NT>
 __device__ __forceinline__ void reg_build_tables(RegTables<(PH + 1) / 2>& tb, void* scratch, const RoiGeom& g,
                                                  const int H, const int W, int& cmin, int& ncols, int& creal0,
-                                                 int& creal1) {
+                                                 int& creal1, int (&grp0)[2], int (&grpn)[2]) {
     constexpr int NU = (PH + 1) / 2;
     RXTap* xs = reinterpret_cast<RXTap*>(scratch);
     RXTap* ys = xs + kRegTap;
@@ -123,6 +123,7 @@ __device__ __forceinline__ void reg_build_tables(RegTables<(PH + 1) / 2>& tb, vo
     const bool tables = !empty && (long long)PW * gw <= kRegTap && (long long)PH * gh <= kRegTap;
     const float rcount = 1.0f / g.count;
     cmin = 0; ncols = 0; creal0 = 0; creal1 = 0;
+    grp0[0] = grp0[1] = grpn[0] = grpn[1] = 0;
     if (tid == 0) tb.mode = empty ? 2 : (tables ? 0 : 1);
     if (tables) {
         const int nx = PW * gw, ny = PH * gh;
@@ -174,6 +175,19 @@ __device__ __forceinline__ void reg_build_tables(RegTables<(PH + 1) / 2>& tb, vo
     lo = __reduce_min_sync(0xffffffffu, lo);
     hi = __reduce_max_sync(0xffffffffu, hi);
     const int rlo = lo, rhi = hi;                     // the columns that carry weight
+    // the same for the two bin groups the forward walks separately (bins [0, kSplit) and [kSplit, PW))
+    constexpr int kSplit = 2 * ((((PW + 1) / 2) + 1) / 2);
+    int glo[2] = {INT_MAX, INT_MAX}, ghi[2] = {-1, -1};
+    for (int s = lane; s < PW * gw; s += 32) {
+        const RXTap X = xs[s];
+        const int gi = s >= kSplit * gw;
+        if (X.lo >= 0) { glo[gi] = min(glo[gi], X.lo); ghi[gi] = max(ghi[gi], X.hi); }
+    }
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+        glo[gi] = __reduce_min_sync(0xffffffffu, glo[gi]);
+        ghi[gi] = __reduce_max_sync(0xffffffffu, ghi[gi]);
+    }
     if (hi >= 0 && ((hi - lo + 1) & 1)) {             // even column count: the forward walks two columns per step
         if (hi + 1 < W) ++hi; else if (lo > 0) --lo;  // (the added column has zero weights; W == 1: mode 1)
     }
@@ -184,6 +198,13 @@ __device__ __forceinline__ void reg_build_tables(RegTables<(PH + 1) / 2>& tb, vo
     } else {
         cmin = lo; ncols = hi - lo + 1;
         creal0 = rlo - lo; creal1 = rhi - lo + 1;
+#pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+            if (ghi[gi] < 0) continue;                // no valid sample in this group of bins
+            int a = glo[gi] - lo, b = ghi[gi] - lo;   // inclusive, relative to cmin; made even inside [0, ncols)
+            if ((b - a + 1) & 1) { if (b + 1 < ncols) ++b; else --a; }
+            grp0[gi] = a; grpn[gi] = b - a + 1;
+        }
         for (int idx = tid; idx < ncols * 16; idx += NT) {   // dense x weights
             const int ci = idx >> 4, pw = idx & 15, col = cmin + ci;
             float w = 0.0f;
@@ -203,28 +224,32 @@ __device__ __forceinline__ void reg_build_tables(RegTables<(PH + 1) / 2>& tb, vo
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-// x phase of one feature column: acc[r][pw] += Wx[col][pw] * t[r] over all PW bins (the weight row is mostly zeros
-// for wide RoIs, but a branch-free body with statically indexed accumulators beats a warp-uniform window switch)
-template <int PW, typename TB>
-__device__ __forceinline__ void fwd_xphase(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const int ci, const float2 t2) {
-    constexpr int NP = (PW + 1) / 2;
-    const float4* wrow = reinterpret_cast<const float4*>(tb.wxd[ci]);
+// x phase of one feature column for the NPG bin pairs starting at pair P0: acc[r][i] += Wx[col][2*(P0+i)..] * t[r]
+template <int P0, int NPG, typename TB>
+__device__ __forceinline__ void fwd_xphase(float2 (&acc)[2][NPG], const TB& tb, const int ci, const float2 t2) {
+    const float* wrow = tb.wxd[ci] + 2 * P0;
 #pragma unroll
-    for (int i = 0; i < (NP + 1) / 2; ++i) {
-        const float4 x = wrow[i];
-        acc[0][2 * i] = ffma2(make_float2(x.x, x.y), t2.x, acc[0][2 * i]);
-        acc[1][2 * i] = ffma2(make_float2(x.x, x.y), t2.y, acc[1][2 * i]);
-        if (2 * i + 1 < NP) {
-            acc[0][2 * i + 1] = ffma2(make_float2(x.z, x.w), t2.x, acc[0][2 * i + 1]);
-            acc[1][2 * i + 1] = ffma2(make_float2(x.z, x.w), t2.y, acc[1][2 * i + 1]);
+    for (int i = 0; i < NPG; i += 2) {
+        if (i + 1 < NPG) {
+            const float4 x = *reinterpret_cast<const float4*>(wrow + 2 * i);
+            acc[0][i] = ffma2(make_float2(x.x, x.y), t2.x, acc[0][i]);
+            acc[1][i] = ffma2(make_float2(x.x, x.y), t2.y, acc[1][i]);
+            acc[0][i + 1] = ffma2(make_float2(x.z, x.w), t2.x, acc[0][i + 1]);
+            acc[1][i + 1] = ffma2(make_float2(x.z, x.w), t2.y, acc[1][i + 1]);
+        } else {
+            const float2 x = *reinterpret_cast<const float2*>(wrow + 2 * i);
+            acc[0][i] = ffma2(x, t2.x, acc[0][i]);
+            acc[1][i] = ffma2(x, t2.y, acc[1][i]);
         }
     }
 }
 
-// One pass over the RoI's feature columns for one unit and NJ consecutive feature rows starting at p0 (row stride rs).
-template <int PW, int CS, int NJ, bool PIPE, typename TB>
-__device__ __forceinline__ void fwd_columns(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const float2 (&yw)[4],
-                                            const float* __restrict__ p0, const int rs, const int ncols, const int C) {
+// One pass over the feature columns [0, ncols) (ncols even) at p0 for one unit, one group of bins and NJ consecutive
+// feature rows (row stride rs): two columns per step, 2 * NJ independent 128-byte loads in flight.
+template <int CS, int NJ, int P0, int NPG, bool PIPE, typename TB>
+__device__ __forceinline__ void fwd_columns(float2 (&acc)[2][NPG], const TB& tb, const float2 (&yw)[4],
+                                            const float* __restrict__ p0, const int rs, const int c0, const int ncols,
+                                            const int C) {
     const int cstride = CS ? CS : C;
     if (PIPE) {   // the loads of step s + 1 are issued before the arithmetic of step s
         float v[2][NJ];
@@ -233,10 +258,10 @@ __device__ __forceinline__ void fwd_columns(float2 (&acc)[2][(PW + 1) / 2], cons
 #pragma unroll
             for (int j = 0; j < NJ; ++j) v[q][j] = __ldg(p0 + j * rs + q * cstride);
 #pragma unroll 1
-        for (int ci = 0; ci < ncols; ci += 2) {
+        for (int ci = c0; ci < c0 + ncols; ci += 2) {
             p0 += 2 * cstride;
             float vn[2][NJ];
-            const bool more = ci + 2 < ncols;
+            const bool more = ci + 2 < c0 + ncols;
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -246,7 +271,7 @@ __device__ __forceinline__ void fwd_columns(float2 (&acc)[2][(PW + 1) / 2], cons
                 float2 t2 = make_float2(yw[0].x * v[q][0], yw[0].y * v[q][0]);
 #pragma unroll
                 for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j], t2);
-                fwd_xphase<PW>(acc, tb, ci + q, t2);
+                fwd_xphase<P0, NPG>(acc, tb, ci + q, t2);
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q)
@@ -256,7 +281,7 @@ __device__ __forceinline__ void fwd_columns(float2 (&acc)[2][(PW + 1) / 2], cons
         return;
     }
 #pragma unroll 1
-    for (int ci = 0; ci < ncols; ci += 2) {   // two columns per step: 2 * NJ independent 128-byte loads in flight
+    for (int ci = c0; ci < c0 + ncols; ci += 2) {
         float v[2][NJ];
 #pragma unroll
         for (int q = 0; q < 2; ++q)
@@ -268,19 +293,66 @@ __device__ __forceinline__ void fwd_columns(float2 (&acc)[2][(PW + 1) / 2], cons
             float2 t2 = make_float2(yw[0].x * v[q][0], yw[0].y * v[q][0]);
 #pragma unroll
             for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j], t2);
-            fwd_xphase<PW>(acc, tb, ci + q, t2);
+            fwd_xphase<P0, NPG>(acc, tb, ci + q, t2);
         }
     }
 }
 
-template <int PW, int CS, bool PIPE, typename TB>
-__device__ __forceinline__ void fwd_chunk(float2 (&acc)[2][(PW + 1) / 2], const TB& tb, const int nj, const float2 (&yw)[4],
-                                          const float* __restrict__ p0, const int rs, const int ncols, const int C) {
-    switch (nj) {   // warp-uniform
-        case 1: fwd_columns<PW, CS, 1, PIPE>(acc, tb, yw, p0, rs, ncols, C); break;
-        case 2: fwd_columns<PW, CS, 2, PIPE>(acc, tb, yw, p0, rs, ncols, C); break;
-        case 3: fwd_columns<PW, CS, 3, PIPE>(acc, tb, yw, p0, rs, ncols, C); break;
-        default: fwd_columns<PW, CS, 4, PIPE>(acc, tb, yw, p0, rs, ncols, C); break;
+// all merged feature rows of the unit for one group of bins (chunks of <= 4 rows; the first chunk's weights are in registers)
+template <int CS, int P0, int NPG, bool PIPE, typename TB>
+__device__ __forceinline__ void fwd_group(float2 (&acc)[2][NPG], const TB& tb, const int u, const int ne, const float2 (&yw0)[4],
+                                          const float* __restrict__ fcol, const int rs, const int c0, const int ncols,
+                                          const int C) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < NPG; ++i) acc[r][i] = make_float2(0.0f, 0.0f);
+    if (ne <= 0 || ncols <= 0) return;
+    const int cstride = CS ? CS : C;
+    const float* __restrict__ p0 = fcol + (size_t)c0 * cstride;
+    switch (min(ne, 4)) {   // warp-uniform
+        case 1: fwd_columns<CS, 1, P0, NPG, PIPE>(acc, tb, yw0, p0, rs, c0, ncols, C); break;
+        case 2: fwd_columns<CS, 2, P0, NPG, PIPE>(acc, tb, yw0, p0, rs, c0, ncols, C); break;
+        case 3: fwd_columns<CS, 3, P0, NPG, PIPE>(acc, tb, yw0, p0, rs, c0, ncols, C); break;
+        default: fwd_columns<CS, 4, P0, NPG, PIPE>(acc, tb, yw0, p0, rs, c0, ncols, C); break;
+    }
+    for (int e0 = 4; e0 < ne; e0 += 4) {   // tall RoIs: further chunks of <= 4 feature rows
+        float2 yw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yw[j] = e0 + j < ne ? tb.yw[u][e0 + j] : make_float2(0.0f, 0.0f);
+        const float* __restrict__ pe = p0 + (size_t)e0 * rs;
+        switch (min(ne - e0, 4)) {
+            case 1: fwd_columns<CS, 1, P0, NPG, PIPE>(acc, tb, yw, pe, rs, c0, ncols, C); break;
+            case 2: fwd_columns<CS, 2, P0, NPG, PIPE>(acc, tb, yw, pe, rs, c0, ncols, C); break;
+            case 3: fwd_columns<CS, 3, P0, NPG, PIPE>(acc, tb, yw, pe, rs, c0, ncols, C); break;
+            default: fwd_columns<CS, 4, P0, NPG, PIPE>(acc, tb, yw, pe, rs, c0, ncols, C); break;
+        }
+    }
+}
+
+// the group's accumulators -> the unit's rows of the [32][PH*PW] tile (tp points at row 2u, bin 0 of this lane's channel)
+template <int PW, int P0, int NPG>
+__device__ __forceinline__ void fwd_store_group(float* __restrict__ tp, const float2 (&acc)[2][NPG], const int nr) {
+    if constexpr (PW % 2 == 0 && (2 * PW) % 4 == 0 && P0 % 2 == 0) {
+        // row 2u starts 16-byte aligned, row 2u+1 (PW floats later, PW = 2 mod 4) 8-byte aligned
+#pragma unroll
+        for (int i = 0; i < NPG; i += 2) {
+            if (i + 1 < NPG)
+                *reinterpret_cast<float4*>(tp + 2 * (P0 + i)) = make_float4(acc[0][i].x, acc[0][i].y, acc[0][i + 1].x, acc[0][i + 1].y);
+            else
+                *reinterpret_cast<float2*>(tp + 2 * (P0 + i)) = acc[0][i];
+        }
+#pragma unroll
+        for (int i = 0; i < NPG; ++i) *reinterpret_cast<float2*>(tp + PW + 2 * (P0 + i)) = acc[1][i];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < NPG; ++i) {
+                const int b = 2 * (P0 + i);
+                if (r < nr && b < PW) tp[r * PW + b] = acc[r][i].x;
+                if (r < nr && b + 1 < PW) tp[r * PW + b + 1] = acc[r][i].y;
+            }
     }
 }
 
@@ -288,7 +360,7 @@ template <int PH, int PW, int CS, int OCC, bool PIPE>
 __global__ void __launch_bounds__(32 * ((PH + 1) / 2), OCC)
 roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int cgroups, const int slabs) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW, NT = 32 * NU, NP = (PW + 1) / 2;
-    constexpr bool VEC = PW % 2 == 0 && (2 * PW) % 4 == 0 && NB % 4 == 0;
+    constexpr int NPA = PW >= 12 ? (NP + 1) / 2 : NP, NPB = NP - NPA;   // bin pairs of the two groups (one for 7x7)
     extern __shared__ __align__(128) float tile[];   // [32 channels][NB]: the CTA's contiguous output region
     __shared__ RegTables<NU> tb;
     static_assert(32 * NB * sizeof(float) >= 2 * kRegTap * 16, "the tile doubles as tap-table scratch");
@@ -306,8 +378,8 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
     const int nslab = min(slabs, (C - cg0) / 32);
     float* __restrict__ oroi = out + (size_t)k * C * NB;
 
-    int cmin, ncols, creal0, creal1;
-    reg_build_tables<PH, PW, NT>(tb, tile, g, H, W, cmin, ncols, creal0, creal1);
+    int cmin, ncols, creal0, creal1, grp0[2], grpn[2];
+    reg_build_tables<PH, PW, NT>(tb, tile, g, H, W, cmin, ncols, creal0, creal1, grp0, grpn);
     const int mode = tb.mode;
 
     if (mode == 2) {   // no sample inside the map: the RoI pools to zeros
@@ -339,9 +411,11 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
         return;
     }
 
-    // the unit's merged y table stays in registers across the CTA's channel slabs (first <= 4 feature rows)
+    // The unit's bins are walked in two groups (left and right half of the output row): a column of a wide RoI
+    // carries weight on a few adjacent bins only, so each group needs its own, nearly disjoint, column range and
+    // half the x-phase arithmetic and accumulator registers of a pass over all bins; narrow RoIs have few columns.
     const int ne = tb.ycnt[u], rs = W * C;
-    float2 yw0[4];
+    float2 yw0[4];   // the unit's merged y table stays in registers across the CTA's channel slabs (first <= 4 rows)
 #pragma unroll
     for (int j = 0; j < 4; ++j) yw0[j] = j < ne ? tb.yw[u][j] : make_float2(0.0f, 0.0f);
     const float* __restrict__ funit = fimg + (size_t)tb.ymin[u] * rs + (size_t)cmin * C + cg0 + lane;
@@ -351,37 +425,18 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
 
     for (int sl = 0; sl < nslab; ++sl) {
         const float* __restrict__ fcol = funit + sl * 32;
-        float2 acc[2][NP];
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < NP; ++i) acc[r][i] = make_float2(0.0f, 0.0f);
-        if (ne > 0) {
-            fwd_chunk<PW, CS, PIPE>(acc, tb, min(ne, 4), yw0, fcol, rs, ncols, C);
-            for (int e0 = 4; e0 < ne; e0 += 4) {   // tall RoIs: further chunks of <= 4 feature rows
-                float2 yw[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) yw[j] = e0 + j < ne ? tb.yw[u][e0 + j] : make_float2(0.0f, 0.0f);
-                fwd_chunk<PW, CS, PIPE>(acc, tb, min(ne - e0, 4), yw, fcol + (size_t)e0 * rs, rs, ncols, C);
-            }
+        {
+            float2 acc[2][NPA];
+            fwd_group<CS, 0, NPA, PIPE>(acc, tb, u, ne, yw0, fcol, rs, NPB > 0 ? grp0[0] : 0, NPB > 0 ? grpn[0] : ncols, C);
+            // the previous slab's bulk store must have read the tile before it is overwritten
+            if (sl > 0 && threadIdx.x == 0) reg_bulk_wait_read();
+            __syncthreads();
+            fwd_store_group<PW, 0, NPA>(tp, acc, nr);
         }
-        // the previous slab's bulk store must have read the tile before it is overwritten
-        if (sl > 0 && threadIdx.x == 0) reg_bulk_wait_read();
-        __syncthreads();
-        if (VEC) {   // rows 2u, 2u+1 are 2*PW consecutive floats of the channel's plane
-            float4* tp4 = reinterpret_cast<float4*>(tp);
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const int r = (2 * i) / NP, a = 2 * i - r * NP;           // pair index 2i, 2i+1 of the 2*NP pairs
-                const int r2 = (2 * i + 1) / NP, b = 2 * i + 1 - r2 * NP;
-                tp4[i] = make_float4(acc[r][a].x, acc[r][a].y, acc[r2][b].x, acc[r2][b].y);
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int b = 0; b < PW; ++b)
-                    if (r < nr) tp[r * PW + b] = (b & 1) ? acc[r][b >> 1].y : acc[r][b >> 1].x;
+        if constexpr (NPB > 0) {
+            float2 acc[2][NPB > 0 ? NPB : 1];
+            fwd_group<CS, NPA, (NPB > 0 ? NPB : 1), PIPE>(acc, tb, u, ne, yw0, fcol, rs, grp0[1], grpn[1], C);
+            fwd_store_group<PW, NPA, (NPB > 0 ? NPB : 1)>(tp, acc, nr);
         }
         reg_fence_async();
         __syncthreads();
@@ -505,8 +560,8 @@ roi_align_bwd_reg_kernel(const RoiParams p, const float* __restrict__ go, const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         reg_bulk_load(tile, groi, kTileBytes, &bar_full, pol);
     }
-    int cmin, ncols, creal0, creal1;
-    reg_build_tables<PH, PW, NT>(tb, tile + 32 * NB, g, H, W, cmin, ncols, creal0, creal1);
+    int cmin, ncols, creal0, creal1, grp0[2], grpn[2];
+    reg_build_tables<PH, PW, NT>(tb, tile + 32 * NB, g, H, W, cmin, ncols, creal0, creal1, grp0, grpn);
     const int mode = tb.mode;
 
     if (mode == 2) {   // no sample inside the map: no gradient (the tile in flight must land before the CTA may exit)
@@ -631,10 +686,7 @@ int launch_roi_align_fwd_reg(const RoiParams& p, void* out, cudaStream_t s) {
     slabs = std::max(1, std::min(slabs, nsl));
     if (p.PH == 14) {
         if (p.C == 1024) {
-            const int occ = reg_env("COIN_ROI_REG_OCC", 4), pipe = reg_env("COIN_ROI_REG_PIPE", 0);
-            if (occ == 3 && pipe) return launch_fwd_reg<14, 14, 1024, 3, true>(p, o, slabs, s);
-            if (occ == 3) return launch_fwd_reg<14, 14, 1024, 3>(p, o, slabs, s);
-            if (pipe) return launch_fwd_reg<14, 14, 1024, 4, true>(p, o, slabs, s);
+            if (reg_env("COIN_ROI_REG_PIPE", 0)) return launch_fwd_reg<14, 14, 1024, 4, true>(p, o, slabs, s);
             return launch_fwd_reg<14, 14, 1024, 4>(p, o, slabs, s);
         }
         return launch_fwd_reg<14, 14, 0, 4>(p, o, slabs, s);
