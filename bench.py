@@ -273,8 +273,8 @@ def main():
                     "frac": nbytes / ms_alone / 1e6 / peak, "ms_in_step": ms_in_step,
                     "achieved_gbs_in_step": nbytes / ms_in_step / 1e6, "frac_in_step": nbytes / ms_in_step / 1e6 / peak}
 
-        kernels = {"roi_align_fwd_sep_kernel": kern(k_fwd, k_fwd_step, fwd_bytes),
-                   "roi_align_bwd_sep_kernel": kern(k_bwd, k_bwd_step, bwd_bytes)}
+        kernels = {"roi_align_fwd_reg_kernel": kern(k_fwd, k_fwd_step, fwd_bytes),
+                   "roi_align_bwd_reg_kernel": kern(k_bwd, k_bwd_step, bwd_bytes)}
         dom = max(kernels, key=lambda name: kernels[name]["ms"])
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                     "peak_source": peak_src, "unit": "GB/s", "frac": kernels[dom]["frac"],
