@@ -244,77 +244,64 @@ __device__ __forceinline__ void fwd_xphase(float2 (&acc)[2][NPG], const TB& tb, 
     }
 }
 
-// One pass over the feature columns [0, ncols) (ncols even) at p0 for one unit, one group of bins and NJ consecutive
-// feature rows (row stride rs): two columns per step, 2 * NJ independent 128-byte loads in flight.
-template <int CS, int NJ, int P0, int NPG, bool PIPE, typename TB>
-__device__ __forceinline__ void fwd_columns(float2 (&acc)[2][NPG], const TB& tb, const float2 (&yw)[4],
-                                            const float* __restrict__ p0, const int rs, const int c0, const int ncols,
-                                            const int C) {
+// One pass over the feature columns [c0, c0 + ncols) (ncols even) at p0 for one unit, one group of bins and NJ
+// consecutive feature rows (row stride rs): two columns per step, 2 * NJ independent loads in flight. CPL: channels per
+// lane - with 2 a lane owns the adjacent channels 2*lane, 2*lane+1 of a 64-channel slab (64-bit loads) and everything
+// that is not an FMA (loads, weight LDS, addresses, loop, per-slab setup) is shared by the two.
+template <int CS, int NJ, int P0, int NPG, int CPL, bool HOIST, typename TB>
+__device__ __forceinline__ void fwd_columns(float2 (&acc)[CPL][2][NPG], const TB& tb, const float2 (&yw_r)[4],
+                                            const float2* __restrict__ yw_s, const float* __restrict__ p0, const int rs,
+                                            const int c0, const int ncols, const int C) {
     const int cstride = CS ? CS : C;
-    if (PIPE) {   // the loads of step s + 1 are issued before the arithmetic of step s
-        float v[2][NJ];
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) v[q][j] = __ldg(p0 + j * rs + q * cstride);
-#pragma unroll 1
-        for (int ci = c0; ci < c0 + ncols; ci += 2) {
-            p0 += 2 * cstride;
-            float vn[2][NJ];
-            const bool more = ci + 2 < c0 + ncols;
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) vn[q][j] = more ? __ldg(p0 + j * rs + q * cstride) : 0.0f;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                float2 t2 = make_float2(yw[0].x * v[q][0], yw[0].y * v[q][0]);
-#pragma unroll
-                for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j], t2);
-                fwd_xphase<P0, NPG>(acc, tb, ci + q, t2);
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) v[q][j] = vn[q][j];
-        }
-        return;
-    }
 #pragma unroll 1
     for (int ci = c0; ci < c0 + ncols; ci += 2) {
-        float v[2][NJ];
+        float v[2][NJ][CPL];
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) v[q][j] = __ldg(p0 + j * rs + q * cstride);
+            for (int j = 0; j < NJ; ++j) {
+                if (CPL == 2) {
+                    const float2 x = __ldg(reinterpret_cast<const float2*>(p0 + j * rs + q * cstride));
+                    v[q][j][0] = x.x; v[q][j][CPL - 1] = x.y;
+                } else {
+                    v[q][j][0] = __ldg(p0 + j * rs + q * cstride);
+                }
+            }
         p0 += 2 * cstride;
+        float2 yw[NJ];   // HOIST: registers held across the slab loop; else re-read from the table every step
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float2 t2 = make_float2(yw[0].x * v[q][0], yw[0].y * v[q][0]);
+        for (int j = 0; j < NJ; ++j) yw[j] = HOIST ? yw_r[j] : yw_s[j];
 #pragma unroll
-            for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j], t2);
-            fwd_xphase<P0, NPG>(acc, tb, ci + q, t2);
-        }
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int ch = 0; ch < CPL; ++ch) {
+                float2 t2 = make_float2(yw[0].x * v[q][0][ch], yw[0].y * v[q][0][ch]);
+#pragma unroll
+                for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j][ch], t2);
+                fwd_xphase<P0, NPG>(acc[ch], tb, ci + q, t2);
+            }
     }
 }
 
 // all merged feature rows of the unit for one group of bins (chunks of <= 4 rows; the first chunk's weights are in registers)
-template <int CS, int P0, int NPG, bool PIPE, typename TB>
-__device__ __forceinline__ void fwd_group(float2 (&acc)[2][NPG], const TB& tb, const int u, const int ne, const float2 (&yw0)[4],
-                                          const float* __restrict__ fcol, const int rs, const int c0, const int ncols,
-                                          const int C) {
+template <int CS, int P0, int NPG, int CPL, bool HOIST, typename TB>
+__device__ __forceinline__ void fwd_group(float2 (&acc)[CPL][2][NPG], const TB& tb, const int u, const int ne,
+                                          const float2 (&yw0)[4], const float* __restrict__ fcol, const int rs, const int c0,
+                                          const int ncols, const int C) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int ch = 0; ch < CPL; ++ch)
 #pragma unroll
-        for (int i = 0; i < NPG; ++i) acc[r][i] = make_float2(0.0f, 0.0f);
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < NPG; ++i) acc[ch][r][i] = make_float2(0.0f, 0.0f);
     if (ne <= 0 || ncols <= 0) return;
     const int cstride = CS ? CS : C;
     const float* __restrict__ p0 = fcol + (size_t)c0 * cstride;
     switch (min(ne, 4)) {   // warp-uniform
-        case 1: fwd_columns<CS, 1, P0, NPG, PIPE>(acc, tb, yw0, p0, rs, c0, ncols, C); break;
-        case 2: fwd_columns<CS, 2, P0, NPG, PIPE>(acc, tb, yw0, p0, rs, c0, ncols, C); break;
-        case 3: fwd_columns<CS, 3, P0, NPG, PIPE>(acc, tb, yw0, p0, rs, c0, ncols, C); break;
-        default: fwd_columns<CS, 4, P0, NPG, PIPE>(acc, tb, yw0, p0, rs, c0, ncols, C); break;
+        case 1: fwd_columns<CS, 1, P0, NPG, CPL, HOIST>(acc, tb, yw0, tb.yw[u], p0, rs, c0, ncols, C); break;
+        case 2: fwd_columns<CS, 2, P0, NPG, CPL, HOIST>(acc, tb, yw0, tb.yw[u], p0, rs, c0, ncols, C); break;
+        case 3: fwd_columns<CS, 3, P0, NPG, CPL, HOIST>(acc, tb, yw0, tb.yw[u], p0, rs, c0, ncols, C); break;
+        default: fwd_columns<CS, 4, P0, NPG, CPL, HOIST>(acc, tb, yw0, tb.yw[u], p0, rs, c0, ncols, C); break;
     }
     for (int e0 = 4; e0 < ne; e0 += 4) {   // tall RoIs: further chunks of <= 4 feature rows
         float2 yw[4];
@@ -322,15 +309,15 @@ __device__ __forceinline__ void fwd_group(float2 (&acc)[2][NPG], const TB& tb, c
         for (int j = 0; j < 4; ++j) yw[j] = e0 + j < ne ? tb.yw[u][e0 + j] : make_float2(0.0f, 0.0f);
         const float* __restrict__ pe = p0 + (size_t)e0 * rs;
         switch (min(ne - e0, 4)) {
-            case 1: fwd_columns<CS, 1, P0, NPG, PIPE>(acc, tb, yw, pe, rs, c0, ncols, C); break;
-            case 2: fwd_columns<CS, 2, P0, NPG, PIPE>(acc, tb, yw, pe, rs, c0, ncols, C); break;
-            case 3: fwd_columns<CS, 3, P0, NPG, PIPE>(acc, tb, yw, pe, rs, c0, ncols, C); break;
-            default: fwd_columns<CS, 4, P0, NPG, PIPE>(acc, tb, yw, pe, rs, c0, ncols, C); break;
+            case 1: fwd_columns<CS, 1, P0, NPG, CPL, true>(acc, tb, yw, tb.yw[u], pe, rs, c0, ncols, C); break;
+            case 2: fwd_columns<CS, 2, P0, NPG, CPL, true>(acc, tb, yw, tb.yw[u], pe, rs, c0, ncols, C); break;
+            case 3: fwd_columns<CS, 3, P0, NPG, CPL, true>(acc, tb, yw, tb.yw[u], pe, rs, c0, ncols, C); break;
+            default: fwd_columns<CS, 4, P0, NPG, CPL, true>(acc, tb, yw, tb.yw[u], pe, rs, c0, ncols, C); break;
         }
     }
 }
 
-// the group's accumulators -> the unit's rows of the [32][PH*PW] tile (tp points at row 2u, bin 0 of this lane's channel)
+// the group's accumulators -> the unit's rows of the [channels][PH*PW] tile (tp points at row 2u, bin 0 of the channel)
 template <int PW, int P0, int NPG>
 __device__ __forceinline__ void fwd_store_group(float* __restrict__ tp, const float2 (&acc)[2][NPG], const int nr) {
     if constexpr (PW % 2 == 0 && (2 * PW) % 4 == 0 && P0 % 2 == 0) {
@@ -356,18 +343,18 @@ __device__ __forceinline__ void fwd_store_group(float* __restrict__ tp, const fl
     }
 }
 
-template <int PH, int PW, int CS, int OCC, bool PIPE>
+template <int PH, int PW, int CS, int OCC, int CPL, bool HOIST>
 __global__ void __launch_bounds__(32 * ((PH + 1) / 2), OCC)
 roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int cgroups, const int slabs) {
-    constexpr int NU = (PH + 1) / 2, NB = PH * PW, NT = 32 * NU, NP = (PW + 1) / 2;
+    constexpr int NU = (PH + 1) / 2, NB = PH * PW, NT = 32 * NU, NP = (PW + 1) / 2, CC = 32 * CPL;
     constexpr int NPA = PW >= 12 ? (NP + 1) / 2 : NP, NPB = NP - NPA;   // bin pairs of the two groups (one for 7x7)
-    extern __shared__ __align__(128) float tile[];   // [32 channels][NB]: the CTA's contiguous output region
+    extern __shared__ __align__(128) float tile[];   // [CC channels][NB]: the CTA's contiguous output region
     __shared__ RegTables<NU> tb;
-    static_assert(32 * NB * sizeof(float) >= 2 * kRegTap * 16, "the tile doubles as tap-table scratch");
+    static_assert(CC * NB * sizeof(float) >= 2 * kRegTap * 16, "the tile doubles as tap-table scratch");
 
     const int k = blockIdx.x / cgroups;
     if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
-    const int cg0 = (blockIdx.x - k * cgroups) * (32 * slabs);
+    const int cg0 = (blockIdx.x - k * cgroups) * (CC * slabs);
     const int lane = threadIdx.x & 31, u = threadIdx.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
     const coin_level_t L = p.lv[lvl];
@@ -375,7 +362,7 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
     const int C = CS ? CS : p.C;
     const RoiGeom g = roi_geometry(p.rois + 5 * (size_t)k, L.spatial_scale, PH, PW, p.sampling_ratio, p.aligned);
     const float* __restrict__ fimg = L.feat_nhwc + (size_t)g.batch * H * W * C;
-    const int nslab = min(slabs, (C - cg0) / 32);
+    const int nslab = min(slabs, (C - cg0) / CC);
     float* __restrict__ oroi = out + (size_t)k * C * NB;
 
     int cmin, ncols, creal0, creal1, grp0[2], grpn[2];
@@ -384,12 +371,12 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
 
     if (mode == 2) {   // no sample inside the map: the RoI pools to zeros
         float* o = oroi + (size_t)cg0 * NB;
-        for (int e = threadIdx.x; e < nslab * 32 * NB; e += NT) o[e] = 0.0f;
+        for (int e = threadIdx.x; e < nslab * CC * NB; e += NT) o[e] = 0.0f;
         return;
     }
     if (mode == 1) {   // exotic geometry (sampling grids beyond the tables): direct 4-tap evaluation
         const float rcount = 1.0f / g.count;
-        for (int sl = 0; sl < nslab; ++sl) {
+        for (int sl = 0; sl < nslab * CPL; ++sl) {
             const int c = cg0 + sl * 32 + lane;
             for (int b = u; b < NB; b += NU) {
                 const int ph = b / PW, pw = b - ph * PW;
@@ -418,39 +405,43 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
     float2 yw0[4];   // the unit's merged y table stays in registers across the CTA's channel slabs (first <= 4 rows)
 #pragma unroll
     for (int j = 0; j < 4; ++j) yw0[j] = j < ne ? tb.yw[u][j] : make_float2(0.0f, 0.0f);
-    const float* __restrict__ funit = fimg + (size_t)tb.ymin[u] * rs + (size_t)cmin * C + cg0 + lane;
+    const float* __restrict__ funit = fimg + (size_t)tb.ymin[u] * rs + (size_t)cmin * C + cg0 + CPL * lane;
     const int nr = min(2, PH - u * 2);
     const uint64_t pol = l2_evict_first_policy();
-    float* __restrict__ tp = tile + lane * NB + u * (2 * PW);
+    float* __restrict__ tp = tile + CPL * lane * NB + u * (2 * PW);
 
     for (int sl = 0; sl < nslab; ++sl) {
-        const float* __restrict__ fcol = funit + sl * 32;
+        const float* __restrict__ fcol = funit + sl * CC;
         {
-            float2 acc[2][NPA];
-            fwd_group<CS, 0, NPA, PIPE>(acc, tb, u, ne, yw0, fcol, rs, NPB > 0 ? grp0[0] : 0, NPB > 0 ? grpn[0] : ncols, C);
+            float2 acc[CPL][2][NPA];
+            fwd_group<CS, 0, NPA, CPL, HOIST>(acc, tb, u, ne, yw0, fcol, rs, NPB > 0 ? grp0[0] : 0, NPB > 0 ? grpn[0] : ncols, C);
             // the previous slab's bulk store must have read the tile before it is overwritten
             if (sl > 0 && threadIdx.x == 0) reg_bulk_wait_read();
             __syncthreads();
-            fwd_store_group<PW, 0, NPA>(tp, acc, nr);
+#pragma unroll
+            for (int ch = 0; ch < CPL; ++ch) fwd_store_group<PW, 0, NPA>(tp + ch * NB, acc[ch], nr);
         }
         if constexpr (NPB > 0) {
-            float2 acc[2][NPB > 0 ? NPB : 1];
-            fwd_group<CS, NPA, (NPB > 0 ? NPB : 1), PIPE>(acc, tb, u, ne, yw0, fcol, rs, grp0[1], grpn[1], C);
-            fwd_store_group<PW, NPA, (NPB > 0 ? NPB : 1)>(tp, acc, nr);
+            float2 acc[CPL][2][NPB > 0 ? NPB : 1];
+            fwd_group<CS, NPA, (NPB > 0 ? NPB : 1), CPL, HOIST>(acc, tb, u, ne, yw0, fcol, rs, grp0[1], grpn[1], C);
+#pragma unroll
+            for (int ch = 0; ch < CPL; ++ch) fwd_store_group<PW, NPA, (NPB > 0 ? NPB : 1)>(tp + ch * NB, acc[ch], nr);
         }
         reg_fence_async();
         __syncthreads();
-        if (threadIdx.x == 0) reg_bulk_store(oroi + (size_t)(cg0 + sl * 32) * NB, tile, 32 * NB * sizeof(float), pol);
+        if (threadIdx.x == 0) reg_bulk_store(oroi + (size_t)(cg0 + sl * CC) * NB, tile, CC * NB * sizeof(float), pol);
     }
     if (threadIdx.x == 0) reg_bulk_wait_read();
 }
 
-template <int PH, int PW, int CS, int OCC, bool PIPE = false>
+template <int PH, int PW, int CS, int OCC, int CPL, bool HOIST = true>
 static int launch_fwd_reg(const RoiParams& p, float* out, int slabs, cudaStream_t s) {
-    constexpr int NU = (PH + 1) / 2, NB = PH * PW;
-    auto kern = roi_align_fwd_reg_kernel<PH, PW, CS, OCC, PIPE>;
-    const size_t smem = (size_t)32 * NB * sizeof(float);
-    const int cgroups = (int)ceil_div(p.C, 32 * slabs);
+    constexpr int NU = (PH + 1) / 2, NB = PH * PW, CC = 32 * CPL;
+    auto kern = roi_align_fwd_reg_kernel<PH, PW, CS, OCC, CPL, HOIST>;
+    const size_t smem = (size_t)CC * NB * sizeof(float);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    slabs = std::max(1, std::min(slabs, p.C / CC));
+    const int cgroups = (int)ceil_div(p.C, CC * slabs);
     kern<<<(unsigned)(p.K * cgroups), 32 * NU, smem, s>>>(p, out, cgroups, slabs);
     return check_launch("roi_align_fwd_reg_kernel");
 }
@@ -661,7 +652,7 @@ int launch_roi_align_bwd_reg(const RoiParams& p, const void* grad_out, cudaStrea
     if (reinterpret_cast<uintptr_t>(grad_out) & 15) return fail(COIN_ERR_INVALID, "roi_align_bwd: grad_out must be 16-byte aligned");
     const float* g = static_cast<const float*>(grad_out);
     const int nsl = (int)(p.C / 32);
-    int slabs = reg_env("COIN_ROI_BWD_REG_SLABS", p.K < 1024 ? 2 : 8);
+    int slabs = reg_env("COIN_ROI_BWD_REG_SLABS", p.K < 1024 ? 2 : (p.PH == 7 ? 4 : 8));
     slabs = std::max(1, std::min(slabs, nsl));
     if (p.PH == 14) {
         if (p.C == 1024) return launch_bwd_reg<14, 14, 1024, 4>(p, g, slabs, s);
@@ -680,19 +671,25 @@ bool roi_align_fwd_reg_supported(const RoiParams& p, int out_dtype) {
 int launch_roi_align_fwd_reg(const RoiParams& p, void* out, cudaStream_t s) {
     if (reinterpret_cast<uintptr_t>(out) & 15) return fail(COIN_ERR_INVALID, "roi_align_fwd: out must be 16-byte aligned");
     float* o = static_cast<float*>(out);
-    const int nsl = (int)(p.C / 32);
-    // few RoIs: fewer channel slabs per CTA so that one very large RoI cannot leave a long tail
-    int slabs = reg_env("COIN_ROI_REG_SLABS", p.K < 1024 ? 2 : 8);
-    slabs = std::max(1, std::min(slabs, nsl));
+    // two channels per lane (64-channel slabs, 64-bit loads) when the channel count allows it
+    const int cpl = (p.C % 64 == 0 && (reinterpret_cast<uintptr_t>(p.lv[0].feat_nhwc) & 7) == 0) ? reg_env("COIN_ROI_REG_CPL", 1) : 1;
+    // channels per CTA: 256 (the tables are built once per CTA; 128 for the cheaper 7x7 units); few RoIs: fewer, so
+    // that one very large RoI cannot leave a long tail (measured: foggy 14x14 256 -> 372 us, 128 -> 380, 512 -> 399)
+    const int chans = reg_env("COIN_ROI_REG_CHANS", p.K < 1024 ? 64 : (p.PH == 7 ? 128 : 256));
     if (p.PH == 14) {
         if (p.C == 1024) {
-            if (reg_env("COIN_ROI_REG_PIPE", 0)) return launch_fwd_reg<14, 14, 1024, 4, true>(p, o, slabs, s);
-            return launch_fwd_reg<14, 14, 1024, 4>(p, o, slabs, s);
+            if (cpl == 2) return launch_fwd_reg<14, 14, 1024, 3, 2>(p, o, chans / 64, s);
+            return launch_fwd_reg<14, 14, 1024, 4, 1>(p, o, chans / 32, s);
         }
-        return launch_fwd_reg<14, 14, 0, 4>(p, o, slabs, s);
+        if (cpl == 2) return launch_fwd_reg<14, 14, 0, 3, 2>(p, o, chans / 64, s);
+        return launch_fwd_reg<14, 14, 0, 4, 1>(p, o, chans / 32, s);
     }
-    if (p.C == 1024) return launch_fwd_reg<7, 7, 1024, 8>(p, o, slabs, s);
-    return launch_fwd_reg<7, 7, 0, 8>(p, o, slabs, s);
+    if (p.C == 1024) {
+        if (cpl == 2) return launch_fwd_reg<7, 7, 1024, 6, 2>(p, o, chans / 64, s);
+        return launch_fwd_reg<7, 7, 1024, 8, 1>(p, o, chans / 32, s);
+    }
+    if (cpl == 2) return launch_fwd_reg<7, 7, 0, 6, 2>(p, o, chans / 64, s);
+    return launch_fwd_reg<7, 7, 0, 8, 1>(p, o, chans / 32, s);
 }
 
 }  // namespace coin
