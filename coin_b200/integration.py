@@ -134,3 +134,22 @@ def label_anchors(matcher: Matcher, a_boxes: Boxes, c_boxes: Boxes, anchors: Box
     gt = Boxes.cat([a_boxes, c_boxes])
     idx, lab = matcher.match_boxes(gt, anchors)
     return ops.relabel_rpn_(idx, lab, len(a_boxes), len(c_boxes))
+
+
+def rpn_predict_proposals(anchors: Boxes, pred_objectness_logits: torch.Tensor, pred_anchor_deltas: torch.Tensor,
+                          image_size: Tuple[int, int], nms_thresh: float, pre_nms_topk: int, post_nms_topk: int,
+                          min_box_size: float = 0.0, training: bool = False,
+                          weights=(1.0, 1.0, 1.0, 1.0)) -> Instances:
+    """detectron2 0.5 ``RPN.predict_proposals`` for one image and one feature level, as reached from
+    coin/modeling/proposal_generator/rpn.py:64,113: ``_decode_proposals`` + ``find_top_rpn_proposals``. Returns
+    ``Instances(image_size)`` with ``proposal_boxes`` and ``objectness_logits`` like the reference. One launch chain on
+    the device (coin_rpn_proposals) and a single 8-byte read-back of (count, status)."""
+    boxes, logits, status = ops.rpn_proposals(anchors.tensor if isinstance(anchors, Boxes) else anchors, pred_anchor_deltas,
+                                              pred_objectness_logits, image_size, pre_nms_topk, post_nms_topk, nms_thresh,
+                                              min_box_size, weights)
+    if status & 1 and training:
+        raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+    res = Instances(image_size)
+    res.proposal_boxes = Boxes(boxes)
+    res.objectness_logits = logits
+    return res

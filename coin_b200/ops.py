@@ -322,6 +322,35 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: Optional[torch.
     return keep[: int(nkeep.item())]
 
 
+def rpn_proposals(anchors: torch.Tensor, deltas: torch.Tensor, logits: torch.Tensor, image_size: Tuple[float, float],
+                  pre_nms_topk: int, post_nms_topk: int, nms_thresh: float, min_box_size: float = 0.0,
+                  weights=(1.0, 1.0, 1.0, 1.0), scale_clamp: float = _SCALE_CLAMP, sync: bool = True):
+    """One image, one level of d2 RPN.predict_proposals (decode + find_top_rpn_proposals) in one launch chain.
+    Returns (boxes[n,4], logits[n], status) - or, with sync=False, the capacity buffers, the device count and the
+    device status word (bit 0: a selected row was non-finite)."""
+    anchors = _boxes(anchors, "anchors")
+    deltas = _boxes(deltas, "deltas")
+    logits = _f32c(logits, "logits").reshape(-1)
+    a = anchors.shape[0]
+    if deltas.shape[0] != a or logits.numel() != a:
+        raise ValueError("coin_b200: anchors, deltas and logits disagree in length")
+    cap = max(min(a, int(pre_nms_topk), int(post_nms_topk)), 1)
+    out_boxes = torch.empty((cap, 4), dtype=torch.float32, device=anchors.device)
+    out_logits = torch.empty((cap,), dtype=torch.float32, device=anchors.device)
+    count = torch.zeros((2,), dtype=torch.int32, device=anchors.device)   # [live rows, status]
+    ws = _workspace(lib.coin_rpn_proposals_workspace_bytes(a, int(pre_nms_topk)), anchors.device)
+    h, w = image_size
+    check(lib.coin_rpn_proposals(_ptr(anchors), _ptr(deltas), _ptr(logits), a, int(pre_nms_topk), int(post_nms_topk),
+                                 float(nms_thresh), float(min_box_size), float(h), float(w), float(weights[0]),
+                                 float(weights[1]), float(weights[2]), float(weights[3]), float(scale_clamp),
+                                 _ptr(out_boxes), _ptr(out_logits), _ptr(count), ctypes.c_void_p(count.data_ptr() + 4),
+                                 _ptr(ws), ws.numel(), _stream()))
+    if not sync:
+        return out_boxes, out_logits, count
+    n, status = count.tolist()
+    return out_boxes[:n], out_logits[:n], status
+
+
 def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float, max_keep: int = -1) -> torch.Tensor:
     return batched_nms(boxes, scores, None, iou_threshold, "plain", max_keep)
 

@@ -343,6 +343,25 @@ int coin_abc_pack(const coin_dets_t* online_host, int64_t nc, const coin_dets_t*
                   const coin_pseudo_t* b_out_host, const coin_pseudo_t* c_out_host, int64_t cap_pairs,
                   coin_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * RPN proposal selection for one image and one feature level.
+ *   replaces: detectron2 0.5 RPN.predict_proposals = _decode_proposals (Box2BoxTransform.apply_deltas on ALL
+ *   anchors) + find_top_rpn_proposals (sort the objectness logits, keep pre_nms_topk, drop non-finite rows,
+ *   Boxes.clip, Boxes.nonempty(min_box_size), batched_nms, keep[:post_nms_topk]) as reached from
+ *   coin/modeling/proposal_generator/rpn.py:64,113 (DualTeacherRPN.forward).
+ * Only the selected anchors are decoded; no host round trip (the reference syncs in nonempty() and nms()).
+ *   anchors, deltas: float32 [A,4] (16-byte aligned); logits: float32 [A]; weights wx..wh = (1,1,1,1) for the RPN.
+ *   out_boxes: float32 [min(A, pre, post), 4]; out_logits: float32 [same]; out_count: device int32 (live rows);
+ *   status: device int32, bit 0 set when a selected row was non-finite (detectron2 raises FloatingPointError in
+ *   training; the Python mirror does the same). Ties of equal logits: lower anchor index first.
+ * ---------------------------------------------------------------------------------------------- */
+size_t coin_rpn_proposals_workspace_bytes(int64_t A, int64_t pre_nms_topk);
+int coin_rpn_proposals(const float* anchors, const float* deltas, const float* logits, int64_t A,
+                       int64_t pre_nms_topk, int64_t post_nms_topk, double nms_thresh, float min_box_size,
+                       float img_h, float img_w, float wx, float wy, float ww, float wh, float scale_clamp,
+                       float* out_boxes, float* out_logits, int32_t* out_count, int32_t* status, void* ws,
+                       size_t ws_bytes, coin_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -231,3 +231,33 @@ def grid_anchors(hf: int, wf: int, stride: int, base: torch.Tensor, offset: floa
     yy, xx = torch.meshgrid(sy, sx, indexing="ij")
     shifts = torch.stack((xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)), dim=1)
     return (shifts.view(-1, 1, 4) + base.view(1, -1, 4)).reshape(-1, 4)
+
+
+def predict_proposals_single(anchors, pred_anchor_deltas, pred_objectness_logits, image_size, nms_thresh: float,
+                             pre_nms_topk: int, post_nms_topk: int, min_box_size: float = 0.0, training: bool = False,
+                             weights=(1.0, 1.0, 1.0, 1.0)):
+    """[d2 0.5] RPN.predict_proposals for ONE image and ONE feature level (<- rpn.py:64,113):
+    proposal_generator/rpn.py::_decode_proposals (Box2BoxTransform.apply_deltas on every anchor) followed by
+    proposal_utils.py::find_top_rpn_proposals: sort the logits (descending), keep pre_nms_topk, drop non-finite rows
+    (FloatingPointError when training), Boxes.clip, Boxes.nonempty(threshold=min_box_size), batched_nms over the
+    level ids (one level: plain nms), keep[:post_nms_topk]. Ties of equal logits keep the lower anchor index
+    (stable sort; torch's default sort leaves the order of ties unspecified) - the determinism policy of DESIGN.md.
+    Returns (proposal_boxes [n,4], objectness_logits [n])."""
+    proposals = Box2BoxTransform(weights).apply_deltas(pred_anchor_deltas.float(), anchors.float())
+    logits = pred_objectness_logits.reshape(-1).float()
+    num = min(logits.numel(), pre_nms_topk)
+    sorted_logits, idx = torch.sort(logits, descending=True, stable=True)
+    scores, idx = sorted_logits[:num], idx[:num]
+    boxes = proposals[idx]
+    valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores)
+    if not valid.all():
+        if training:
+            raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+        boxes, scores = boxes[valid], scores[valid]
+    boxes = box_clip(boxes, image_size)
+    keep = box_nonempty(boxes, threshold=min_box_size)
+    if keep.sum().item() != len(boxes):
+        boxes, scores = boxes[keep], scores[keep]
+    keep = batched_nms(boxes, scores, torch.zeros(len(boxes), dtype=torch.int64), nms_thresh)
+    keep = keep[:post_nms_topk]
+    return boxes[keep], scores[keep]

@@ -144,6 +144,36 @@ def test_roi_align_backward_register_tile_cases(dev, c, pooled, sr, aligned):
     close(xx.grad, xr.grad, scale=float(xr.grad.abs().max()))
 
 
+def test_roi_align_register_tile_full_size(dev, monkeypatch):
+    """BASELINE configs[1] size (3 x 512 RoIs, C = 1024, 14x14, map [3,1024,37,75]): the register-tile forward against
+    the bit-exact parity kernel (itself pinned to torchvision CPU), the register-tile backward against the separable
+    kernel, and the adjoint identity <pool(x), G> = <x, pool^T(G)> that ties the two together."""
+    shape = synth.SHAPES["foggy_roi_head"]
+    g = synth.gen(77)
+    x = synth.features(g, shape).to(dev)
+    n = x.shape[0]
+    boxes = [synth.random_boxes(g, shape.rois, shape.height, shape.width) for _ in range(n)]
+    rois = torch.cat([torch.cat((torch.full((len(b), 1), float(i)), b), 1) for i, b in enumerate(boxes)]).to(dev)
+    layer = coin_b200.ROIAlign(shape.pooled, 1.0 / 16, 0, True)
+    monkeypatch.setenv("COIN_ROI_EXACT", "1")
+    ref = layer(x, rois)
+    monkeypatch.setenv("COIN_ROI_EXACT", "0")
+    xx = x.clone().requires_grad_(True)
+    out = layer(xx, rois)
+    scale = float(x.abs().max())
+    assert float((out - ref).abs().max()) <= 1e-5 * scale
+    go = torch.randn(out.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    out.backward(go)
+    monkeypatch.setenv("COIN_ROI_REG", "0")
+    xs = x.clone().requires_grad_(True)
+    layer(xs, rois).backward(go)
+    gscale = float(xs.grad.abs().max())
+    assert float((xx.grad - xs.grad).abs().max()) <= 1e-5 * gscale
+    lhs = float((out.detach().double() * go.double()).sum())
+    rhs = float((x.double() * xx.grad.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
+
+
 def test_roi_align_edge_cases(dev):
     x = torch.arange(2 * 3 * 6 * 9, dtype=torch.float32).reshape(2, 3, 6, 9)
     layer = coin_b200.ROIAlign(7, 0.5, 0, True)
@@ -441,6 +471,41 @@ def test_match_dual_teacher_empty_sides(dev):
             got = integration.match_dual_teacher(_inst(on, dev), _inst(off, dev), tag)
             for g_, w_ in zip(got, want):
                 _cmp_sets(g_, w_)
+
+
+@pytest.mark.parametrize("hw,pre,post,min_size,seed", [((37, 75), 12000, 2000, 0.0, 1), ((37, 75), 6000, 1000, 0.0, 2),
+                                                      ((10, 12), 300, 50, 4.0, 3), ((37, 66), 12000, 2000, 0.0, 4)])
+def test_rpn_predict_proposals_vs_oracle(dev, hw, pre, post, min_size, seed):
+    """d2 RPN.predict_proposals (decode + find_top_rpn_proposals, <- rpn.py:64,113) for one image
+    and one level, 41 625 anchors at the Foggy shape: the kept logits (copies: bit-exact, descending, ties by anchor
+    index) and the decoded, clipped boxes (1e-5 relative: expf) against the restated detectron2 0.5 code."""
+    g = synth.gen(500 + seed)
+    hf, wf = hw
+    anchors = d2_ref.grid_anchors(hf, wf, 16, d2_ref.cell_anchors())
+    a = anchors.shape[0]
+    deltas = 0.2 * torch.randn(a, 4, generator=g)
+    deltas[torch.randint(0, a, (8,), generator=g), 2] = 9.0           # hits scale_clamp
+    logits = torch.randn(a, generator=g)
+    logits[torch.randint(0, a, (40,), generator=g)] = 1.25            # exact ties
+    if seed == 3:
+        logits[7] = float("nan")
+        deltas[11, 0] = float("inf")
+    size = (hf * 16, wf * 16)
+    want_b, want_s = d2_ref.predict_proposals_single(anchors, deltas, logits, size, 0.7, pre, post, min_size)
+    res = integration.rpn_predict_proposals(coin_b200.Boxes(anchors.to(dev)), logits.to(dev), deltas.to(dev), size, 0.7,
+                                            pre, post, min_size)
+    got_b, got_s = res.proposal_boxes.tensor.cpu(), res.objectness_logits.cpu()
+    assert got_s.shape == want_s.shape
+    assert torch.equal(got_s, want_s)
+    close(got_b, want_b, scale=float(max(size)))
+    if seed == 3:
+        with pytest.raises(FloatingPointError):
+            integration.rpn_predict_proposals(anchors.to(dev), logits.to(dev), deltas.to(dev), size, 0.7, pre, post,
+                                              min_size, training=True)
+    # empty input
+    e = integration.rpn_predict_proposals(torch.zeros(0, 4, device=dev), torch.zeros(0, device=dev),
+                                          torch.zeros(0, 4, device=dev), size, 0.7, pre, post)
+    assert len(e.proposal_boxes) == 0 and e.objectness_logits.numel() == 0
 
 
 def test_errors(dev):

@@ -238,6 +238,35 @@ def test_process_boxes_scale_flip():
 
 
 # ---------------------------------------------------------------------------------------------
+def test_predict_proposals_single_properties():
+    """d2 RPN.predict_proposals restatement (one image, one level): a hand case, and on random input the invariants
+    of find_top_rpn_proposals - descending logits, boxes inside the image and larger than min_box_size, pairwise
+    IoU <= nms_thresh, at most post_nms_topk rows, non-finite rows dropped (FloatingPointError when training)."""
+    anchors = torch.tensor([[0.0, 0.0, 10.0, 10.0], [0.0, 0.0, 10.0, 10.0], [20.0, 20.0, 40.0, 40.0], [100.0, 100.0, 130.0, 130.0]])
+    deltas = torch.zeros(4, 4)
+    deltas[1, 0] = 0.05                      # shifted by half a pixel: IoU with box 0 > 0.7 -> suppressed
+    logits = torch.tensor([2.0, 1.0, 3.0, 0.5])
+    boxes, sc = d2_ref.predict_proposals_single(anchors, deltas, logits, (50, 50), 0.7, 4, 10)
+    assert sc.tolist() == [3.0, 2.0]         # box 3 lies outside the 50x50 image: clipped to empty
+    assert torch.equal(boxes, torch.tensor([[20.0, 20.0, 40.0, 40.0], [0.0, 0.0, 10.0, 10.0]]))
+    g = torch.Generator().manual_seed(11)
+    base = d2_ref.grid_anchors(10, 12, 16, d2_ref.cell_anchors((32, 64), (0.5, 1.0, 2.0)))
+    d = 0.3 * torch.randn(base.shape[0], 4, generator=g)
+    lg = torch.randn(base.shape[0], generator=g)
+    lg[5] = float("nan")
+    d[9, 2] = float("inf")
+    boxes, sc = d2_ref.predict_proposals_single(base, d, lg, (160, 192), 0.7, 300, 50, min_box_size=2.0)
+    assert len(boxes) <= 50 and torch.isfinite(boxes).all() and torch.isfinite(sc).all()
+    assert (sc[:-1] >= sc[1:]).all()
+    assert (boxes[:, 0] >= 0).all() and (boxes[:, 2] <= 192).all() and (boxes[:, 3] <= 160).all()
+    assert ((boxes[:, 2] - boxes[:, 0]) > 2.0).all() and ((boxes[:, 3] - boxes[:, 1]) > 2.0).all()
+    iou = torchvision.ops.box_iou(boxes, boxes)
+    iou.fill_diagonal_(0)
+    assert float(iou.max()) <= 0.7
+    with pytest.raises(FloatingPointError):
+        d2_ref.predict_proposals_single(base, d, lg, (160, 192), 0.7, 300, 50, training=True)
+
+
 # the C ABI: the library loads and exports every symbol include/coinops.h declares
 # ---------------------------------------------------------------------------------------------
 def test_abi_exports_match_header():
