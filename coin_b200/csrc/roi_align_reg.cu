@@ -665,6 +665,11 @@ int launch_roi_align_bwd_reg(const RoiParams& p, const void* grad_out, cudaStrea
 bool roi_align_fwd_reg_supported(const RoiParams& p, int out_dtype) {
     if (reg_env("COIN_ROI_REG", 1) == 0) return false;
     if (out_dtype != COIN_F32 || p.C % 32 != 0) return false;
+    // few RoIs (the step's private-box call, <= ~150 boxes that can each span the whole map): the grid cannot hide the
+    // load latency of this kernel's long per-warp column walks, and the call runs next to the backward, which owns the
+    // register file; the separable kernel (one 64-channel slab per CTA, 8 columns of loads in flight) finishes it in
+    // time (measured on the step's timeline: 1273 vs 1531 us for the heaviest seed). COIN_ROI_REG_MINK=0: always.
+    if (p.K < reg_env("COIN_ROI_REG_MINK", 1024) && p.k_dev) return false;
     return (p.PH == 14 && p.PW == 14) || (p.PH == 7 && p.PW == 7);
 }
 
@@ -675,7 +680,7 @@ int launch_roi_align_fwd_reg(const RoiParams& p, void* out, cudaStream_t s) {
     const int cpl = (p.C % 64 == 0 && (reinterpret_cast<uintptr_t>(p.lv[0].feat_nhwc) & 7) == 0) ? reg_env("COIN_ROI_REG_CPL", 1) : 1;
     // channels per CTA: 256 (the tables are built once per CTA; 128 for the cheaper 7x7 units); few RoIs: fewer, so
     // that one very large RoI cannot leave a long tail (measured: foggy 14x14 256 -> 372 us, 128 -> 380, 512 -> 399)
-    const int chans = reg_env("COIN_ROI_REG_CHANS", p.K < 1024 ? 64 : (p.PH == 7 ? 128 : 256));
+    const int chans = p.K < 1024 ? reg_env("COIN_ROI_REG_CHANS_SMALL", 64) : reg_env("COIN_ROI_REG_CHANS", p.PH == 7 ? 128 : 256);
     if (p.PH == 14) {
         if (p.C == 1024) {
             if (cpl == 2) return launch_fwd_reg<14, 14, 1024, 3, 2>(p, o, chans / 64, s);

@@ -347,6 +347,8 @@ class RoIPathStep:
                     per_tag[tag] = (a, bb, cc)
                     n_a, n_b, n_c = cnt[0:1], cnt[1:2], cnt[2:3]
                     if tag == "RCNN":
+                        # the private-box ROIAlign only needs the C set: it may start before the labelling below
+                        c_segs.append((cc["gt_boxes"], n_c, float(i), st.record_event()))
                         gt, n_gt = ops.concat_rows([(a["gt_boxes"], n_a, 0.0), (bb["gt_boxes"], n_b, 0.0),
                                                     (cc["gt_boxes"], n_c, 0.0)])
                         props, n_props = ops.concat_rows([(d[f"{i}.proposals"], None, 0.0), (a["gt_boxes"], n_a, 0.0),
@@ -356,7 +358,6 @@ class RoIPathStep:
                         out["roi_labels"].append((idx, lab))
                         slot(f"props{i}", n_props)
                         self._mark(f"img{i}.roi_labels_done")
-                        c_segs.append((cc["gt_boxes"], n_c, float(i), st.record_event()))
                     else:
                         gt2, n_gt2 = ops.concat_rows([(a["gt_boxes"], n_a, 0.0), (cc["gt_boxes"], n_c, 0.0)])
                         idx2, lab2 = ops.iou_match_dev(gt2, n_gt2, self.anchors, None, [0.3, 0.7], [0, -1, 1], True)  # S2
