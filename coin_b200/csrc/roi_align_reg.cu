@@ -283,7 +283,43 @@ __device__ __forceinline__ void fwd_columns(float2 (&acc)[CPL][2][NPG], const TB
     }
 }
 
-// all merged feature rows of the unit for one group of bins (chunks of <= 4 rows; the first chunk's weights are in registers)
+// The same for units that touch 5..8 feature rows (RoIs taller than ~14 cells: two or three samples per bin along y):
+// one column per step with all NJ rows' loads in flight, so the x phase - the bulk of the arithmetic - runs once per
+// column instead of once per chunk of 4 rows. Rows 0..3 take their weights from registers, the rest from the table.
+template <int CS, int NJ, int P0, int NPG, int CPL, typename TB>
+__device__ __forceinline__ void fwd_columns_tall(float2 (&acc)[CPL][2][NPG], const TB& tb, const float2 (&yw_r)[4],
+                                                 const float2* __restrict__ yw_s, const float* __restrict__ p0, const int rs,
+                                                 const int c0, const int ncols, const int C) {
+    static_assert(NJ > 4 && NJ <= 8, "5..8 merged rows");
+    const int cstride = CS ? CS : C;
+#pragma unroll 1
+    for (int ci = c0; ci < c0 + ncols; ++ci) {
+        float v[NJ][CPL];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if (CPL == 2) {
+                const float2 x = __ldg(reinterpret_cast<const float2*>(p0 + j * rs));
+                v[j][0] = x.x; v[j][CPL - 1] = x.y;
+            } else {
+                v[j][0] = __ldg(p0 + j * rs);
+            }
+        }
+        p0 += cstride;
+        float2 yw[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) yw[j] = j < 4 ? yw_r[j & 3] : yw_s[j];
+#pragma unroll
+        for (int ch = 0; ch < CPL; ++ch) {
+            float2 t2 = make_float2(yw[0].x * v[0][ch], yw[0].y * v[0][ch]);
+#pragma unroll
+            for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[j][ch], t2);
+            fwd_xphase<P0, NPG>(acc[ch], tb, ci, t2);
+        }
+    }
+}
+
+// all merged feature rows of the unit for one group of bins, <= 8 rows per pass over the columns (the first pass's
+// first four weights are in registers across the CTA's slabs)
 template <int CS, int P0, int NPG, int CPL, bool HOIST, typename TB>
 __device__ __forceinline__ void fwd_group(float2 (&acc)[CPL][2][NPG], const TB& tb, const int u, const int ne,
                                           const float2 (&yw0)[4], const float* __restrict__ fcol, const int rs, const int c0,
@@ -297,22 +333,22 @@ __device__ __forceinline__ void fwd_group(float2 (&acc)[CPL][2][NPG], const TB& 
     if (ne <= 0 || ncols <= 0) return;
     const int cstride = CS ? CS : C;
     const float* __restrict__ p0 = fcol + (size_t)c0 * cstride;
-    switch (min(ne, 4)) {   // warp-uniform
-        case 1: fwd_columns<CS, 1, P0, NPG, CPL, HOIST>(acc, tb, yw0, tb.yw[u], p0, rs, c0, ncols, C); break;
-        case 2: fwd_columns<CS, 2, P0, NPG, CPL, HOIST>(acc, tb, yw0, tb.yw[u], p0, rs, c0, ncols, C); break;
-        case 3: fwd_columns<CS, 3, P0, NPG, CPL, HOIST>(acc, tb, yw0, tb.yw[u], p0, rs, c0, ncols, C); break;
-        default: fwd_columns<CS, 4, P0, NPG, CPL, HOIST>(acc, tb, yw0, tb.yw[u], p0, rs, c0, ncols, C); break;
-    }
-    for (int e0 = 4; e0 < ne; e0 += 4) {   // tall RoIs: further chunks of <= 4 feature rows
+    for (int e0 = 0; e0 < ne; e0 += 8) {   // one pass for all but whole-map RoIs
+        const int n = min(ne - e0, 8);
         float2 yw[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) yw[j] = e0 + j < ne ? tb.yw[u][e0 + j] : make_float2(0.0f, 0.0f);
+        for (int j = 0; j < 4; ++j) yw[j] = e0 == 0 ? yw0[j] : (e0 + j < ne ? tb.yw[u][e0 + j] : make_float2(0.0f, 0.0f));
+        const float2* __restrict__ yws = tb.yw[u] + e0;
         const float* __restrict__ pe = p0 + (size_t)e0 * rs;
-        switch (min(ne - e0, 4)) {
-            case 1: fwd_columns<CS, 1, P0, NPG, CPL, true>(acc, tb, yw, tb.yw[u], pe, rs, c0, ncols, C); break;
-            case 2: fwd_columns<CS, 2, P0, NPG, CPL, true>(acc, tb, yw, tb.yw[u], pe, rs, c0, ncols, C); break;
-            case 3: fwd_columns<CS, 3, P0, NPG, CPL, true>(acc, tb, yw, tb.yw[u], pe, rs, c0, ncols, C); break;
-            default: fwd_columns<CS, 4, P0, NPG, CPL, true>(acc, tb, yw, tb.yw[u], pe, rs, c0, ncols, C); break;
+        switch (n) {   // warp-uniform
+            case 1: fwd_columns<CS, 1, P0, NPG, CPL, true>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 2: fwd_columns<CS, 2, P0, NPG, CPL, true>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 3: fwd_columns<CS, 3, P0, NPG, CPL, true>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 4: fwd_columns<CS, 4, P0, NPG, CPL, true>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 5: fwd_columns_tall<CS, 5, P0, NPG, CPL>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 6: fwd_columns_tall<CS, 6, P0, NPG, CPL>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 7: fwd_columns_tall<CS, 7, P0, NPG, CPL>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            default: fwd_columns_tall<CS, 8, P0, NPG, CPL>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
         }
     }
 }
