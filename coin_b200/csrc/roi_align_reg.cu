@@ -248,50 +248,87 @@ __device__ __forceinline__ void fwd_xphase(float2 (&acc)[2][NPG], const TB& tb, 
 // consecutive feature rows (row stride rs): two columns per step, 2 * NJ independent loads in flight. CPL: channels per
 // lane - with 2 a lane owns the adjacent channels 2*lane, 2*lane+1 of a 64-channel slab (64-bit loads) and everything
 // that is not an FMA (loads, weight LDS, addresses, loop, per-slab setup) is shared by the two.
-template <int CS, int NJ, int P0, int NPG, int CPL, bool HOIST, typename TB>
+// NQ columns at p0: all NJ * NQ loads first, then the y and x phases
+template <int CS, int NJ, int NQ, int P0, int NPG, int CPL, typename TB>
+__device__ __forceinline__ void fwd_step(float2 (&acc)[CPL][2][NPG], const TB& tb, const float2 (&yw)[4],
+                                         const float* __restrict__ p0, const int rs, const int ci, const int cstride) {
+    float v[NQ][NJ][CPL];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if (CPL == 2) {
+                const float2 x = __ldg(reinterpret_cast<const float2*>(p0 + j * rs + q * cstride));
+                v[q][j][0] = x.x; v[q][j][CPL - 1] = x.y;
+            } else {
+                v[q][j][0] = __ldg(p0 + j * rs + q * cstride);
+            }
+        }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int ch = 0; ch < CPL; ++ch) {
+            float2 t2 = make_float2(yw[0].x * v[q][0][ch], yw[0].y * v[q][0][ch]);
+#pragma unroll
+            for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j][ch], t2);
+            fwd_xphase<P0, NPG>(acc[ch], tb, ci + q, t2);
+        }
+}
+
+template <int CS, int NJ, int P0, int NPG, int CPL, int MLP, typename TB>
 __device__ __forceinline__ void fwd_columns(float2 (&acc)[CPL][2][NPG], const TB& tb, const float2 (&yw_r)[4],
                                             const float2* __restrict__ yw_s, const float* __restrict__ p0, const int rs,
                                             const int c0, const int ncols, const int C) {
     const int cstride = CS ? CS : C;
+    // columns per step = independent 128-byte loads in flight per warp: 8..12 is the measured optimum (more spills,
+    // less leaves the L2 latency exposed). MLP 0: NJ 1..3 -> 4 columns, NJ 4 -> 2; MLP 1: NJ 1 -> 8, NJ 2 -> 6.
+    constexpr int NQ = MLP == 1 ? (NJ == 1 ? 8 : NJ == 2 ? 6 : NJ == 3 ? 4 : 2) : (NJ <= 3 ? 4 : 2);
+    int ci = c0;
+    const int cend = c0 + ncols;
 #pragma unroll 1
-    for (int ci = c0; ci < c0 + ncols; ci += 2) {
-        float v[2][NJ][CPL];
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                if (CPL == 2) {
-                    const float2 x = __ldg(reinterpret_cast<const float2*>(p0 + j * rs + q * cstride));
-                    v[q][j][0] = x.x; v[q][j][CPL - 1] = x.y;
-                } else {
-                    v[q][j][0] = __ldg(p0 + j * rs + q * cstride);
-                }
-            }
-        p0 += 2 * cstride;
-        float2 yw[NJ];   // HOIST: registers held across the slab loop; else re-read from the table every step
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) yw[j] = HOIST ? yw_r[j] : yw_s[j];
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int ch = 0; ch < CPL; ++ch) {
-                float2 t2 = make_float2(yw[0].x * v[q][0][ch], yw[0].y * v[q][0][ch]);
-#pragma unroll
-                for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j][ch], t2);
-                fwd_xphase<P0, NPG>(acc[ch], tb, ci + q, t2);
-            }
+    for (; ci + NQ <= cend; ci += NQ) {
+        fwd_step<CS, NJ, NQ, P0, NPG, CPL>(acc, tb, yw_r, p0, rs, ci, cstride);
+        p0 += NQ * cstride;
     }
+    if (NQ > 4 && ci + 4 <= cend) {   // ncols is even: the rest is 0, 2, 4 (or 6 after an 8-step)
+        fwd_step<CS, NJ, 4, P0, NPG, CPL>(acc, tb, yw_r, p0, rs, ci, cstride);
+        p0 += 4 * cstride;
+        ci += 4;
+    }
+    if (NQ > 2 && ci < cend) fwd_step<CS, NJ, 2, P0, NPG, CPL>(acc, tb, yw_r, p0, rs, ci, cstride);
 }
 
 // The same for units that touch 5..8 feature rows (RoIs taller than ~14 cells: two or three samples per bin along y):
 // one column per step with all NJ rows' loads in flight, so the x phase - the bulk of the arithmetic - runs once per
 // column instead of once per chunk of 4 rows. Rows 0..3 take their weights from registers, the rest from the table.
-template <int CS, int NJ, int P0, int NPG, int CPL, typename TB>
+template <int CS, int NJ, int P0, int NPG, int CPL, int MLP, typename TB>
 __device__ __forceinline__ void fwd_columns_tall(float2 (&acc)[CPL][2][NPG], const TB& tb, const float2 (&yw_r)[4],
                                                  const float2* __restrict__ yw_s, const float* __restrict__ p0, const int rs,
                                                  const int c0, const int ncols, const int C) {
     static_assert(NJ > 4 && NJ <= 8, "5..8 merged rows");
     const int cstride = CS ? CS : C;
+    if (MLP == 1 && NJ <= 6) {   // two columns per step: 10..12 loads in flight
+#pragma unroll 1
+        for (int ci = c0; ci < c0 + ncols; ci += 2) {
+            float v[2][NJ];
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) v[q][j] = __ldg(p0 + j * rs + q * cstride);
+            p0 += 2 * cstride;
+            float2 yw[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) yw[j] = j < 4 ? yw_r[j & 3] : yw_s[j];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float2 t2 = make_float2(yw[0].x * v[q][0], yw[0].y * v[q][0]);
+#pragma unroll
+                for (int j = 1; j < NJ; ++j) t2 = ffma2(yw[j], v[q][j], t2);
+                fwd_xphase<P0, NPG>(acc[0], tb, ci + q, t2);
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int ci = c0; ci < c0 + ncols; ++ci) {
         float v[NJ][CPL];
@@ -320,7 +357,7 @@ __device__ __forceinline__ void fwd_columns_tall(float2 (&acc)[CPL][2][NPG], con
 
 // all merged feature rows of the unit for one group of bins, <= 8 rows per pass over the columns (the first pass's
 // first four weights are in registers across the CTA's slabs)
-template <int CS, int P0, int NPG, int CPL, bool HOIST, typename TB>
+template <int CS, int P0, int NPG, int CPL, int MLP, typename TB>
 __device__ __forceinline__ void fwd_group(float2 (&acc)[CPL][2][NPG], const TB& tb, const int u, const int ne,
                                           const float2 (&yw0)[4], const float* __restrict__ fcol, const int rs, const int c0,
                                           const int ncols, const int C) {
@@ -341,14 +378,14 @@ __device__ __forceinline__ void fwd_group(float2 (&acc)[CPL][2][NPG], const TB& 
         const float2* __restrict__ yws = tb.yw[u] + e0;
         const float* __restrict__ pe = p0 + (size_t)e0 * rs;
         switch (n) {   // warp-uniform
-            case 1: fwd_columns<CS, 1, P0, NPG, CPL, true>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
-            case 2: fwd_columns<CS, 2, P0, NPG, CPL, true>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
-            case 3: fwd_columns<CS, 3, P0, NPG, CPL, true>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
-            case 4: fwd_columns<CS, 4, P0, NPG, CPL, true>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
-            case 5: fwd_columns_tall<CS, 5, P0, NPG, CPL>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
-            case 6: fwd_columns_tall<CS, 6, P0, NPG, CPL>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
-            case 7: fwd_columns_tall<CS, 7, P0, NPG, CPL>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
-            default: fwd_columns_tall<CS, 8, P0, NPG, CPL>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 1: fwd_columns<CS, 1, P0, NPG, CPL, MLP>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 2: fwd_columns<CS, 2, P0, NPG, CPL, MLP>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 3: fwd_columns<CS, 3, P0, NPG, CPL, MLP>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 4: fwd_columns<CS, 4, P0, NPG, CPL, MLP>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 5: fwd_columns_tall<CS, 5, P0, NPG, CPL, (CPL == 1 ? MLP : 0)>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 6: fwd_columns_tall<CS, 6, P0, NPG, CPL, (CPL == 1 ? MLP : 0)>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            case 7: fwd_columns_tall<CS, 7, P0, NPG, CPL, (CPL == 1 ? MLP : 0)>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
+            default: fwd_columns_tall<CS, 8, P0, NPG, CPL, (CPL == 1 ? MLP : 0)>(acc, tb, yw, yws, pe, rs, c0, ncols, C); break;
         }
     }
 }
@@ -379,7 +416,7 @@ __device__ __forceinline__ void fwd_store_group(float* __restrict__ tp, const fl
     }
 }
 
-template <int PH, int PW, int CS, int OCC, int CPL, bool HOIST>
+template <int PH, int PW, int CS, int OCC, int CPL, int MLP>
 __global__ void __launch_bounds__(32 * ((PH + 1) / 2), OCC)
 roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int cgroups, const int slabs) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW, NT = 32 * NU, NP = (PW + 1) / 2, CC = 32 * CPL;
@@ -450,7 +487,7 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
         const float* __restrict__ fcol = funit + sl * CC;
         {
             float2 acc[CPL][2][NPA];
-            fwd_group<CS, 0, NPA, CPL, HOIST>(acc, tb, u, ne, yw0, fcol, rs, NPB > 0 ? grp0[0] : 0, NPB > 0 ? grpn[0] : ncols, C);
+            fwd_group<CS, 0, NPA, CPL, MLP>(acc, tb, u, ne, yw0, fcol, rs, NPB > 0 ? grp0[0] : 0, NPB > 0 ? grpn[0] : ncols, C);
             // the previous slab's bulk store must have read the tile before it is overwritten
             if (sl > 0 && threadIdx.x == 0) reg_bulk_wait_read();
             __syncthreads();
@@ -459,7 +496,7 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
         }
         if constexpr (NPB > 0) {
             float2 acc[CPL][2][NPB > 0 ? NPB : 1];
-            fwd_group<CS, NPA, (NPB > 0 ? NPB : 1), CPL, HOIST>(acc, tb, u, ne, yw0, fcol, rs, grp0[1], grpn[1], C);
+            fwd_group<CS, NPA, (NPB > 0 ? NPB : 1), CPL, MLP>(acc, tb, u, ne, yw0, fcol, rs, grp0[1], grpn[1], C);
 #pragma unroll
             for (int ch = 0; ch < CPL; ++ch) fwd_store_group<PW, NPA, (NPB > 0 ? NPB : 1)>(tp + ch * NB, acc[ch], nr);
         }
@@ -470,10 +507,10 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
     if (threadIdx.x == 0) reg_bulk_wait_read();
 }
 
-template <int PH, int PW, int CS, int OCC, int CPL, bool HOIST = true>
+template <int PH, int PW, int CS, int OCC, int CPL, int MLP = 1>
 static int launch_fwd_reg(const RoiParams& p, float* out, int slabs, cudaStream_t s) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW, CC = 32 * CPL;
-    auto kern = roi_align_fwd_reg_kernel<PH, PW, CS, OCC, CPL, HOIST>;
+    auto kern = roi_align_fwd_reg_kernel<PH, PW, CS, OCC, CPL, MLP>;
     const size_t smem = (size_t)CC * NB * sizeof(float);
     if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     slabs = std::max(1, std::min(slabs, p.C / CC));
@@ -720,6 +757,7 @@ int launch_roi_align_fwd_reg(const RoiParams& p, void* out, cudaStream_t s) {
     if (p.PH == 14) {
         if (p.C == 1024) {
             if (cpl == 2) return launch_fwd_reg<14, 14, 1024, 3, 2>(p, o, chans / 64, s);
+            if (reg_env("COIN_ROI_REG_MLP", 1) == 0) return launch_fwd_reg<14, 14, 1024, 4, 1, 0>(p, o, chans / 32, s);
             return launch_fwd_reg<14, 14, 1024, 4, 1>(p, o, chans / 32, s);
         }
         if (cpl == 2) return launch_fwd_reg<14, 14, 0, 3, 2>(p, o, chans / 64, s);
