@@ -472,7 +472,7 @@ extern "C" int coin_roi_align_fwd(const coin_level_t* levels_host, int nlevels, 
     // COIN_ROI_EXACT: 0 (default) separable fast kernel; 1 bit-exact parity kernel; 2 the parity kernel's FMA variant
     const int mode = env_int("COIN_ROI_EXACT", 0);
     if (mode == 0) {
-        if (roi_align_fwd_reg_supported(p, out_dtype)) return launch_roi_align_fwd_reg(p, out, as_stream(stream));
+        if (roi_align_fwd_reg_supported(p, out_dtype)) return launch_roi_align_fwd_reg(p, out, out_dtype, as_stream(stream));
         return launch_roi_align_fwd_sep(p, out, out_dtype, as_stream(stream));
     }
     LaunchCfg cfg;
@@ -494,7 +494,7 @@ extern "C" int coin_roi_align_fwd_dev(const coin_level_t* levels_host, int nleve
     p.k_dev = k_dev;
     const int mode = env_int("COIN_ROI_EXACT", 0);
     if (mode == 0) {
-        if (roi_align_fwd_reg_supported(p, out_dtype)) return launch_roi_align_fwd_reg(p, out, as_stream(stream));
+        if (roi_align_fwd_reg_supported(p, out_dtype)) return launch_roi_align_fwd_reg(p, out, out_dtype, as_stream(stream));
         return launch_roi_align_fwd_sep(p, out, out_dtype, as_stream(stream));
     }
     LaunchCfg cfg;
@@ -514,7 +514,7 @@ extern "C" int coin_roi_align_bwd(const coin_level_t* grad_levels_host, int nlev
     COIN_REQUIRE(grad_out, "roi_align_bwd: grad_out is null");
     // COIN_ROI_BWD_SEP: 1 (default) the separable kernel of roi_align_sep.cu; 0 the per-sample kernel below
     if (env_int("COIN_ROI_BWD_SEP", 1) != 0 && roi_align_bwd_reg_supported(p, grad_dtype))
-        return launch_roi_align_bwd_reg(p, grad_out, as_stream(stream));
+        return launch_roi_align_bwd_reg(p, grad_out, grad_dtype, as_stream(stream));
     if (PW <= 32 && env_int("COIN_ROI_BWD_SEP", 1) != 0) return launch_roi_align_bwd_sep(p, grad_out, grad_dtype, as_stream(stream));
     LaunchCfg cfg;
     if (int rc = pick_cfg(cfg, C, PH, PW, grad_dtype == COIN_F32 ? 4 : 2, "COIN_ROI_BWD")) return rc;

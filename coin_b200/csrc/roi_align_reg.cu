@@ -392,6 +392,23 @@ __device__ __forceinline__ void fwd_group(float2 (&acc)[CPL][2][NPG], const TB& 
 
 // the group's accumulators -> the unit's rows of the [channels][PH*PW] tile (tp points at row 2u, bin 0 of the channel)
 template <int PW, int P0, int NPG>
+__device__ __forceinline__ void fwd_store_group(__half* __restrict__ tp, const float2 (&acc)[2][NPG], const int nr) {
+    // fp16 output (the reference under autocast): fp32 accumulate, round to nearest even like the torchvision autocast path
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < NPG; ++i) {
+            const int b = 2 * (P0 + i);
+            if (PW % 2 == 0) {   // rows start 4-byte aligned: one half2 store per bin pair
+                if (r < nr) *reinterpret_cast<__half2*>(tp + r * PW + b) = __floats2half2_rn(acc[r][i].x, acc[r][i].y);
+            } else {
+                if (r < nr && b < PW) tp[r * PW + b] = __float2half_rn(acc[r][i].x);
+                if (r < nr && b + 1 < PW) tp[r * PW + b + 1] = __float2half_rn(acc[r][i].y);
+            }
+        }
+}
+
+template <int PW, int P0, int NPG>
 __device__ __forceinline__ void fwd_store_group(float* __restrict__ tp, const float2 (&acc)[2][NPG], const int nr) {
     if constexpr (PW % 2 == 0 && (2 * PW) % 4 == 0 && P0 % 2 == 0) {
         // row 2u starts 16-byte aligned, row 2u+1 (PW floats later, PW = 2 mod 4) 8-byte aligned
@@ -416,14 +433,14 @@ __device__ __forceinline__ void fwd_store_group(float* __restrict__ tp, const fl
     }
 }
 
-template <int PH, int PW, int CS, int OCC, int CPL, int MLP>
+template <typename T, int PH, int PW, int CS, int OCC, int CPL, int MLP>
 __global__ void __launch_bounds__(32 * ((PH + 1) / 2), OCC)
-roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int cgroups, const int slabs) {
+roi_align_fwd_reg_kernel(const RoiParams p, T* __restrict__ out, const int cgroups, const int slabs) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW, NT = 32 * NU, NP = (PW + 1) / 2, CC = 32 * CPL;
     constexpr int NPA = PW >= 12 ? (NP + 1) / 2 : NP, NPB = NP - NPA;   // bin pairs of the two groups (one for 7x7)
-    extern __shared__ __align__(128) float tile[];   // [CC channels][NB]: the CTA's contiguous output region
+    extern __shared__ __align__(128) float tile_raw[];   // [CC channels][NB] of T: the CTA's contiguous output region
+    T* tile = reinterpret_cast<T*>(tile_raw);            // (>= 4 KB: it doubles as tap-table scratch while the tables are built)
     __shared__ RegTables<NU> tb;
-    static_assert(CC * NB * sizeof(float) >= 2 * kRegTap * 16, "the tile doubles as tap-table scratch");
 
     const int k = blockIdx.x / cgroups;
     if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
@@ -436,15 +453,15 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
     const RoiGeom g = roi_geometry(p.rois + 5 * (size_t)k, L.spatial_scale, PH, PW, p.sampling_ratio, p.aligned);
     const float* __restrict__ fimg = L.feat_nhwc + (size_t)g.batch * H * W * C;
     const int nslab = min(slabs, (C - cg0) / CC);
-    float* __restrict__ oroi = out + (size_t)k * C * NB;
+    T* __restrict__ oroi = out + (size_t)k * C * NB;
 
     int cmin, ncols, creal0, creal1, grp0[2], grpn[2];
-    reg_build_tables<PH, PW, NT>(tb, tile, g, H, W, cmin, ncols, creal0, creal1, grp0, grpn);
+    reg_build_tables<PH, PW, NT>(tb, tile_raw, g, H, W, cmin, ncols, creal0, creal1, grp0, grpn);
     const int mode = tb.mode;
 
     if (mode == 2) {   // no sample inside the map: the RoI pools to zeros
-        float* o = oroi + (size_t)cg0 * NB;
-        for (int e = threadIdx.x; e < nslab * CC * NB; e += NT) o[e] = 0.0f;
+        T* o = oroi + (size_t)cg0 * NB;
+        for (int e = threadIdx.x; e < nslab * CC * NB; e += NT) o[e] = from_f32<T>(0.0f);
         return;
     }
     if (mode == 1) {   // exotic geometry (sampling grids beyond the tables): direct 4-tap evaluation
@@ -465,7 +482,7 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
                                Y.l * X.h * __ldg(f + Y.hi + X.lo) + Y.l * X.l * __ldg(f + Y.hi + X.hi);
                     }
                 }
-                oroi[(size_t)c * NB + b] = acc * rcount;
+                oroi[(size_t)c * NB + b] = from_f32<T>(acc * rcount);
             }
         }
         return;
@@ -481,7 +498,7 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
     const float* __restrict__ funit = fimg + (size_t)tb.ymin[u] * rs + (size_t)cmin * C + cg0 + CPL * lane;
     const int nr = min(2, PH - u * 2);
     const uint64_t pol = l2_evict_first_policy();
-    float* __restrict__ tp = tile + CPL * lane * NB + u * (2 * PW);
+    T* __restrict__ tp = tile + CPL * lane * NB + u * (2 * PW);
 
     for (int sl = 0; sl < nslab; ++sl) {
         const float* __restrict__ fcol = funit + sl * CC;
@@ -502,16 +519,16 @@ roi_align_fwd_reg_kernel(const RoiParams p, float* __restrict__ out, const int c
         }
         reg_fence_async();
         __syncthreads();
-        if (threadIdx.x == 0) reg_bulk_store(oroi + (size_t)(cg0 + sl * CC) * NB, tile, CC * NB * sizeof(float), pol);
+        if (threadIdx.x == 0) reg_bulk_store(oroi + (size_t)(cg0 + sl * CC) * NB, tile, CC * NB * sizeof(T), pol);
     }
     if (threadIdx.x == 0) reg_bulk_wait_read();
 }
 
-template <int PH, int PW, int CS, int OCC, int CPL, int MLP = 1>
-static int launch_fwd_reg(const RoiParams& p, float* out, int slabs, cudaStream_t s) {
+template <typename T, int PH, int PW, int CS, int OCC, int CPL, int MLP = 1>
+static int launch_fwd_reg(const RoiParams& p, T* out, int slabs, cudaStream_t s) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW, CC = 32 * CPL;
-    auto kern = roi_align_fwd_reg_kernel<PH, PW, CS, OCC, CPL, MLP>;
-    const size_t smem = (size_t)CC * NB * sizeof(float);
+    auto kern = roi_align_fwd_reg_kernel<T, PH, PW, CS, OCC, CPL, MLP>;
+    const size_t smem = std::max<size_t>((size_t)CC * NB * sizeof(T), 2 * kRegTap * sizeof(RXTap));
     if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     slabs = std::max(1, std::min(slabs, p.C / CC));
     const int cgroups = (int)ceil_div(p.C, CC * slabs);
@@ -594,13 +611,14 @@ __device__ __forceinline__ void bwd_columns(const float2 (&gr)[2][(PW + 1) / 2],
     }
 }
 
-template <int PH, int PW, int CS, int OCC>
+template <typename T, int PH, int PW, int CS, int OCC>
 __global__ void __launch_bounds__(32 * ((PH + 1) / 2), OCC)
-roi_align_bwd_reg_kernel(const RoiParams p, const float* __restrict__ go, const int cgroups, const int slabs) {
+roi_align_bwd_reg_kernel(const RoiParams p, const T* __restrict__ go, const int cgroups, const int slabs) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW, NT = 32 * NU, NP = (PW + 1) / 2;
     constexpr bool VEC = PW % 2 == 0 && (2 * PW) % 4 == 0 && NB % 4 == 0;
-    constexpr uint32_t kTileBytes = 32 * NB * sizeof(float);
-    extern __shared__ __align__(128) float tile[];   // [32 channels][NB] grad_out tile, then 4 KB of tap-table scratch
+    constexpr uint32_t kTileBytes = 32 * NB * sizeof(T);
+    extern __shared__ __align__(128) float tile_raw[];   // [32 channels][NB] grad_out tile of T, then 4 KB of tap-table scratch
+    const T* tile = reinterpret_cast<const T*>(tile_raw);
     __shared__ RegTables<NU> tb;
     __shared__ __align__(8) uint64_t bar_full;
 
@@ -616,16 +634,16 @@ roi_align_bwd_reg_kernel(const RoiParams p, const float* __restrict__ go, const 
     if (g.grid_h <= 0 || g.grid_w <= 0) return;    // no samples: no gradient
     float* __restrict__ gimg = const_cast<float*>(L.feat_nhwc) + (size_t)g.batch * H * W * C;
     const int nslab = min(slabs, (C - cg0) / 32);
-    const float* __restrict__ groi = go + ((size_t)k * C + cg0) * NB;
+    const T* __restrict__ groi = go + ((size_t)k * C + cg0) * NB;
     const uint64_t pol = l2_evict_first_policy();
 
     if (threadIdx.x == 0) {   // the first tile streams in while the tables are built
         reg_mbar_init(&bar_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        reg_bulk_load(tile, groi, kTileBytes, &bar_full, pol);
+        reg_bulk_load(tile_raw, groi, kTileBytes, &bar_full, pol);
     }
     int cmin, ncols, creal0, creal1, grp0[2], grpn[2];
-    reg_build_tables<PH, PW, NT>(tb, tile + 32 * NB, g, H, W, cmin, ncols, creal0, creal1, grp0, grpn);
+    reg_build_tables<PH, PW, NT>(tb, reinterpret_cast<char*>(tile_raw) + kTileBytes, g, H, W, cmin, ncols, creal0, creal1, grp0, grpn);
     const int mode = tb.mode;
 
     if (mode == 2) {   // no sample inside the map: no gradient (the tile in flight must land before the CTA may exit)
@@ -639,7 +657,7 @@ roi_align_bwd_reg_kernel(const RoiParams p, const float* __restrict__ go, const 
             const int c = cg0 + sl * 32 + lane;
             for (int b = u; b < NB; b += NU) {
                 const int ph = b / PW, pw = b - ph * PW;
-                const float gv = __ldg(groi + (size_t)(sl * 32 + lane) * NB + b) * rcount;
+                const float gv = to_f32(__ldg(groi + (size_t)(sl * 32 + lane) * NB + b)) * rcount;
                 for (int iy = 0; iy < g.grid_h; ++iy) {
                     const Tap Y = make_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H, W * C);
                     if (Y.lo < 0) continue;
@@ -664,12 +682,25 @@ roi_align_bwd_reg_kernel(const RoiParams p, const float* __restrict__ go, const 
     for (int j = 0; j < 4; ++j) yw0[j] = j < ne ? tb.yw[u][j] : make_float2(0.0f, 0.0f);
     float* __restrict__ gunit = gimg + (size_t)tb.ymin[u] * rs + (size_t)cmin * C + cg0 + lane;
     const int nr = min(2, PH - u * 2);
-    const float* __restrict__ tp = tile + lane * NB + u * (2 * PW);
+    const T* __restrict__ tp = tile + lane * NB + u * (2 * PW);
 
     for (int sl = 0; sl < nslab; ++sl) {
         reg_mbar_wait(&bar_full, sl & 1);          // the slab's [32][NB] grad_out tile has landed
         float2 gr[2][NP];
-        if (VEC) {   // rows 2u, 2u+1 are 2*PW consecutive floats of the channel's plane
+        if constexpr (sizeof(T) == 2) {   // fp16 gradients (the reference under autocast): widened to fp32 here
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const int b0 = 2 * i, b1 = 2 * i + 1;
+                    if (PW % 2 == 0) {
+                        gr[r][i] = r < nr ? __half22float2(*reinterpret_cast<const __half2*>(tp + r * PW + b0)) : make_float2(0.0f, 0.0f);
+                    } else {
+                        gr[r][i].x = (r < nr && b0 < PW) ? to_f32(tp[r * PW + b0]) : 0.0f;
+                        gr[r][i].y = (r < nr && b1 < PW) ? to_f32(tp[r * PW + b1]) : 0.0f;
+                    }
+                }
+        } else if (VEC) {   // rows 2u, 2u+1 are 2*PW consecutive floats of the channel's plane
             const float4* tp4 = reinterpret_cast<const float4*>(tp);
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
@@ -685,13 +716,13 @@ roi_align_bwd_reg_kernel(const RoiParams p, const float* __restrict__ go, const 
 #pragma unroll
                 for (int i = 0; i < NP; ++i) {
                     const int b0 = 2 * i, b1 = 2 * i + 1;
-                    gr[r][i].x = (r < nr && b0 < PW) ? tp[r * PW + b0] : 0.0f;
-                    gr[r][i].y = (r < nr && b1 < PW) ? tp[r * PW + b1] : 0.0f;
+                    gr[r][i].x = (r < nr && b0 < PW) ? to_f32(tp[r * PW + b0]) : 0.0f;
+                    gr[r][i].y = (r < nr && b1 < PW) ? to_f32(tp[r * PW + b1]) : 0.0f;
                 }
         }
         __syncthreads();                            // every warp holds its rows in registers: the tile is free
         if (threadIdx.x == 0 && sl + 1 < nslab)     // the next tile streams in under this slab's arithmetic
-            reg_bulk_load(tile, groi + (size_t)(sl + 1) * 32 * NB, kTileBytes, &bar_full, pol);
+            reg_bulk_load(tile_raw, groi + (size_t)(sl + 1) * 32 * NB, kTileBytes, &bar_full, pol);
         if (ne > 0) {
             float* __restrict__ gcol = gunit + sl * 32;
             switch (min(ne, 5)) {   // warp-uniform
@@ -705,11 +736,11 @@ roi_align_bwd_reg_kernel(const RoiParams p, const float* __restrict__ go, const 
     }
 }
 
-template <int PH, int PW, int CS, int OCC>
-static int launch_bwd_reg(const RoiParams& p, const float* go, int slabs, cudaStream_t s) {
+template <typename T, int PH, int PW, int CS, int OCC>
+static int launch_bwd_reg(const RoiParams& p, const T* go, int slabs, cudaStream_t s) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW;
-    auto kern = roi_align_bwd_reg_kernel<PH, PW, CS, OCC>;
-    const size_t smem = (size_t)32 * NB * sizeof(float) + 2 * kRegTap * sizeof(RXTap);
+    auto kern = roi_align_bwd_reg_kernel<T, PH, PW, CS, OCC>;
+    const size_t smem = (size_t)32 * NB * sizeof(T) + 2 * kRegTap * sizeof(RXTap);
     const int cgroups = (int)ceil_div(p.C, 32 * slabs);
     kern<<<(unsigned)(p.K * cgroups), 32 * NU, smem, s>>>(p, go, cgroups, slabs);
     return check_launch("roi_align_bwd_reg_kernel");
@@ -717,27 +748,32 @@ static int launch_bwd_reg(const RoiParams& p, const float* go, int slabs, cudaSt
 
 bool roi_align_bwd_reg_supported(const RoiParams& p, int grad_dtype) {
     if (reg_env("COIN_ROI_REG", 1) == 0 || reg_env("COIN_ROI_BWD_REG", 1) == 0) return false;
-    if (grad_dtype != COIN_F32 || p.C % 32 != 0) return false;
+    if ((grad_dtype != COIN_F32 && grad_dtype != COIN_F16) || p.C % 32 != 0) return false;
     return (p.PH == 14 && p.PW == 14) || (p.PH == 7 && p.PW == 7);
 }
 
-int launch_roi_align_bwd_reg(const RoiParams& p, const void* grad_out, cudaStream_t s) {
-    if (reinterpret_cast<uintptr_t>(grad_out) & 15) return fail(COIN_ERR_INVALID, "roi_align_bwd: grad_out must be 16-byte aligned");
-    const float* g = static_cast<const float*>(grad_out);
+template <typename T>
+static int dispatch_bwd_reg(const RoiParams& p, const T* g, cudaStream_t s) {
     const int nsl = (int)(p.C / 32);
     int slabs = reg_env("COIN_ROI_BWD_REG_SLABS", p.K < 1024 ? 2 : (p.PH == 7 ? 4 : 8));
     slabs = std::max(1, std::min(slabs, nsl));
     if (p.PH == 14) {
-        if (p.C == 1024) return launch_bwd_reg<14, 14, 1024, 4>(p, g, slabs, s);
-        return launch_bwd_reg<14, 14, 0, 4>(p, g, slabs, s);
+        if (p.C == 1024) return launch_bwd_reg<T, 14, 14, 1024, 4>(p, g, slabs, s);
+        return launch_bwd_reg<T, 14, 14, 0, 4>(p, g, slabs, s);
     }
-    if (p.C == 1024) return launch_bwd_reg<7, 7, 1024, 8>(p, g, slabs, s);
-    return launch_bwd_reg<7, 7, 0, 8>(p, g, slabs, s);
+    if (p.C == 1024) return launch_bwd_reg<T, 7, 7, 1024, 8>(p, g, slabs, s);
+    return launch_bwd_reg<T, 7, 7, 0, 8>(p, g, slabs, s);
+}
+
+int launch_roi_align_bwd_reg(const RoiParams& p, const void* grad_out, int grad_dtype, cudaStream_t s) {
+    if (reinterpret_cast<uintptr_t>(grad_out) & 15) return fail(COIN_ERR_INVALID, "roi_align_bwd: grad_out must be 16-byte aligned");
+    if (grad_dtype == COIN_F16) return dispatch_bwd_reg<__half>(p, static_cast<const __half*>(grad_out), s);
+    return dispatch_bwd_reg<float>(p, static_cast<const float*>(grad_out), s);
 }
 
 bool roi_align_fwd_reg_supported(const RoiParams& p, int out_dtype) {
     if (reg_env("COIN_ROI_REG", 1) == 0) return false;
-    if (out_dtype != COIN_F32 || p.C % 32 != 0) return false;
+    if ((out_dtype != COIN_F32 && out_dtype != COIN_F16) || p.C % 32 != 0) return false;
     // few RoIs (the step's private-box call, <= ~150 boxes that can each span the whole map): the grid cannot hide the
     // load latency of this kernel's long per-warp column walks, and the call runs next to the backward, which owns the
     // register file; the separable kernel (one 64-channel slab per CTA, 8 columns of loads in flight) finishes it in
@@ -746,29 +782,34 @@ bool roi_align_fwd_reg_supported(const RoiParams& p, int out_dtype) {
     return (p.PH == 14 && p.PW == 14) || (p.PH == 7 && p.PW == 7);
 }
 
-int launch_roi_align_fwd_reg(const RoiParams& p, void* out, cudaStream_t s) {
-    if (reinterpret_cast<uintptr_t>(out) & 15) return fail(COIN_ERR_INVALID, "roi_align_fwd: out must be 16-byte aligned");
-    float* o = static_cast<float*>(out);
-    // two channels per lane (64-channel slabs, 64-bit loads) when the channel count allows it
+template <typename T>
+static int dispatch_fwd_reg(const RoiParams& p, T* o, cudaStream_t s) {
+    // two channels per lane (64-channel slabs, 64-bit loads): measured slower than one (3 CTAs/SM), kept selectable
     const int cpl = (p.C % 64 == 0 && (reinterpret_cast<uintptr_t>(p.lv[0].feat_nhwc) & 7) == 0) ? reg_env("COIN_ROI_REG_CPL", 1) : 1;
     // channels per CTA: 256 (the tables are built once per CTA; 128 for the cheaper 7x7 units); few RoIs: fewer, so
     // that one very large RoI cannot leave a long tail (measured: foggy 14x14 256 -> 372 us, 128 -> 380, 512 -> 399)
     const int chans = p.K < 1024 ? reg_env("COIN_ROI_REG_CHANS_SMALL", 64) : reg_env("COIN_ROI_REG_CHANS", p.PH == 7 ? 128 : 256);
     if (p.PH == 14) {
         if (p.C == 1024) {
-            if (cpl == 2) return launch_fwd_reg<14, 14, 1024, 3, 2>(p, o, chans / 64, s);
-            if (reg_env("COIN_ROI_REG_MLP", 1) == 0) return launch_fwd_reg<14, 14, 1024, 4, 1, 0>(p, o, chans / 32, s);
-            return launch_fwd_reg<14, 14, 1024, 4, 1>(p, o, chans / 32, s);
+            if (cpl == 2) return launch_fwd_reg<T, 14, 14, 1024, 3, 2>(p, o, chans / 64, s);
+            if (reg_env("COIN_ROI_REG_MLP", 1) == 0) return launch_fwd_reg<T, 14, 14, 1024, 4, 1, 0>(p, o, chans / 32, s);
+            return launch_fwd_reg<T, 14, 14, 1024, 4, 1>(p, o, chans / 32, s);
         }
-        if (cpl == 2) return launch_fwd_reg<14, 14, 0, 3, 2>(p, o, chans / 64, s);
-        return launch_fwd_reg<14, 14, 0, 4, 1>(p, o, chans / 32, s);
+        if (cpl == 2) return launch_fwd_reg<T, 14, 14, 0, 3, 2>(p, o, chans / 64, s);
+        return launch_fwd_reg<T, 14, 14, 0, 4, 1>(p, o, chans / 32, s);
     }
     if (p.C == 1024) {
-        if (cpl == 2) return launch_fwd_reg<7, 7, 1024, 6, 2>(p, o, chans / 64, s);
-        return launch_fwd_reg<7, 7, 1024, 8, 1>(p, o, chans / 32, s);
+        if (cpl == 2) return launch_fwd_reg<T, 7, 7, 1024, 6, 2>(p, o, chans / 64, s);
+        return launch_fwd_reg<T, 7, 7, 1024, 8, 1>(p, o, chans / 32, s);
     }
-    if (cpl == 2) return launch_fwd_reg<7, 7, 0, 6, 2>(p, o, chans / 64, s);
-    return launch_fwd_reg<7, 7, 0, 8, 1>(p, o, chans / 32, s);
+    if (cpl == 2) return launch_fwd_reg<T, 7, 7, 0, 6, 2>(p, o, chans / 64, s);
+    return launch_fwd_reg<T, 7, 7, 0, 8, 1>(p, o, chans / 32, s);
+}
+
+int launch_roi_align_fwd_reg(const RoiParams& p, void* out, int out_dtype, cudaStream_t s) {
+    if (reinterpret_cast<uintptr_t>(out) & 15) return fail(COIN_ERR_INVALID, "roi_align_fwd: out must be 16-byte aligned");
+    if (out_dtype == COIN_F16) return dispatch_fwd_reg<__half>(p, static_cast<__half*>(out), s);
+    return dispatch_fwd_reg<float>(p, static_cast<float*>(out), s);
 }
 
 }  // namespace coin

@@ -101,8 +101,8 @@ int launch_roi_align_bwd_sep(const RoiParams& p, const void* grad_out, int grad_
 
 // register-tile kernels (roi_align_reg.cu): 14x14 / 7x7 outputs, C % 32 == 0, fp32
 bool roi_align_fwd_reg_supported(const RoiParams& p, int out_dtype);
-int launch_roi_align_fwd_reg(const RoiParams& p, void* out, cudaStream_t s);
+int launch_roi_align_fwd_reg(const RoiParams& p, void* out, int out_dtype, cudaStream_t s);
 bool roi_align_bwd_reg_supported(const RoiParams& p, int grad_dtype);
-int launch_roi_align_bwd_reg(const RoiParams& p, const void* grad_out, cudaStream_t s);
+int launch_roi_align_bwd_reg(const RoiParams& p, const void* grad_out, int grad_dtype, cudaStream_t s);
 
 }  // namespace coin

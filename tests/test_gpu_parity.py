@@ -142,6 +142,19 @@ def test_roi_align_backward_register_tile_cases(dev, c, pooled, sr, aligned):
     xx = x.to(dev).requires_grad_(True)
     coin_b200.ROIAlign(pooled, 1.0 / 16, sr, aligned)(xx, rois.to(dev)).backward(go.to(dev))
     close(xx.grad, xr.grad, scale=float(xr.grad.abs().max()))
+    # fp16 I/O (the reference runs this path under autocast, trainer.py:175): fp16 features / RoIs / gradients, fp32 math
+    x16, go16, rois16 = x.half(), go.half(), rois.half()
+    xr16 = x16.float().requires_grad_(True)
+    ref16 = torchvision.ops.roi_align(xr16, rois16.float(), (pooled, pooled), 1.0 / 16, sr, aligned)
+    ref16.backward(go16.float())
+    xh = x16.to(dev).requires_grad_(True)
+    out16 = coin_b200.ROIAlign(pooled, 1.0 / 16, sr, aligned)(xh, rois.to(dev))
+    assert out16.dtype == torch.float16
+    assert float((out16.cpu().float() - ref16.detach()).abs().max()) < 4e-3
+    out16.backward(go16.to(dev))
+    assert xh.grad.dtype == torch.float16
+    gmax = float(xr16.grad.abs().max())
+    assert float((xh.grad.cpu().float() - xr16.grad).abs().max()) <= 2e-3 * gmax
 
 
 def test_roi_align_register_tile_full_size(dev, monkeypatch):
