@@ -38,7 +38,12 @@ def main():
         out_bytes = k * c * pooled * pooled * 4
         alg_f = out_bytes + x.numel() * 4 + k * 20
         alg_b = out_bytes + 2 * x.numel() * 4 + k * 20
-        go = torch.randn(k, c, pooled, pooled, device=dev)
+        io = torch.float16 if os.environ.get("ROI_TIME_FP16") else torch.float32   # fp16 I/O: the autocast path
+        esz = 2 if io == torch.float16 else 4
+        out_bytes = k * c * pooled * pooled * esz
+        alg_f = out_bytes + x.numel() * 4 + k * 20
+        alg_b = out_bytes + 2 * x.numel() * 4 + k * 20
+        go = torch.randn(k, c, pooled, pooled, device=dev).to(io)
         buf = torch.zeros((n, h, w, c), device=dev)
         lv = ops._levels([buf], (1 / 16,))
         print(f"== {name}: K={k} C={c} map {h}x{w} pooled {pooled}: algorithmic fwd {alg_f/1e6:.1f} MB bwd {alg_b/1e6:.1f} MB", flush=True)
@@ -46,8 +51,8 @@ def main():
             for kv in filter(None, cfg.split(",")):
                 a, b = kv.split("=")
                 os.environ[a] = b
-            tf = timeit(lambda: ops.roi_align_forward([nhwc], (1 / 16,), rois, None, (pooled, pooled), 0, True, torch.float32))
-            tb = timeit(lambda: check(lib.coin_roi_align_bwd(lv, 1, ops._ptr(rois), ops._ptr(None), ops._ptr(go), 0, c, k,
+            tf = timeit(lambda: ops.roi_align_forward([nhwc], (1 / 16,), rois, None, (pooled, pooled), 0, True, io))
+            tb = timeit(lambda: check(lib.coin_roi_align_bwd(lv, 1, ops._ptr(rois), ops._ptr(None), ops._ptr(go), 0 if esz == 4 else 1, c, k,
                                                              pooled, pooled, 0, 1, ops._stream())))
             print(f"[{cfg}] fwd {tf:8.1f} us ({alg_f/tf/1e3:7.1f} GB/s)   bwd {tb:8.1f} us ({alg_b/tb/1e3:7.1f} GB/s)", flush=True)
             for kv in filter(None, cfg.split(",")):
