@@ -153,3 +153,49 @@ def rpn_predict_proposals(anchors: Boxes, pred_objectness_logits: torch.Tensor, 
     res.proposal_boxes = Boxes(boxes)
     res.objectness_logits = logits
     return res
+
+
+def detector_postprocess(results: Instances, output_height: int, output_width: int) -> Instances:
+    """detectron2 0.5 ``modeling/postprocessing.py::detector_postprocess`` as reached from
+    ``GeneralizedRCNN._postprocess`` (coin/modeling/meta_arch/clip_rcnn.py:424, clip_rcnn_oracle.py:251): rescale the
+    boxes from the network input size to the requested output size, clip, drop empty boxes (the
+    scale and clip run in the A13 / A4 kernels). Like detectron2 it rescales the Boxes object the input shares."""
+    new_size = (output_height, output_width)
+    scale_x, scale_y = output_width / results.image_size[1], output_height / results.image_size[0]
+    results = Instances(new_size, **results.get_fields())
+    if results.has("pred_boxes"):
+        output_boxes = results.pred_boxes
+    elif results.has("proposal_boxes"):
+        output_boxes = results.proposal_boxes
+    else:
+        output_boxes = None
+    assert output_boxes is not None, "Predictions must contain boxes!"
+    output_boxes.scale(scale_x, scale_y)
+    output_boxes.clip(results.image_size)
+    return results[output_boxes.nonempty()]
+
+
+def box_reg_loss(box2box_transform, proposal_boxes: torch.Tensor, gt_boxes: torch.Tensor, pred_deltas: torch.Tensor,
+                 gt_classes: torch.Tensor, num_classes: int, smooth_l1_beta: float = 0.0, normalizer=None) -> torch.Tensor:
+    """``FastRCNNOutputLayers.box_reg_loss`` (coin/modeling/roi_heads/fast_rcnn.py:601-646, smooth_l1 type): the
+    regression targets of the foreground proposals come from the A5 kernel (``Box2BoxTransform.get_deltas``, no
+    gradient), the smooth-L1 / L1 sum and its normalisation by the number of regions stay differentiable PyTorch."""
+    box_dim = proposal_boxes.shape[1]
+    fg_inds = torch.nonzero((gt_classes >= 0) & (gt_classes < num_classes), as_tuple=True)[0]
+    if pred_deltas.shape[1] == box_dim:   # class-agnostic regression (Base-Cloud.yaml:39)
+        fg_pred_deltas = pred_deltas[fg_inds]
+    else:
+        fg_pred_deltas = pred_deltas.view(-1, num_classes, box_dim)[fg_inds, gt_classes[fg_inds]]
+    if fg_inds.numel():
+        with torch.no_grad():
+            target = box2box_transform.get_deltas(proposal_boxes[fg_inds].contiguous(), gt_boxes[fg_inds].contiguous())
+    else:
+        target = fg_pred_deltas.detach()
+    n = torch.abs(fg_pred_deltas - target)
+    if smooth_l1_beta < 1e-5:             # fvcore smooth_l1_loss: plain L1 below this beta
+        loss = n.sum()
+    else:
+        loss = torch.where(n < smooth_l1_beta, 0.5 * n ** 2 / smooth_l1_beta, n - 0.5 * smooth_l1_beta).sum()
+    if normalizer is not None:
+        return loss / normalizer
+    return loss / max(gt_classes.numel(), 1.0)

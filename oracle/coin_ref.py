@@ -365,3 +365,25 @@ def match_dual_teacher(online: DetSet, offline: DetSet, tag: str, iou_thr: float
     else:
         raise ValueError(tag)
     return A, B, C
+
+
+def box_reg_loss(weights, proposal_boxes, gt_boxes, pred_deltas, gt_classes, num_classes: int, smooth_l1_beta: float = 0.0,
+                 normalizer=None):
+    """coin/modeling/roi_heads/fast_rcnn.py:601-646 (box_reg_loss_type == "smooth_l1") with fvcore's smooth_l1_loss
+    (beta < 1e-5 -> L1), reduction "sum", normalised by the number of regions (or `normalizer`)."""
+    from . import d2_ref
+    box_dim = proposal_boxes.shape[1]
+    fg_inds = torch.nonzero((gt_classes >= 0) & (gt_classes < num_classes), as_tuple=True)[0]
+    if pred_deltas.shape[1] == box_dim:
+        fg_pred_deltas = pred_deltas[fg_inds]
+    else:
+        fg_pred_deltas = pred_deltas.view(-1, num_classes, box_dim)[fg_inds, gt_classes[fg_inds]]
+    gt_pred_deltas = d2_ref.Box2BoxTransform(weights).get_deltas(proposal_boxes[fg_inds], gt_boxes[fg_inds])
+    n = torch.abs(fg_pred_deltas - gt_pred_deltas)
+    if smooth_l1_beta < 1e-5:
+        loss = n.sum()
+    else:
+        loss = torch.where(n < smooth_l1_beta, 0.5 * n ** 2 / smooth_l1_beta, n - 0.5 * smooth_l1_beta).sum()
+    if normalizer is not None:
+        return loss / normalizer
+    return loss / max(gt_classes.numel(), 1.0)

@@ -261,3 +261,13 @@ def predict_proposals_single(anchors, pred_anchor_deltas, pred_objectness_logits
     keep = batched_nms(boxes, scores, torch.zeros(len(boxes), dtype=torch.int64), nms_thresh)
     keep = keep[:post_nms_topk]
     return boxes[keep], scores[keep]
+
+
+def detector_postprocess(boxes: torch.Tensor, image_size, output_height: int, output_width: int):
+    """[d2 0.5] modeling/postprocessing.py::detector_postprocess on the box tensor (<- clip_rcnn.py:424 via
+    GeneralizedRCNN._postprocess): Boxes.scale(out_w / in_w, out_h / in_h), Boxes.clip((out_h, out_w)), nonempty().
+    Returns (boxes of the kept rows, keep mask)."""
+    sx, sy = output_width / image_size[1], output_height / image_size[0]
+    b = box_clip(box_scale(boxes, sx, sy), (output_height, output_width))
+    keep = box_nonempty(b)
+    return b[keep], keep

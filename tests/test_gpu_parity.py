@@ -521,6 +521,48 @@ def test_rpn_predict_proposals_vs_oracle(dev, hw, pre, post, min_size, seed):
     assert len(e.proposal_boxes) == 0 and e.objectness_logits.numel() == 0
 
 
+def test_detector_postprocess_and_box_reg_loss_vs_oracle(dev):
+    """SURVEY 8(f) ranks 4 / 2, the parts that sit directly on the path's kernels: detectron2's detector_postprocess
+    (<- clip_rcnn.py:424: scale, clip, nonempty) and FastRCNNOutputLayers.box_reg_loss (fast_rcnn.py:601-646: get_deltas
+    targets + L1 / smooth-L1 sum), value and gradient."""
+    g = synth.gen(321)
+    boxes = synth.random_boxes(g, 200, 600, 1200, lo=1.0, hi=900.0, min_side=0.0)
+    boxes[3] = torch.tensor([100.0, 50.0, 100.0, 80.0])          # zero width -> dropped
+    boxes[7] = torch.tensor([1300.0, 10.0, 1400.0, 50.0])        # outside after clip -> dropped
+    scores = torch.rand(200, generator=g)
+    want_b, keep = d2_ref.detector_postprocess(boxes, (600, 1200), 1024, 2048)
+    inst = Instances((600, 1200), pred_boxes=Boxes(boxes.to(dev)), scores=scores.to(dev))
+    got = integration.detector_postprocess(inst, 1024, 2048)
+    assert got.image_size == (1024, 2048) and len(got) == int(keep.sum())
+    close(got.pred_boxes.tensor, want_b, scale=2048.0)
+    assert torch.equal(got.scores.cpu(), scores[keep])
+
+    for kreg, beta in ((1, 0.0), (8, 0.0), (8, 0.5)):
+        k = 8
+        props = synth.random_boxes(g, 300, 600, 1200)
+        gts = synth.random_boxes(g, 300, 600, 1200)
+        cls = torch.randint(0, k + 1, (300,), generator=g)           # k = background
+        cls[:5] = -1                                                   # ignored
+        deltas = torch.randn(300, 4 * kreg, generator=g)
+        want = coin_ref.box_reg_loss((10.0, 10.0, 5.0, 5.0), props, gts, deltas.clone().requires_grad_(True), cls, k, beta)
+        dref = deltas.clone().requires_grad_(True)
+        coin_ref.box_reg_loss((10.0, 10.0, 5.0, 5.0), props, gts, dref, cls, k, beta).backward()
+        dd = deltas.to(dev).requires_grad_(True)
+        loss = integration.box_reg_loss(coin_b200.Box2BoxTransform((10.0, 10.0, 5.0, 5.0)), props.to(dev), gts.to(dev), dd,
+                                        cls.to(dev), k, beta)
+        loss.backward()
+        assert abs(float(loss.detach()) - float(want.detach())) <= 1e-5 * max(abs(float(want.detach())), 1.0)
+        if beta == 0.0:
+            # d|x|/dx = sign(x): compare where the residual is not within rounding of zero
+            mask = (dref.grad != 0)
+            assert torch.equal(torch.sign(dd.grad.cpu())[mask], torch.sign(dref.grad)[mask])
+        else:
+            close(dd.grad, dref.grad, scale=float(dref.grad.abs().max()))
+    empty = integration.box_reg_loss(coin_b200.Box2BoxTransform((10.0, 10.0, 5.0, 5.0)), props.to(dev), gts.to(dev),
+                                     torch.randn(300, 4, device=dev), torch.full((300,), 8, device=dev), 8)
+    assert float(empty) == 0.0
+
+
 def test_errors(dev):
     with pytest.raises(ValueError):
         ops.roi_align_forward([torch.zeros(1, 4, 4, 32, device=dev)], (1.0,), torch.zeros(2, 4, device=dev), None, (7, 7), 0, True, torch.float32)
