@@ -267,6 +267,27 @@ def test_predict_proposals_single_properties():
         d2_ref.predict_proposals_single(base, d, lg, (160, 192), 0.7, 300, 50, training=True)
 
 
+def test_detector_postprocess_and_box_reg_loss_hand_cases():
+    """Hand-computed cases for the restatements of detectron2's detector_postprocess (<- clip_rcnn.py:424) and of
+    FastRCNNOutputLayers.box_reg_loss (fast_rcnn.py:601-646)."""
+    boxes = torch.tensor([[10.0, 20.0, 110.0, 220.0], [590.0, 10.0, 700.0, 50.0], [5.0, 5.0, 5.0, 9.0]])
+    out, keep = d2_ref.detector_postprocess(boxes, (300, 600), 600, 1200)      # x2 in both directions
+    assert keep.tolist() == [True, True, False]                                 # zero-width box dropped
+    assert torch.equal(out, torch.tensor([[20.0, 40.0, 220.0, 440.0], [1180.0, 20.0, 1200.0, 100.0]]))  # clipped to w=1200
+    # one foreground proposal identical to its GT except a shift of dx = w/10: target delta = (wx * 0.1, 0, 0, 0)
+    props = torch.tensor([[0.0, 0.0, 100.0, 50.0], [0.0, 0.0, 10.0, 10.0]])
+    gts = torch.tensor([[10.0, 0.0, 110.0, 50.0], [0.0, 0.0, 10.0, 10.0]])
+    cls = torch.tensor([2, 8])                                                   # second row is background (K = 8)
+    pred = torch.zeros(2, 4)
+    loss = coin_ref.box_reg_loss((10.0, 10.0, 5.0, 5.0), props, gts, pred, cls, 8)
+    assert abs(float(loss) - 1.0 / 2) < 1e-6                                     # |0 - 10*0.1| summed, / R = 2 regions
+    loss = coin_ref.box_reg_loss((10.0, 10.0, 5.0, 5.0), props, gts, pred, cls, 8, smooth_l1_beta=2.0, normalizer=4.0)
+    assert abs(float(loss) - 0.5 * 1.0 / 2.0 / 4.0) < 1e-6                       # quadratic branch: 0.5 * n^2 / beta
+    per_class = torch.zeros(2, 32)
+    per_class[0, 8:12] = torch.tensor([1.0, 0.0, 0.0, 0.0])                      # class 2's slot already equals the target
+    assert float(coin_ref.box_reg_loss((10.0, 10.0, 5.0, 5.0), props, gts, per_class, cls, 8)) < 1e-6
+
+
 # the C ABI: the library loads and exports every symbol include/coinops.h declares
 # ---------------------------------------------------------------------------------------------
 def test_abi_exports_match_header():
