@@ -1,26 +1,26 @@
 // roi_align_reg.cu -- register-tile ROIAlign forward / backward for sm_100a (the default kernels for the
-// reference's head shapes: 14x14 and 7x7 outputs, C a multiple of 32, fp32).
+// reference's head shapes: 14x14 and 7x7 outputs, C a multiple of 32; fp32 or fp16 I/O, fp32 arithmetic).
 //
 // Replaces torchvision::roi_align / torchvision::_roi_align_backward as reached from
 // coin/modeling/roi_heads/clip_roi_heads.py:51-63,142-147,172-176 (ROIPooler -> ROIAlign). Same sample
 // positions, bilinear weights, validity rule and 1/count scaling as the torchvision kernels; the summation is
 // re-associated through the separable form (roi_align_sep.cu), so results agree to ~1e-7 relative.
 //
-// What changed against roi_align_sep.cu, and why (profiles/r01g_roi_align_ncu.md): that kernel spent one
-// shared-memory load per FMA (lane = output bin walking channels) and ~1430 LSU wavefronts per RoI and 32
-// channels, which pinned the L1/LSU data pipe at ~70 % while DRAM idled at 33 %. Here a lane IS a channel for
-// the whole computation and the unit's R x PW outputs live in registers:
+// What changed against roi_align_sep.cu, and why (profiles/r01g_roi_align_ncu.md, r01h_roi_align_ncu.md): that
+// kernel spent one shared-memory load per FMA (lane = output bin walking channels) and ~1430 LSU wavefronts per
+// RoI and 32 channels, which pinned the L1/LSU data pipe at ~70 % while DRAM idled at 33 %. Here a lane IS a
+// channel for the whole computation and the unit's 2 x PW outputs live in registers as FFMA2 pairs:
 //   forward   for every feature column of the RoI: t_r = sum_y Wy[r][y] * F[y][x][c]   (coalesced 128-byte loads,
-//             the y taps of the unit's R rows merged into one table so shared feature rows are loaded once),
-//             then acc[r][pw] += Wx[x][pw] * t_r for the <= 4 bins that touch the column (warp-uniform window
-//             start -> a switch over statically indexed registers; RoIs narrower than ~7 cells use all PW bins).
+//             the y taps of the unit's two rows merged into one table so shared feature rows are loaded once),
+//             then acc[r][pw] += Wx[x][pw] * t_r with the column's weight row broadcast from shared memory. The
+//             bins are walked in two groups (left / right half of the row) with their own column ranges, and a
+//             step covers as many columns as keep 8-12 independent loads in flight per warp.
 //             The accumulators go to a [32 channels][PH*PW] tile in shared memory laid out exactly like the
 //             CTA's contiguous output region out[k, c0:c0+32, :, :], and the tile leaves through ONE 1-D TMA
 //             bulk store (25 KB for 14x14) with an L2 evict-first hint - no LDS / STG for the 1.2 GB output.
 //   backward  the mirror image: the [32][PH*PW] grad_out tile arrives through ONE TMA bulk load, each lane
-//             pulls its channel's R x PW values into registers, u_r = sum_pw Wx[x][pw] * g[r][pw] per column,
+//             pulls its channel's 2 x PW values into registers, u_r = sum_pw Wx[x][pw] * g[r][pw] per column,
 //             and one fp32 RED per touched (feature row, column, channel) flushes sum_r Wy[r][y] * u_r.
-// ~480 LSU wavefronts per RoI and 32 channels instead of ~1430 / ~1200.
 #include <climits>
 
 #include "roi_common.cuh"
