@@ -288,6 +288,25 @@ def test_detector_postprocess_and_box_reg_loss_hand_cases():
     assert float(coin_ref.box_reg_loss((10.0, 10.0, 5.0, 5.0), props, gts, per_class, cls, 8)) < 1e-6
 
 
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port, timed on the host cores) prints ONE JSON
+    line with the keys the driver reads, and does not need a GPU."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "roi_path_images_per_sec" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"] == "foggy_roi_head"
+
+
 # the C ABI: the library loads and exports every symbol include/coinops.h declares
 # ---------------------------------------------------------------------------------------------
 def test_abi_exports_match_header():
