@@ -73,6 +73,74 @@ def process_boxes(boxes: torch.Tensor, old_size, new_size, flip: str = "no") -> 
     return b
 
 
+def process(inst: DetSet, old_size, new_size, flip: str = "no", thresh=None, keep_name: bool = False) -> DetSet:
+    """BASE_Trainer.process, base.py:80-126, on a field dict: deep copy, Boxes.scale, flip, pred_* -> gt_* renames
+    (unless keep_name), optional `scores >= thresh` row filter (on the ORIGINAL scores, base.py:117)."""
+    out = {k: v.clone() for k, v in inst.items()}
+    key = "pred_boxes" if "pred_boxes" in out else "gt_boxes"
+    boxes = process_boxes(out.pop(key), old_size, new_size, flip)
+    out[key if (keep_name or key == "gt_boxes") else "gt_boxes"] = boxes
+    if not keep_name:
+        out["gt_classes"] = out.pop("pred_classes")
+    if thresh is not None:
+        keep = inst["scores"] >= thresh
+        out = {k: v[keep] for k, v in out.items()}
+    return out
+
+
+def preprocess_results(results: Dict[str, DetSet], old_size, new_size, flip: str, thresh=None) -> Dict[str, DetSet]:
+    """BASE_Trainer.preprocess_results, base.py:128-136: 'RPN_AUG' (when collected) replaces 'RPN'."""
+    out = {"RCNN": process(results["RCNN"], old_size, new_size, flip, thresh)}
+    out["RPN"] = process(results["RPN_AUG" if "RPN_AUG" in results else "RPN"], old_size, new_size, flip, thresh)
+    return out
+
+
+def resize_boxes(boxes: torch.Tensor, size) -> torch.Tensor:
+    """GDINO.resize_boxes, gdino.py:144-160: cxcywh in [0,1] -> xyxy in pixels (per box: scale, x1y1 = c - wh/2,
+    x2y2 = wh + x1y1). An empty input is returned as is."""
+    h, w = size
+    if boxes.shape[0] == 0:
+        return boxes
+    b = boxes * torch.tensor([w, h, w, h], dtype=torch.float32)
+    xy = b[:, :2] - b[:, 2:] / 2
+    return torch.cat((xy, b[:, 2:] + xy), dim=1)
+
+
+def gdino_collect(ori: DetSet, method: str, rcnn_thresh: float, rpn_thresh: float, nms_thresh: float):
+    """GDINO_PROCESSOR.post_process without ZOOM/AUG (gdino_processor.py:287-293) + .nms (:164-182): score
+    thresholds for the two tags, then MyNMS(method).nms per tag."""
+    out = {}
+    for tag, thr in (("RCNN", rcnn_thresh), ("RPN", rpn_thresh)):
+        keep = ori["scores"] >= thr
+        sub = {k: v[keep] for k, v in ori.items()}
+        _, b, s, p, l = mynms(method, sub["pred_boxes"], sub["scores"], sub["probs"], sub["pred_classes"], nms_thresh)
+        out[tag] = {"pred_boxes": b, "scores": s, "pred_classes": l, "probs": p}
+    return out
+
+
+def rpn_distillation_loss(pred_logits: torch.Tensor, distillation_labels: torch.Tensor, teacher_probs: torch.Tensor,
+                          weight: float = 1.0):
+    """DualTeacherRPN.losses(only_distillation=True), rpn.py:326-340: KLDivLoss(reduction='mean') between
+    log([p, 1-p] + 1e-7), p = sigmoid(logit), and [q, 1-q] over the anchors with distillation label > 0.
+    Returns None when no anchor is selected (the reference then reports no such loss)."""
+    valid = distillation_labels > 0
+    p = torch.sigmoid(pred_logits[valid])
+    p = torch.stack((p, 1 - p), dim=1)
+    q = teacher_probs[valid]
+    q = torch.stack((q, 1 - q), dim=1)
+    if valid.float().sum() == 0:
+        return None
+    loss = torch.nn.functional.kl_div(torch.log(p + 1e-7), q, reduction="mean") * weight
+    assert not torch.isnan(loss)
+    return loss
+
+
+def roi_distillation_loss(scores_c: torch.Tensor, gt_probs: torch.Tensor, weight: float = 1.0):
+    """FastRCNNOutputLayers.losses, fast_rcnn.py:541-545: KLDivLoss(reduction='mean')(log(softmax(scores_c) + 1e-7),
+    gt_probs) over the private (C) boxes' class logits."""
+    return torch.nn.functional.kl_div(torch.log(torch.softmax(scores_c, dim=1) + 1e-7), gt_probs, reduction="mean") * weight
+
+
 # ------------------------------------------------------------------------------------------------
 # A12  coin/layers/nms.py  probabilistic-fusion NMS (MyNMS)
 # ------------------------------------------------------------------------------------------------
@@ -352,6 +420,9 @@ def match_dual_teacher(online: DetSet, offline: DetSet, tag: str, iou_thr: float
             out["gt_classes"] = off_s["gt_classes"]
         out["gt_scores_online"], out["gt_scores_offline"] = on_s["scores"], off_s["scores"]
         out["gt_probs_online"], out["gt_probs_offline"] = on_s["probs"], off_s["probs"]
+        # Instances.set asserts equal field lengths (trainer.py:404,440): a duplicate group with several members of
+        # the matched class appends several offline rows against one online row (trainer.py:379-383) and fails here
+        assert len({int(v.shape[0]) for v in out.values()}) == 1, "Adding a field of another length to an Instances"
         return delete_duplicate_boxes(out, choose=choose)
 
     if tag == "RCNN":

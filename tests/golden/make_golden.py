@@ -4,12 +4,11 @@ and torchvision's CPU operators exist):
     python tests/golden/make_golden.py
 
 * fusion_nms_<method>.pt : outputs of the reference's OWN coin/layers/nms.py (loaded unmodified from
-  /root/reference through the detectron2 stub in oracle/d2_shim) on seeded cloud-like detections.
+  /root/reference through oracle/ref_loader.py and the detectron2 stand-in in oracle/d2_shim) on seeded cloud-like detections.
 * tv_ops.pt              : torchvision 0.26 CPU roi_align (fwd + bwd) / nms / batched_nms / box_iou
   on small seeded inputs, including adversarial RoIs (outside the map, sub-bin, whole map, inverted).
 The GPU box has no /root/reference; tests only read the .pt files.
 """
-import importlib.util
 import os
 import sys
 
@@ -19,17 +18,14 @@ import torchvision
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle", "d2_shim"))
 
 from coin_b200 import synth  # noqa: E402
 
 
 def load_reference_nms():
-    path = "/root/reference/coin/layers/nms.py"
-    spec = importlib.util.spec_from_file_location("ref_coin_layers_nms", path)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+    """The reference's coin/layers/nms.py, loaded unmodified by path behind the detectron2 stand-in."""
+    from oracle import ref_loader
+    return ref_loader.load("coin.layers.nms")
 
 
 def cloud_like(seed, n, k, height=600, width=1200):
