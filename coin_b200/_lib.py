@@ -44,6 +44,9 @@ _SIGNATURES = {
     "coin_last_error": (c_char_p, []),
     "coin_version": (c_int, []),
     "coin_launch_count": (ctypes.c_longlong, []),
+    "coin_set_option": (c_int, [c_char_p, c_int]),
+    "coin_unset_option": (c_int, [c_char_p]),
+    "coin_get_option": (c_int, [c_char_p, c_int]),
     "coin_nchw_to_nhwc_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, P]),
     "coin_nhwc_f32_to_nchw": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "coin_roi_align_fwd": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
@@ -56,6 +59,7 @@ _SIGNATURES = {
     "coin_get_deltas": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P]),
     "coin_boxes_clip": (c_int, [P, c_int64, c_float, c_float, P]),
     "coin_boxes_scale_flip": (c_int, [P, P, c_int64, c_float, c_float, c_int, c_float, c_float, P]),
+    "coin_boxes_cxcywh_to_xyxy": (c_int, [P, P, c_int64, c_float, c_float, c_int, P]),
     "coin_pairwise_iou": (c_int, [P, c_int64, P, c_int64, P, P]),
     "coin_matcher": (c_int, [P, c_int64, c_int64, POINTER(c_float), c_int, POINTER(ctypes.c_int8), c_int,
                              P, P, P, P, P]),
@@ -85,6 +89,8 @@ _SIGNATURES = {
     "coin_relabel_rpn_dev": (c_int, [P, P, c_int64, P, P, P, P, P]),
     "coin_match_abc_dev": (c_int, [P, P, P, c_int64, P, P, P, c_int64, P, c_int, c_float, c_float, c_int64,
                                    P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "coin_match_abc_both_dev": (c_int, [P, P, P, c_int64, P, P, P, c_int64, P, c_float, c_float, c_int64,
+                                        P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "coin_rpn_proposals_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "coin_rpn_proposals": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_double, c_float, c_float, c_float, c_float,
                                    c_float, c_float, c_float, c_float, P, P, P, P, P, c_size_t, P]),
@@ -106,6 +112,35 @@ for _name, (_res, _args) in _SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = the library does not export the declared ABI
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+def set_option(name: str, value) -> None:
+    """Process-wide mode / tuning switch of the library (include/coinops.h: coin_set_option); None unsets."""
+    if value is None:
+        check(lib.coin_unset_option(name.encode()))
+    else:
+        check(lib.coin_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str, default: int = 0) -> int:
+    return int(lib.coin_get_option(name.encode(), int(default)))
+
+
+class options:
+    """Context manager: ``with _lib.options(COIN_ROI_EXACT=1): ...`` (restores the previous state)."""
+
+    def __init__(self, **kw):
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = get_option(k, -(2 ** 31))
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, None if v == -(2 ** 31) else v)
 
 
 class CoinError(RuntimeError):

@@ -74,6 +74,23 @@ __global__ void scale_flip_kernel(const float4* __restrict__ in, float4* __restr
     out[i] = b;
 }
 
+// GDINO.resize_boxes (gdino.py:144-160) + Boxes.clip (gdino.py:135-136): normalised cxcywh -> pixel xyxy.
+// Per box, in the reference's order: b *= (W, H, W, H); xy1 = c - wh / 2; xy2 = wh + xy1.
+__global__ void cxcywh_to_xyxy_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t n, float W, float H,
+                                      int clip) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 b = in[i];
+    b.x *= W; b.y *= H; b.z *= W; b.w *= H;
+    const float x1 = b.x - b.z / 2.0f, y1 = b.y - b.w / 2.0f;
+    float4 o = make_float4(x1, y1, b.z + x1, b.w + y1);
+    if (clip) {
+        o.x = fminf(fmaxf(o.x, 0.0f), W); o.y = fminf(fmaxf(o.y, 0.0f), H);
+        o.z = fminf(fmaxf(o.z, 0.0f), W); o.w = fminf(fmaxf(o.w, 0.0f), H);
+    }
+    out[i] = o;
+}
+
 }  // namespace coin
 using namespace coin;
 
@@ -121,4 +138,14 @@ extern "C" int coin_boxes_scale_flip(const float* in, float* out, int64_t n, flo
     scale_flip_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), n, sx, sy, flip, net_w, net_h);
     return check_launch("scale_flip_kernel");
+}
+
+extern "C" int coin_boxes_cxcywh_to_xyxy(const float* in, float* out, int64_t n, float img_h, float img_w, int clip,
+                                         coin_stream_t stream) {
+    COIN_REQUIRE(n >= 0, "boxes_cxcywh_to_xyxy: bad size");
+    if (n == 0) return COIN_OK;
+    COIN_REQUIRE(in && out && aligned16(in) && aligned16(out), "boxes_cxcywh_to_xyxy: null or misaligned pointer");
+    cxcywh_to_xyxy_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), n, img_w, img_h, clip);
+    return check_launch("cxcywh_to_xyxy_kernel");
 }

@@ -2,6 +2,9 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
 
 namespace coin {
 static thread_local char g_err[512] = "";
@@ -15,7 +18,53 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+
+// Tuning / mode switches (COIN_ROI_EXACT, COIN_ROI_REG, ...). Each name is looked up in the environment ONCE, on first
+// use, and cached; coin_set_option overrides it for the process. Launch paths read an int from a small table instead
+// of calling getenv() per launch.
+namespace {
+struct Opt { char name[48]; int value; bool set; };
+constexpr int kMaxOpts = 64;
+Opt g_opts[kMaxOpts];
+int g_nopts = 0;
+std::mutex g_opt_mu;
+Opt* find_opt(const char* name) {
+    for (int i = 0; i < g_nopts; ++i)
+        if (strcmp(g_opts[i].name, name) == 0) return &g_opts[i];
+    if (g_nopts == kMaxOpts || strlen(name) >= sizeof(g_opts[0].name)) return nullptr;
+    Opt* o = &g_opts[g_nopts++];
+    strcpy(o->name, name);
+    const char* v = getenv(name);
+    o->set = v != nullptr;
+    o->value = v ? atoi(v) : 0;
+    return o;
+}
+}  // namespace
+
+int option(const char* name, int dflt) {
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    Opt* o = find_opt(name);
+    return (o && o->set) ? o->value : dflt;
+}
 }  // namespace coin
+
+extern "C" int coin_set_option(const char* name, int value) {
+    if (!name) return coin::fail(COIN_ERR_INVALID, "coin_set_option: null name");
+    std::lock_guard<std::mutex> lk(coin::g_opt_mu);
+    coin::Opt* o = coin::find_opt(name);
+    if (!o) return coin::fail(COIN_ERR_CAPACITY, "coin_set_option: option table full or name too long (%s)", name);
+    o->value = value;
+    o->set = true;
+    return COIN_OK;
+}
+extern "C" int coin_unset_option(const char* name) {
+    if (!name) return coin::fail(COIN_ERR_INVALID, "coin_unset_option: null name");
+    std::lock_guard<std::mutex> lk(coin::g_opt_mu);
+    coin::Opt* o = coin::find_opt(name);
+    if (o) o->set = false;
+    return COIN_OK;
+}
+extern "C" int coin_get_option(const char* name, int dflt) { return name ? coin::option(name, dflt) : dflt; }
 
 extern "C" const char* coin_last_error(void) { return coin::g_err; }
 extern "C" int coin_version(void) { return 100; }

@@ -17,6 +17,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 int fail(int code, const char* fmt, ...);
 
 void count_launch();  // capi.cu: process-wide counter behind coin_launch_count()
+int option(const char* name, int dflt);  // capi.cu: cached environment lookup, overridable by coin_set_option()
 
 inline int check_launch(const char* what) {
     count_launch();

@@ -380,10 +380,7 @@ __global__ void pooler_levels_kernel(const float* __restrict__ boxes, int64_t n,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
+static inline int env_int(const char* name, int dflt) { return option(name, dflt); }
 
 static int fill_params(RoiParams& p, const coin_level_t* levels, int nlevels, const float* rois,
                        const int32_t* roi_level, int C, int K, int PH, int PW, int sr, int aligned) {

@@ -27,10 +27,7 @@
 
 namespace coin {
 
-static inline int reg_env(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
+static inline int reg_env(const char* name, int dflt) { return option(name, dflt); }
 
 constexpr int kRegTap = 128;    // x / y tap-table entries (PW*grid_w and PH*grid_h must fit)
 constexpr int kRegCols = 96;    // feature columns of one RoI handled by the tables

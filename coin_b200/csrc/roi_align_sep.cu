@@ -30,10 +30,7 @@
 
 namespace coin {
 
-static inline int sep_env(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
+static inline int sep_env(const char* name, int dflt) { return option(name, dflt); }
 
 constexpr int kSepTap = 128;     // tap-table entries per axis (PW*grid_w and PH*grid_h must fit)
 constexpr int kSepCells = 32;    // T cells (row x feature column) per unit

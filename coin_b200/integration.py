@@ -34,13 +34,53 @@ def process(instances: Instances, old_size, new_size, random_flip: str, thresh: 
     boxes = Boxes(ops.boxes_scale_flip(fields.pop(name).tensor, net_w / img_w, net_h / img_h, random_flip,
                                        (net_h, net_w)))
     for k, v in fields.items():
-        out.set(k, v)
+        # the reference deep-copies every field (base.py:84): the result must not alias its input (e.g. a cache entry)
+        out.set(k, v.clone() if hasattr(v, "clone") else v)
     out.set(name if (keep_name or name == "gt_boxes") else "gt_boxes", boxes)
     if not keep_name:
         out.set("gt_classes", out.get("pred_classes"))
         out.remove("pred_classes")
     if thresh is not None:
         return out[instances.scores >= thresh]
+    return out
+
+
+def preprocess_results(results: dict, new_image_size, random_flip: str, thresh: Optional[float] = None) -> dict:
+    """BASE_Trainer.preprocess_results (base.py:128-136): process() for both tags of a cached cloud result; a collected
+    'RPN_AUG' set replaces 'RPN'. Like the reference it rewrites the dict it is given."""
+    old = (results["height"], results["width"])
+    results["RCNN"] = process(results["RCNN"]["instances"], old, new_image_size, random_flip, thresh)
+    if "RPN_AUG" in results:
+        del results["RPN"]
+        results["RPN"] = process(results["RPN_AUG"]["instances"], old, new_image_size, random_flip, thresh)
+        del results["RPN_AUG"]
+    else:
+        results["RPN"] = process(results["RPN"]["instances"], old, new_image_size, random_flip, thresh)
+    return results
+
+
+def resize_boxes(boxes: torch.Tensor, size: Tuple[int, int], clip: bool = False) -> torch.Tensor:
+    """GDINO.resize_boxes (gdino.py:144-160): cxcywh in [0,1] -> xyxy in pixels of an (H, W) image; clip=True also
+    applies the Boxes.clip(size) the caller does next (gdino.py:135-136). One launch instead of a Python loop per box."""
+    if boxes.shape[0] == 0:
+        return boxes
+    return ops.boxes_cxcywh_to_xyxy(boxes, size, clip)
+
+
+def gdino_collect(ori: Instances, nms_module, rcnn_thresh: float, rpn_thresh: float, nms_thresh: float) -> dict:
+    """GDINO_PROCESSOR.post_process without ZOOM / AUG (gdino_processor.py:287-293) + GDINO_PROCESSOR.nms (:164-182):
+    the two score thresholds, then ``mynms.nms`` (coin_b200.layers.MyNMS) per tag."""
+    out = {}
+    for tag, thr in (("RCNN", rcnn_thresh), ("RPN", rpn_thresh)):
+        sub = ori[ori.scores >= thr]
+        _, boxes, scores, probs, labels = nms_module.nms(sub.pred_boxes.tensor, sub.scores, sub.probs, sub.pred_classes,
+                                                         nms_thresh)
+        inst = Instances(ori.image_size)
+        inst.pred_boxes = Boxes(boxes)
+        inst.scores = scores
+        inst.pred_classes = labels
+        inst.probs = probs
+        out[tag] = {"instances": inst}
     return out
 
 

@@ -221,6 +221,16 @@ def boxes_scale_flip(boxes: torch.Tensor, sx: float, sy: float, flip: str = "no"
     return out
 
 
+def boxes_cxcywh_to_xyxy(boxes: torch.Tensor, image_size: Tuple[float, float], clip: bool = False) -> torch.Tensor:
+    """GDINO.resize_boxes (gdino.py:144-160): normalised cxcywh -> pixel xyxy (optionally followed by Boxes.clip)."""
+    boxes = _boxes(boxes, "boxes")
+    out = torch.empty_like(boxes)
+    h, w = image_size
+    check(lib.coin_boxes_cxcywh_to_xyxy(_ptr(boxes), _ptr(out), boxes.shape[0], float(h), float(w), int(bool(clip)),
+                                        _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # IoU / Matcher
 # ------------------------------------------------------------------------------------------------
@@ -518,9 +528,17 @@ def relabel_rpn_dev_(matches, labels, len_a, len_c):
 
 
 def match_abc_fields_dev(on: dict, off: dict, nd_dev: torch.Tensor, tag: str, iou_thr: float, weight_for_box_a: float):
-    """Knowledge separation + field gathers with the CLIP-detector detection count on the device.
+    """Knowledge separation + field gathers for ONE tag with the CLIP-detector detection count on the device.
+    Returns (A, B or None, C, counts); see match_abc_fields_both_dev."""
+    return match_abc_fields_both_dev(on, off, nd_dev, iou_thr, weight_for_box_a, tags=(tag,))[tag]
+
+
+def match_abc_fields_both_dev(on: dict, off: dict, nd_dev: torch.Tensor, iou_thr: float, weight_for_box_a: float,
+                              tags=("RCNN", "RPN")):
+    """Knowledge separation (one launch for all requested tags) + field gathers (one launch per tag), with the
+    CLIP-detector detection count on the device.
     on / off: dicts with gt_boxes [n,4], gt_classes int64 [n], scores [n], probs [n,k1] (off is padded to
-    its capacity; nd_dev holds the live count). Returns (A, B or None, C, counts): padded field dicts with
+    its capacity; nd_dev holds the live count). Returns {tag: (A, B or None, C, counts)}: padded field dicts with
     the reference's names and the device int32 counts [nA, nB, nC, status, nC_off, 0, 0, 0]."""
     on_boxes, off_boxes = _boxes(on["gt_boxes"], "online boxes"), _boxes(off["gt_boxes"], "offline boxes")
     on_cls, off_cls = _i64c(on["gt_classes"], "online classes"), _i64c(off["gt_classes"], "offline classes")
@@ -533,16 +551,32 @@ def match_abc_fields_dev(on: dict, off: dict, nd_dev: torch.Tensor, tag: str, io
     i32 = lambda n: torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
     f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
     i64 = lambda n: torch.empty((n,), dtype=torch.int64, device=dev)
-    a_on, a_off, b_on, b_off = i32(cap), i32(cap), i32(cap), i32(cap)
     c_on, c_off = i32(nc + nd), i32(nc + nd)
-    a_box, b_box = f32(max(cap, 1), 4), f32(max(cap, 1), 4)
-    counts = torch.zeros((8,), dtype=torch.int32, device=dev)
     ws = _workspace(lib.coin_match_abc_workspace_bytes(nc, nd), dev)
-    code = {"RCNN": _lib.TAG_RCNN, "RPN": _lib.TAG_RPN}[tag]
-    check(lib.coin_match_abc_dev(_ptr(on_boxes), _ptr(on_cls), _ptr(on_s), nc, _ptr(off_boxes), _ptr(off_cls),
-                                 _ptr(off_s), nd, _ptr(_count(nd_dev)), code, float(iou_thr), float(weight_for_box_a),
-                                 cap, _ptr(a_on), _ptr(a_off), _ptr(a_box), _ptr(b_on), _ptr(b_off), _ptr(b_box),
-                                 _ptr(c_on), _ptr(c_off), _ptr(counts), _ptr(ws), ws.numel(), _stream()))
+    idx = {}
+    for tag in tags:
+        idx[tag] = {"a_on": i32(cap), "a_off": i32(cap), "a_box": f32(max(cap, 1), 4),
+                    "counts": torch.zeros((8,), dtype=torch.int32, device=dev)}
+        if tag == "RCNN":
+            idx[tag].update({"b_on": i32(cap), "b_off": i32(cap), "b_box": f32(max(cap, 1), 4)})
+    nd_ptr = _ptr(_count(nd_dev))
+    if len(tags) == 2:
+        r, p = idx["RCNN"], idx["RPN"]
+        check(lib.coin_match_abc_both_dev(_ptr(on_boxes), _ptr(on_cls), _ptr(on_s), nc, _ptr(off_boxes), _ptr(off_cls),
+                                          _ptr(off_s), nd, nd_ptr, float(iou_thr), float(weight_for_box_a), cap,
+                                          _ptr(r["a_on"]), _ptr(r["a_off"]), _ptr(r["a_box"]), _ptr(r["b_on"]),
+                                          _ptr(r["b_off"]), _ptr(r["b_box"]), _ptr(p["a_on"]), _ptr(p["a_off"]),
+                                          _ptr(p["a_box"]), _ptr(c_on), _ptr(c_off), _ptr(r["counts"]), _ptr(p["counts"]),
+                                          _ptr(ws), ws.numel(), _stream()))
+    else:
+        tag = tags[0]
+        t = idx[tag]
+        code = {"RCNN": _lib.TAG_RCNN, "RPN": _lib.TAG_RPN}[tag]
+        check(lib.coin_match_abc_dev(_ptr(on_boxes), _ptr(on_cls), _ptr(on_s), nc, _ptr(off_boxes), _ptr(off_cls),
+                                     _ptr(off_s), nd, nd_ptr, code, float(iou_thr), float(weight_for_box_a), cap,
+                                     _ptr(t["a_on"]), _ptr(t["a_off"]), _ptr(t["a_box"]), _ptr(t.get("b_on")),
+                                     _ptr(t.get("b_off")), _ptr(t.get("b_box")), _ptr(c_on), _ptr(c_off),
+                                     _ptr(t["counts"]), _ptr(ws), ws.numel(), _stream()))
 
     def pseudo(n, boxes, split):
         d = {"gt_boxes": boxes}
@@ -553,11 +587,6 @@ def match_abc_fields_dev(on: dict, off: dict, nd_dev: torch.Tensor, tag: str, io
         d["gt_scores_online"], d["gt_scores_offline"] = f32(n), f32(n)
         d["gt_probs_online"], d["gt_probs_offline"] = f32(n, k1), f32(n, k1)
         return d
-
-    a = pseudo(max(cap, 1), a_box, False)
-    b = pseudo(max(cap, 1), b_box, True) if tag == "RCNN" else None
-    c = {"gt_boxes": f32(max(nc + nd, 1), 4), "gt_classes": i64(max(nc + nd, 1)), "gt_scores": f32(max(nc + nd, 1)),
-         "gt_probs": f32(max(nc + nd, 1), k1)}
 
     def dets_struct(boxes, cls, s, p):
         st = _lib.CoinDets()
@@ -579,10 +608,19 @@ def match_abc_fields_dev(on: dict, off: dict, nd_dev: torch.Tensor, tag: str, io
         return st
 
     on_st, off_st = dets_struct(on_boxes, on_cls, on_s, on_p), dets_struct(off_boxes, off_cls, off_s, off_p)
-    a_st, c_st = pseudo_struct(a, "A"), pseudo_struct(c, "C")
-    b_st = pseudo_struct(b, "B") if b is not None else None
-    check(lib.coin_abc_pack(ctypes.byref(on_st), nc, ctypes.byref(off_st), nd, _ptr(_count(nd_dev)), k1, code,
-                            _ptr(a_on), _ptr(a_off), _ptr(b_on), _ptr(b_off), _ptr(c_on), _ptr(c_off), _ptr(counts),
-                            ctypes.byref(a_st), ctypes.byref(b_st) if b_st is not None else None, ctypes.byref(c_st),
-                            cap, _stream()))
-    return a, b, c, counts
+    out = {}
+    for tag in tags:
+        t = idx[tag]
+        code = {"RCNN": _lib.TAG_RCNN, "RPN": _lib.TAG_RPN}[tag]
+        a = pseudo(max(cap, 1), t["a_box"], False)
+        b = pseudo(max(cap, 1), t["b_box"], True) if tag == "RCNN" else None
+        c = {"gt_boxes": f32(max(nc + nd, 1), 4), "gt_classes": i64(max(nc + nd, 1)), "gt_scores": f32(max(nc + nd, 1)),
+             "gt_probs": f32(max(nc + nd, 1), k1)}
+        a_st, c_st = pseudo_struct(a, "A"), pseudo_struct(c, "C")
+        b_st = pseudo_struct(b, "B") if b is not None else None
+        check(lib.coin_abc_pack(ctypes.byref(on_st), nc, ctypes.byref(off_st), nd, nd_ptr, k1, code,
+                                _ptr(t["a_on"]), _ptr(t["a_off"]), _ptr(t.get("b_on")), _ptr(t.get("b_off")), _ptr(c_on),
+                                _ptr(c_off), _ptr(t["counts"]), ctypes.byref(a_st),
+                                ctypes.byref(b_st) if b_st is not None else None, ctypes.byref(c_st), cap, _stream()))
+        out[tag] = (a, b, c, t["counts"])
+    return out

@@ -338,12 +338,17 @@ class RoIPathStep:
         for i in range(n_img):
             cloud, clip, ndet = clouds[i], clips[i], ndets[i]
             per_tag = {}
-            for tag, st in (("RCNN", s_img[i]), ("RPN", s_img[2 * n_img + i])):
-                st.wait_event(det_done[i])
+            st_t, st_r = s_img[i], s_img[2 * n_img + i]
+            with torch.cuda.stream(st_t):
+                # T4: ONE launch separates the knowledge for both tags (they share everything up to the A/B split)
+                both = ops.match_abc_fields_both_dev(cloud, clip, ndet, self.MATCH_THRESH, self.w_a)
+                self._mark(f"img{i}.abc_done")
+                abc_done = st_t.record_event()
+            for tag, st in (("RCNN", st_t), ("RPN", st_r)):
+                st.wait_event(abc_done)
                 with torch.cuda.stream(st):
-                    a, bb, cc, cnt = ops.match_abc_fields_dev(cloud, clip, ndet, tag, self.MATCH_THRESH, self.w_a)  # T4
+                    a, bb, cc, cnt = both[tag]
                     slot(f"abc{i}.{tag}", cnt)
-                    self._mark(f"img{i}.abc_{tag}_done")
                     per_tag[tag] = (a, bb, cc)
                     n_a, n_b, n_c = cnt[0:1], cnt[1:2], cnt[2:3]
                     if tag == "RCNN":
@@ -364,6 +369,7 @@ class RoIPathStep:
                         out["rpn_labels"].append(ops.relabel_rpn_dev_(idx2, lab2, n_a, n_c))
                         self._mark(f"img{i}.rpn_labels_done")
             out["abc"].append(per_tag)
+            out.setdefault("_keepalive2", []).append(both)
 
         # ---- ROIAlign forward on the private (C) boxes of every image: a high-priority stream, so it does
         #      not wait for the big forward/backward to drain

@@ -54,6 +54,13 @@ int coin_version(void);
 /* Number of kernels this library has launched in the process so far (bench.py reports the delta
  * over its timed region as `gpu_launches`; the radix sort of N > 4096 boxes counts as one). */
 long long coin_launch_count(void);
+/* Mode / tuning switches, by name (e.g. "COIN_ROI_EXACT" = 1: the bit-exact ROIAlign forward kernel, un-fused tap
+ * arithmetic in torchvision's order; "COIN_ROI_REG" = 0: separable kernels for every shape). A name is read from the
+ * environment once, on first use; coin_set_option overrides it for the process, coin_unset_option returns to the
+ * built-in default. No reference counterpart: the reference selects kernels through the torch dispatcher. */
+int coin_set_option(const char* name_host, int value);
+int coin_unset_option(const char* name_host);
+int coin_get_option(const char* name_host, int dflt);
 
 /* ---------------------------------------------------------------------------------------------
  * ROIAlign / ROIPooler
@@ -121,6 +128,11 @@ int coin_boxes_clip(float* boxes, int64_t n, float h, float w, coin_stream_t str
  * 2 vertical. in may equal out. */
 int coin_boxes_scale_flip(const float* in, float* out, int64_t n, float sx, float sy, int flip,
                           float net_w, float net_h, coin_stream_t stream);
+
+/* GDINO.resize_boxes (coin/modeling/meta_arch/gdino.py:144-160): cxcywh in [0,1] -> xyxy in pixels of an
+ * img_h x img_w image; clip != 0 also applies the Boxes.clip that follows it (gdino.py:135-136). in may equal out. */
+int coin_boxes_cxcywh_to_xyxy(const float* in, float* out, int64_t n, float img_h, float img_w, int clip,
+                              coin_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * IoU and Matcher
@@ -244,8 +256,12 @@ int coin_det_postprocess(const float* boxes, const float* scores, int64_t R, int
  * C rows reference exactly one side. All index outputs have capacity cap_pairs = nc*nd + nc + nd
  * (A, B) and nc + nd (C). counts: device int32 [8] = {nA, nB, nC, status, nC_off, 0, 0, 0}: C rows
  * [0, nC_off) are CLIP-detector rows (c_off valid), rows [nC_off, nC) cloud rows (c_on valid);
- * status != 0 when an assertion of the reference would fire. The device resolves the reference's random.randint
- * picks as "first" and its set iterations as ascending ("determinism policy"). */
+ * status bits: 4 = pair capacity exceeded; 8 = a duplicate group holds several boxes of the matched class (the
+ * reference fails at trainer.py:402 on that input); 16 = a cloud self-cluster with a single class (the reference
+ * asserts, util.py:488); 32 = a self-cluster too large for the on-chip replay of CPython's set order (then, and only
+ * then, clusters are taken lowest-member-first). Rows come in the REFERENCE's order: the Python-set iterations of
+ * trainer.py:369,391 and util.py:481 are replayed exactly (csrc/pyset.cuh); random.randint picks take the first
+ * element, i.e. the reference with randint pinned to its lower bound ("determinism policy"). */
 size_t coin_match_abc_workspace_bytes(int64_t nc, int64_t nd);
 int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float* on_scores, int64_t nc,
                    const float* off_boxes, const int64_t* off_classes, const float* off_scores,
@@ -296,6 +312,18 @@ int coin_match_abc_dev(const float* on_boxes, const int64_t* on_classes, const f
                        int64_t cap_pairs, int32_t* a_on, int32_t* a_off, float* a_boxes, int32_t* b_on,
                        int32_t* b_off, float* b_boxes, int32_t* c_on, int32_t* c_off, int32_t* counts,
                        void* ws, size_t ws_bytes, coin_stream_t stream);
+
+/* Both tags of one image in ONE launch: 'RCNN' and 'RPN' share everything up to the A/B split (trainer.py:401), so
+ * match_boxes (trainer.py:463-478) need not run the matching twice. rcnn_* / rpn_* as a_* / b_* above (tag 'RPN' has
+ * no B set), c_on / c_off are common to both tags, counts_rcnn / counts_rpn are two device int32 [8] vectors. */
+int coin_match_abc_both_dev(const float* on_boxes, const int64_t* on_classes, const float* on_scores, int64_t nc,
+                            const float* off_boxes, const int64_t* off_classes, const float* off_scores,
+                            int64_t nd_cap, const int32_t* nd_dev, float iou_thr, float weight_for_box_a,
+                            int64_t cap_pairs, int32_t* rcnn_a_on, int32_t* rcnn_a_off, float* rcnn_a_boxes,
+                            int32_t* rcnn_b_on, int32_t* rcnn_b_off, float* rcnn_b_boxes, int32_t* rpn_a_on,
+                            int32_t* rpn_a_off, float* rpn_a_boxes, int32_t* c_on, int32_t* c_off,
+                            int32_t* counts_rcnn, int32_t* counts_rpn, void* ws, size_t ws_bytes,
+                            coin_stream_t stream);
 
 /* One segment of a row concatenation: `count` rows at `ptr` (or *count_dev <= count rows when
  * count_dev is non-NULL); `prefix` is the value of the extra leading column, if any. */

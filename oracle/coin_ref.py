@@ -8,9 +8,11 @@ A detection set is a plain ``dict`` of equally long CPU tensors (the reference u
 Two places of the reference are not functions of their inputs alone:
   * ``random.randint`` picks (coin/engine/trainer.py:385,387; coin/utils/util.py:450);
   * iteration order of CPython ``set`` objects (trainer.py:369,391; util.py:471-482).
-Both are exposed as policies: ``choose`` (callable n -> index; default = first, the device policy;
-pass ``random_choice`` for the reference's behaviour) and ``set_order`` ("ascending" = device
-policy, "cpython" = literal ``list(set)`` as the reference executes it).
+Both are exposed as policies: ``choose`` (callable n -> index; default = first = the reference with
+random.randint pinned to its lower bound, which is what the device does; pass ``random_choice`` for
+the seeded behaviour) and ``set_order`` ("cpython", the default = literal ``list(set)`` as the
+reference executes it, which the device replays exactly; "ascending" = sorted, kept to show where the
+two differ).
 """
 import random
 from typing import Callable, Dict, List, Optional, Tuple
@@ -315,7 +317,7 @@ def delete_duplicate_boxes(d: DetSet, return_split: bool = False,
     return cat([singles] + groups)
 
 
-def self_clusters(boxes: torch.Tensor, thresh: float, set_order: str = "ascending") -> List[List[int]]:
+def self_clusters(boxes: torch.Tensor, thresh: float, set_order: str = "cpython") -> List[List[int]]:
     """util.py:459-482 (filter_result + find_same): index clusters of size != 1 among boxes whose
     mutual IoU >= thresh, closed transitively by the reference's recursive set union."""
     adj = d2_ref.pairwise_iou(boxes, boxes) >= thresh
@@ -339,7 +341,7 @@ def self_clusters(boxes: torch.Tensor, thresh: float, set_order: str = "ascendin
 
 
 def online_boxes_merging(online: DetSet, common_off: DetSet, common_on: DetSet,
-                         set_order: str = "ascending"):
+                         set_order: str = "cpython"):
     """util.py:484-507: resolve cloud boxes that overlap each other at IoU >= 0.95 with
     different classes."""
     for cluster in self_clusters(online["gt_boxes"], 0.95, set_order):
@@ -366,7 +368,7 @@ def online_boxes_merging(online: DetSet, common_off: DetSet, common_on: DetSet,
 
 def match_dual_teacher(online: DetSet, offline: DetSet, tag: str, iou_thr: float = 0.5,
                        weight_for_box_a: float = 1.0,
-                       choose: Callable[[int], int] = first_choice, set_order: str = "ascending"):
+                       choose: Callable[[int], int] = first_choice, set_order: str = "cpython"):
     """trainer.py:338-461. ``online`` = cloud detections (after process()), ``offline`` =
     CLIP-detector detections; both with fields gt_boxes, gt_classes, scores, probs.
     Returns (A, B or None, C) as dicts."""

@@ -26,6 +26,24 @@ def head_grad(shape, seed=2024):
     return torch.randn(shape.images * shape.rois, shape.channels, shape.pooled, shape.pooled, generator=g)
 
 
+def label_stage(abc_per_image, batch, anchors=None):
+    """S3 + S2 alone (clip_roi_heads.py:345-362, rpn.py:209-228) on GIVEN pseudo-label sets: fed with the device's own
+    A/B/C boxes it shows the labelling exact on bit-identical inputs, with no tolerance budget."""
+    sh = batch["shape"]
+    anchors = anchors_for(sh) if anchors is None else anchors
+    roi_labels, rpn_labels = [], []
+    for img, per_tag in zip(batch["images"], abc_per_image):
+        a, b, c = (x["gt_boxes"].cpu() for x in per_tag["RCNN"])
+        gt = torch.cat((a, b, c))
+        props = torch.cat((img["proposals"], a, b))
+        idx, lab = d2_ref.Matcher([0.5], [0, 1], False)(d2_ref.pairwise_iou(gt, props))
+        roi_labels.append((idx, coin_ref.relabel_roi(idx, lab, len(a), len(b), len(c))))
+        a2, c2 = per_tag["RPN"][0]["gt_boxes"].cpu(), per_tag["RPN"][2]["gt_boxes"].cpu()
+        idx2, lab2 = d2_ref.Matcher([0.3, 0.7], [0, -1, 1], True)(d2_ref.pairwise_iou(torch.cat((a2, c2)), anchors))
+        rpn_labels.append(coin_ref.relabel_rpn(idx2, lab2, len(a2), len(c2)))
+    return roi_labels, rpn_labels
+
+
 def run(batch, backward=True, weight_for_box_a=1.0, anchors=None, grad=None, roi_limit=None):
     """roi_limit: bound the number of RoIs per image fed to ROIAlign (bench.py's bounded CPU sample)."""
     sh = batch["shape"]
@@ -94,17 +112,20 @@ def _close(a, b, what, atol):
     torch.testing.assert_close(a, b, rtol=1e-5, atol=atol, msg=lambda m: f"{what}: {m}")
 
 
-def _labels(a, b, what, budget):
+def _labels(a, b, what, budget, flips=None):
     a = a.cpu()
     assert a.shape == b.shape, f"{what}: shape"
     bad = int((a != b).sum())
+    if flips is not None:
+        flips[what] = (bad, a.numel())
     assert bad <= budget * a.numel(), f"{what}: {bad} of {a.numel()} entries differ (budget {budget})"
 
 
-def compare(got, want, pix_atol=1.2e-4, label_budget=0.0, pooled_exact=None):
+def compare(got, want, pix_atol=1.2e-4, label_budget=0.0, pooled_exact=None, flips=None):
     """Bit-exact on every index / label / keep list and on ROIAlign forward; 1e-5 relative on floats
     (pixel coordinates: atol 1.2e-4 px; gradients: atol 1e-5 * max|grad|).
 
+    flips: optional dict that receives, per label vector, (number of differing entries, length).
     label_budget: fraction of proposal / anchor labels allowed to differ. It must be 0 whenever the
     pseudo boxes fed to the Matcher are bit-identical on both sides (WEIGHT_FOR_BOX_A == 1: they are the
     cloud boxes). With score-weighted merging the A/B boxes inherit the one-ulp difference between the
@@ -130,14 +151,13 @@ def compare(got, want, pix_atol=1.2e-4, label_budget=0.0, pooled_exact=None):
                     else:
                         _eq(gp[k], v, f"abc[{i}].{tag}.{name}.{k}")
     for i, (g, w) in enumerate(zip(got["roi_labels"], want["roi_labels"])):
-        _labels(g[0], w[0], f"roi_labels[{i}].matched_idxs", label_budget)
-        _labels(g[1], w[1], f"roi_labels[{i}].matched_labels", label_budget)
+        _labels(g[0], w[0], f"roi_labels[{i}].matched_idxs", label_budget, flips)
+        _labels(g[1], w[1], f"roi_labels[{i}].matched_labels", label_budget, flips)
     for i, (g, w) in enumerate(zip(got["rpn_labels"], want["rpn_labels"])):
         for j, name in enumerate(("gt_labels", "matched_idxs", "distillation_idxs", "distillation_labels")):
-            _labels(g[j], w[j], f"rpn_labels[{i}].{name}", label_budget)
+            _labels(g[j], w[j], f"rpn_labels[{i}].{name}", label_budget, flips)
     if pooled_exact is None:
-        import os
-        pooled_exact = os.environ.get("COIN_ROI_EXACT", "0") == "1"
+        pooled_exact = False
     if pooled_exact:   # parity mode of the forward kernel: bit-identical to the CPU kernel
         _eq(got["pooled"], want["pooled"], "pooled (ROIAlign forward, bit-exact)")
     else:              # default FMA accumulation: 1e-5 relative to the feature scale

@@ -4,9 +4,9 @@ import sys
 import pytest
 import torch
 
-# ROIAlign forward has a bit-exact parity mode (un-fused tap arithmetic) and a default FMA mode; the GPU
-# suite runs in parity mode and checks the default mode separately within the 1e-5 tolerance.
-os.environ.setdefault("COIN_ROI_EXACT", "1")
+# The GPU suite runs the DEFAULT kernels (what bench.py times). ROIAlign forward additionally has a bit-exact parity
+# mode (option COIN_ROI_EXACT=1: un-fused tap arithmetic in torchvision's order); tests that check it turn it on
+# with the `roi_exact` fixture / `_lib.options(COIN_ROI_EXACT=1)`.
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 if ROOT not in sys.path:
@@ -31,6 +31,13 @@ def pytest_collection_modifyitems(config, items):
 def dev():
     assert torch.cuda.is_available()
     return torch.device("cuda:0")
+
+
+@pytest.fixture
+def roi_exact():
+    from coin_b200 import _lib
+    with _lib.options(COIN_ROI_EXACT=1):
+        yield
 
 
 def load_golden(name):

@@ -26,7 +26,14 @@ def test_bdd_shape_step_matches_oracle(dev):
     # CPU libm by an ulp, and the RPN Matcher's low-quality rule (label 1 where IoU EQUALS the row maximum) is
     # discontinuous in the box coordinates: a handful of the 36 630 anchor labels may flip (budget 1e-3; every
     # index / keep list / field stays exact and the boxes stay within 1e-5 relative).
-    pipeline_ref.compare(got, want, label_budget=1e-3)
+    flips = {}
+    pipeline_ref.compare(got, want, label_budget=1e-3, flips=flips)
+    print("label entries that differ from the CPU run:", {k: v for k, v in flips.items() if v[0]} or "none")
+    # ... and on bit-identical pseudo boxes (the device's own) the labelling stage is exact, budget 0
+    roi, rpn = pipeline_ref.label_stage(got["abc"], batch)
+    for i in range(shape.images):
+        assert all(torch.equal(g.cpu(), w) for g, w in zip(got["roi_labels"][i], roi[i]))
+        assert all(torch.equal(g.cpu(), w) for g, w in zip(got["rpn_labels"][i], rpn[i]))
     assert got["pooled"].shape == (2 * 2000, 32, 14, 14)
     assert got["summary"]["rpn_keep"] == want["summary"]["rpn_keep"]
 
@@ -98,16 +105,7 @@ def test_sweep_roi_align_10k_rois(dev, pooled):
     x = torch.randn(1, 1024, 37, 50, generator=g)
     boxes = synth.random_boxes(g, 10_000, 600, 800, lo=8.0, hi=780.0)
     rois = torch.cat((torch.zeros(10_000, 1), boxes), dim=1)
-    import os
-    old = os.environ.get("COIN_ROI_EXACT")
-    os.environ["COIN_ROI_EXACT"] = "0"
-    try:
-        out = coin_b200.ROIAlign(pooled, 1.0 / 16, 0, True)(x.to(dev), rois.to(dev))
-    finally:
-        if old is None:
-            os.environ.pop("COIN_ROI_EXACT", None)
-        else:
-            os.environ["COIN_ROI_EXACT"] = old
+    out = coin_b200.ROIAlign(pooled, 1.0 / 16, 0, True)(x.to(dev), rois.to(dev))
     assert out.shape == (10_000, 1024, pooled, pooled) and bool(torch.isfinite(out).all())
     sel = torch.arange(0, 10_000, 97)
     ref = torchvision.ops.roi_align(x, rois[sel], (pooled, pooled), 1.0 / 16, 0, True)

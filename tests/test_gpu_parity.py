@@ -11,7 +11,7 @@ import torch
 import torchvision
 
 import coin_b200
-from coin_b200 import integration, ops, synth
+from coin_b200 import _lib, integration, ops, synth
 from coin_b200.structures import Boxes, Instances
 from conftest import load_golden
 from oracle import clib, coin_ref, d2_ref
@@ -28,7 +28,7 @@ def close(a, b, scale=1.0):
 # ---------------------------------------------------------------------------------------------
 # ROIAlign
 # ---------------------------------------------------------------------------------------------
-def test_roi_align_golden_fwd_bwd(dev):
+def test_roi_align_golden_fwd_bwd(dev, roi_exact):
     tv = load_golden("tv_ops.pt")
     x, rois = tv["x"].to(dev), tv["rois"].to(dev)
     for case in tv["roi_align"]:
@@ -42,7 +42,7 @@ def test_roi_align_golden_fwd_bwd(dev):
 
 @pytest.mark.parametrize("pooled", [7, 14])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
-def test_roi_align_foggy_shape(dev, pooled, dtype):
+def test_roi_align_foggy_shape(dev, roi_exact, pooled, dtype):
     g = synth.gen(31)
     shape = synth.SHAPES["foggy_cpu"]
     h, w = shape.feat_hw
@@ -60,8 +60,7 @@ def test_roi_align_foggy_shape(dev, pooled, dtype):
         assert torch.equal(out.cpu(), ref)  # fp32 accumulate + round-to-nearest-even, same as autocast
 
 
-def test_roi_align_default_fma_mode_within_tolerance(dev, monkeypatch):
-    monkeypatch.setenv("COIN_ROI_EXACT", "0")
+def test_roi_align_default_fma_mode_within_tolerance(dev):
     g = synth.gen(34)
     shape = synth.SHAPES["foggy_cpu"]
     h, w = shape.feat_hw
@@ -82,11 +81,10 @@ def test_roi_align_default_fma_mode_within_tolerance(dev, monkeypatch):
                                                   # the register-tile kernels (C % 32 == 0, 14x14 / 7x7)
                                                   (64, 14, 14, 0, True), (96, 14, 14, 2, False), (32, 7, 7, 0, True),
                                                   (128, 14, 14, 1, True), (160, 7, 7, 3, False)])
-def test_roi_align_separable_kernel_cases(dev, monkeypatch, c, ph, pw, sr, aligned):
+def test_roi_align_separable_kernel_cases(dev, c, ph, pw, sr, aligned):
     """The default (separable) forward kernel against torchvision CPU over geometry edge cases: channel
     tails, non-square outputs, fixed sampling ratios (sample spacing > 1 cell), RoIs outside / larger
     than / much smaller than the map, inverted RoIs, fp16 output."""
-    monkeypatch.setenv("COIN_ROI_EXACT", "0")
     g = synth.gen(35 + c)
     h, w = 37, 75
     x = torch.randn(2, c, h, w, generator=g)
@@ -157,7 +155,7 @@ def test_roi_align_backward_register_tile_cases(dev, c, pooled, sr, aligned):
     assert float((xh.grad.cpu().float() - xr16.grad).abs().max()) <= 2e-3 * gmax
 
 
-def test_roi_align_register_tile_full_size(dev, monkeypatch):
+def test_roi_align_register_tile_full_size(dev):
     """BASELINE configs[1] size (3 x 512 RoIs, C = 1024, 14x14, map [3,1024,37,75]): the register-tile forward against
     the bit-exact parity kernel (itself pinned to torchvision CPU), the register-tile backward against the separable
     kernel, and the adjoint identity <pool(x), G> = <x, pool^T(G)> that ties the two together."""
@@ -168,18 +166,17 @@ def test_roi_align_register_tile_full_size(dev, monkeypatch):
     boxes = [synth.random_boxes(g, shape.rois, shape.height, shape.width) for _ in range(n)]
     rois = torch.cat([torch.cat((torch.full((len(b), 1), float(i)), b), 1) for i, b in enumerate(boxes)]).to(dev)
     layer = coin_b200.ROIAlign(shape.pooled, 1.0 / 16, 0, True)
-    monkeypatch.setenv("COIN_ROI_EXACT", "1")
-    ref = layer(x, rois)
-    monkeypatch.setenv("COIN_ROI_EXACT", "0")
+    with _lib.options(COIN_ROI_EXACT=1):
+        ref = layer(x, rois)
     xx = x.clone().requires_grad_(True)
     out = layer(xx, rois)
     scale = float(x.abs().max())
     assert float((out - ref).abs().max()) <= 1e-5 * scale
     go = torch.randn(out.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
     out.backward(go)
-    monkeypatch.setenv("COIN_ROI_REG", "0")
-    xs = x.clone().requires_grad_(True)
-    layer(xs, rois).backward(go)
+    with _lib.options(COIN_ROI_REG=0):
+        xs = x.clone().requires_grad_(True)
+        layer(xs, rois).backward(go)
     gscale = float(xs.grad.abs().max())
     assert float((xx.grad - xs.grad).abs().max()) <= 1e-5 * gscale
     lhs = float((out.detach().double() * go.double()).sum())
@@ -187,7 +184,46 @@ def test_roi_align_register_tile_full_size(dev, monkeypatch):
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
 
 
-def test_roi_align_edge_cases(dev):
+def test_roi_align_non_finite_features(dev):
+    """Inf / NaN cells in the feature map (fp16 overflow under AMP). torchvision multiplies a cell only when it is one of
+    the 4 taps of a sample, so only RoIs that sample the cell turn non-finite. Contract of this library:
+      * COIN_ROI_EXACT=1 (parity kernel): the output equals torchvision's bit for bit, non-finite pattern included;
+      * default kernels (register-tile / separable): they walk the bounding tile of a unit's samples with zero weights for
+        the cells a sample does not touch, and 0 * Inf = NaN - so an RoI whose sampled tile contains a non-finite cell may
+        return NaN where torchvision returns a finite number. Every RoI whose tile is clean is unaffected, and every
+        output torchvision makes non-finite is non-finite here too (never a silently finite value)."""
+    g = synth.gen(55)
+    h, w = 37, 75
+    x = torch.randn(1, 64, h, w, generator=g)
+    x[0, 3, 10, 20] = float("inf")
+    x[0, 40, 30, 60] = float("nan")
+    boxes = synth.random_boxes(g, 200, 600, 1200, lo=24.0, hi=400.0)
+    rois = torch.cat((torch.zeros(200, 1), boxes), dim=1)
+    ref = torchvision.ops.roi_align(x, rois, (14, 14), 1.0 / 16, 0, True)
+    layer = coin_b200.ROIAlign(14, 1.0 / 16, 0, True)
+    with _lib.options(COIN_ROI_EXACT=1):
+        exact = layer(x.to(dev), rois.to(dev)).cpu()
+    assert torch.equal(torch.isnan(exact), torch.isnan(ref)) and torch.equal(torch.isinf(exact), torch.isinf(ref))
+    fin = torch.isfinite(ref)
+    assert torch.equal(exact[fin], ref[fin])
+    out = layer(x.to(dev), rois.to(dev)).cpu()
+    assert bool((~torch.isfinite(out))[~fin].all())          # never finite where the reference is not
+    # RoIs (with a one-cell margin) that do not cover either bad cell are untouched
+    cells = [(10, 20), (30, 60)]
+    x1, y1, x2, y2 = (boxes[:, i] / 16 - 0.5 for i in range(4))
+    clean = torch.ones(200, dtype=torch.bool)
+    for cy, cx in cells:
+        clean &= ~((x1 - 2 <= cx) & (cx <= x2 + 2) & (y1 - 2 <= cy) & (cy <= y2 + 2))
+    assert int(clean.sum()) > 50 and int((~clean).sum()) > 5
+    assert bool(torch.isfinite(out[clean]).all())
+    assert float((out[clean] - ref[clean]).abs().max()) < 4e-6 * 5
+    # channels other than the two poisoned ones are clean for EVERY RoI
+    ok_ch = torch.ones(64, dtype=torch.bool)
+    ok_ch[3] = ok_ch[40] = False
+    assert float((out[:, ok_ch] - ref[:, ok_ch]).abs().max()) < 4e-6 * 5
+
+
+def test_roi_align_edge_cases(dev, roi_exact):
     x = torch.arange(2 * 3 * 6 * 9, dtype=torch.float32).reshape(2, 3, 6, 9)
     layer = coin_b200.ROIAlign(7, 0.5, 0, True)
     assert layer(x.to(dev), torch.zeros(0, 5, device=dev)).shape == (0, 3, 7, 7)
@@ -204,7 +240,7 @@ def test_roi_align_edge_cases(dev):
         layer(x.to(dev), torch.zeros(3, 4, device=dev))
 
 
-def test_roi_pooler_multilevel(dev):
+def test_roi_pooler_multilevel(dev, roi_exact):
     g = synth.gen(33)
     feats = [torch.randn(2, 40, 64 // s, 96 // s, generator=g) for s in (1, 2, 4, 8)]
     scales = (1 / 4, 1 / 8, 1 / 16, 1 / 32)
