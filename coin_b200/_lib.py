@@ -63,6 +63,7 @@ _SIGNATURES = {
     "coin_pairwise_iou": (c_int, [P, c_int64, P, c_int64, P, P]),
     "coin_matcher": (c_int, [P, c_int64, c_int64, POINTER(c_float), c_int, POINTER(ctypes.c_int8), c_int,
                              P, P, P, P, P]),
+    "coin_iou_match_workspace_floats": (c_size_t, [c_int64, c_int64]),
     "coin_iou_match": (c_int, [P, c_int64, P, c_int64, POINTER(c_float), c_int, POINTER(ctypes.c_int8),
                                c_int, P, P, P, P, P]),
     "coin_relabel_roi": (c_int, [P, P, c_int64, c_int64, c_int64, P]),

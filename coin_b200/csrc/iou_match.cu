@@ -49,24 +49,37 @@ __global__ void pairwise_iou_kernel(const float4* __restrict__ b1, int64_t N, co
     }
 }
 
-// Fused IoU + column arg-max (+ optional row maxima). One thread per column.
-// n_dev / m_dev: optional device-side live counts (<= the host capacities N / M) for sync-free chaining.
-template <bool kRowMax>
-__global__ void iou_match_kernel(const float4* __restrict__ gt, int64_t N, const float4* __restrict__ boxes,
-                                 int64_t M, MatcherCfg cfg, int64_t* __restrict__ matches,
-                                 int8_t* __restrict__ labels, float* __restrict__ vals, int* __restrict__ row_max,
-                                 const int32_t* __restrict__ n_dev, const int32_t* __restrict__ m_dev) {
+// Fused IoU + column arg-max (+ optional row maxima). A CTA of 256 threads owns CW = 256 / G consecutive columns;
+// G thread groups split the GT rows (row t of a tile goes to group t % G) so that a few thousand columns still fill
+// the machine and a thread's serial chain is N / G IoUs. n_dev / m_dev: optional device-side live counts (<= the host
+// capacities N / M) for sync-free chaining.
+// Row maxima (low-quality rule): one REDUX per warp and row on the IoU bit pattern (IoU >= 0, so the unsigned order is the
+// float order), one shared-memory atomicMax per warp and row, one global atomicMax per CTA and row - and the CTA's own
+// maximum of every row is kept in cta_rmax[cta][row]: the second kernel then re-evaluates a row only in the CTAs that
+// reached the global maximum (about one CTA per row) instead of re-evaluating every pair.
+template <bool kRowMax, int G>
+__global__ void __launch_bounds__(256)
+iou_match_kernel(const float4* __restrict__ gt, int64_t N, const float4* __restrict__ boxes, int64_t M, MatcherCfg cfg,
+                 int64_t* __restrict__ matches, int8_t* __restrict__ labels, float* __restrict__ vals,
+                 unsigned* __restrict__ row_max, unsigned* __restrict__ cta_rmax, const int32_t* __restrict__ n_dev,
+                 const int32_t* __restrict__ m_dev) {
+    constexpr int CW = 256 / G;
     __shared__ float4 srow[kRowTile];
     __shared__ float sarea[kRowTile];
+    __shared__ unsigned s_rmax[kRowMax ? kRowTile : 1];
+    __shared__ float s_best[G > 1 ? 256 : 1];
+    __shared__ int s_besti[G > 1 ? 256 : 1];
+    const int64_t n_cap = N;
     if (n_dev) N = min((int64_t)max(__ldg(n_dev), 0), N);
     if (m_dev) M = min((int64_t)max(__ldg(m_dev), 0), M);
-    if ((int64_t)blockIdx.x * blockDim.x >= M) return;   // capacity launch: whole CTA beyond the live columns
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int64_t)blockIdx.x * CW >= M) return;   // capacity launch: whole CTA beyond the live columns
+    const int c = threadIdx.x % CW, g = threadIdx.x / CW;
+    const int64_t j = (int64_t)blockIdx.x * CW + c;
     const bool live = j < M;
     const float4 b = live ? __ldg(boxes + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float area_b = box_area(b);
-    float best = -1.0f;  // IoU >= 0, so row 0 always wins the first comparison (torch: first max)
-    int64_t best_i = 0;
+    float best = -1.0f;  // IoU >= 0, so the first row always wins the first comparison (torch: first max)
+    int best_i = 0;
     for (int64_t r0 = 0; r0 < N; r0 += kRowTile) {
         const int nr = (int)min((int64_t)kRowTile, N - r0);
         __syncthreads();
@@ -74,17 +87,36 @@ __global__ void iou_match_kernel(const float4* __restrict__ gt, int64_t N, const
             const float4 a = __ldg(gt + r0 + t);
             srow[t] = a;
             sarea[t] = box_area(a);
+            if (kRowMax) s_rmax[t] = 0u;
         }
         __syncthreads();
-        for (int t = 0; t < nr; ++t) {
+        for (int t = g; t < nr; t += G) {
             const float v = live ? iou_d2(srow[t], sarea[t], b, area_b) : 0.0f;
-            if (v > best) { best = v; best_i = r0 + t; }
+            if (v > best) { best = v; best_i = (int)r0 + t; }
             if (kRowMax) {
-                float m = v;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(row_max + r0 + t, __float_as_int(m));
+                const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
+                if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(&s_rmax[t], m);
             }
+        }
+        if (kRowMax) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < nr; t += blockDim.x) {
+                const unsigned m = s_rmax[t];
+                cta_rmax[(size_t)blockIdx.x * n_cap + r0 + t] = m;
+                if (m != 0u) atomicMax(row_max + r0 + t, m);
+            }
+        }
+    }
+    if (G > 1) {   // combine the row groups: larger IoU wins, equal IoU -> lower row (torch.max: first maximum)
+        __syncthreads();
+        s_best[threadIdx.x] = best;
+        s_besti[threadIdx.x] = best_i;
+        __syncthreads();
+        if (g != 0) return;
+        for (int q = 1; q < G; ++q) {
+            const float v = s_best[q * CW + c];
+            const int i = s_besti[q * CW + c];
+            if (v > best || (v == best && i < best_i)) { best = v; best_i = i; }
         }
     }
     if (!live) return;
@@ -99,32 +131,49 @@ __global__ void iou_match_kernel(const float4* __restrict__ gt, int64_t N, const
     if (vals) vals[j] = best;
 }
 
-// Low-quality rule: every column whose IoU with some GT row equals that row's maximum gets label 1.
-__global__ void iou_low_quality_kernel(const float4* __restrict__ gt, int64_t N, const float4* __restrict__ boxes,
-                                       int64_t M, const float* __restrict__ row_max, int8_t* __restrict__ labels,
-                                       const int32_t* __restrict__ n_dev, const int32_t* __restrict__ m_dev) {
-    __shared__ float4 srow[kRowTile];
-    __shared__ float sarea[kRowTile];
-    __shared__ float smax[kRowTile];
+// Low-quality rule: every column whose IoU with some GT row equals that row's maximum gets label 1. Same column
+// partition as iou_match_kernel; a CTA re-evaluates only the rows whose maximum it reached itself (cta_rmax == row_max,
+// which includes the rows that overlap nothing: their maximum 0 is reached by every column, as in detectron2).
+template <int G>
+__global__ void __launch_bounds__(256)
+iou_low_quality_kernel(const float4* __restrict__ gt, int64_t N, const float4* __restrict__ boxes, int64_t M,
+                       const unsigned* __restrict__ row_max, const unsigned* __restrict__ cta_rmax,
+                       int8_t* __restrict__ labels, const int32_t* __restrict__ n_dev, const int32_t* __restrict__ m_dev) {
+    constexpr int CW = 256 / G;
+    __shared__ int s_rows[kRowTile];
+    __shared__ int s_n;
+    __shared__ int s_hit[CW];
+    const int64_t n_cap = N;
     if (n_dev) N = min((int64_t)max(__ldg(n_dev), 0), N);
     if (m_dev) M = min((int64_t)max(__ldg(m_dev), 0), M);
-    if ((int64_t)blockIdx.x * blockDim.x >= M) return;
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int64_t)blockIdx.x * CW >= M) return;
+    const int c = threadIdx.x % CW, g = threadIdx.x / CW;
+    const int64_t j = (int64_t)blockIdx.x * CW + c;
     const bool live = j < M;
     const float4 b = live ? __ldg(boxes + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float area_b = box_area(b);
+    if (threadIdx.x < CW) s_hit[threadIdx.x] = 0;
     bool hit = false;
     for (int64_t r0 = 0; r0 < N; r0 += kRowTile) {
         const int nr = (int)min((int64_t)kRowTile, N - r0);
         __syncthreads();
-        for (int t = threadIdx.x; t < nr; t += blockDim.x) {
-            const float4 a = __ldg(gt + r0 + t);
-            srow[t] = a;
-            sarea[t] = box_area(a);
-            smax[t] = row_max[r0 + t];
-        }
+        if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
-        for (int t = 0; t < nr; ++t) hit |= (iou_d2(srow[t], sarea[t], b, area_b) == smax[t]);
+        for (int t = threadIdx.x; t < nr; t += blockDim.x)
+            if (cta_rmax[(size_t)blockIdx.x * n_cap + r0 + t] == __ldg(row_max + r0 + t)) s_rows[atomicAdd(&s_n, 1)] = (int)r0 + t;
+        __syncthreads();
+        const int n = s_n;
+        for (int q = g; q < n; q += G) {
+            const int r = s_rows[q];
+            const float4 a = __ldg(gt + r);
+            hit |= (__float_as_uint(iou_d2(a, box_area(a), b, area_b)) == __ldg(row_max + r));
+        }
+    }
+    if (G > 1) {
+        if (hit) s_hit[c] = 1;
+        __syncthreads();
+        hit = s_hit[c] != 0;
+        if (g != 0) return;
     }
     if (live && hit) labels[j] = 1;
 }
@@ -329,6 +378,16 @@ extern "C" int coin_pairwise_iou(const float* b1, int64_t N, const float* b2, in
     return check_launch("pairwise_iou_kernel");
 }
 
+// column partition of the fused kernels: G row groups x (256 / G) columns per CTA
+// (M is a capacity: the live column count may be far smaller, so only very wide problems take one row group)
+static int match_groups(int64_t M) { return M >= 65536 ? 1 : 8; }
+
+extern "C" size_t coin_iou_match_workspace_floats(int64_t N, int64_t M) {
+    if (N <= 0 || M <= 0) return 1;
+    const int64_t cw = 256 / match_groups(M);
+    return (size_t)N * (size_t)(1 + ceil_div(M, cw));
+}
+
 static int iou_match_impl(const float* gt, int64_t N, const float* boxes, int64_t M,
                           const float* thresholds_host, int nthr, const int8_t* labels_host,
                           int allow_low_quality, int64_t* matches, int8_t* match_labels,
@@ -340,28 +399,39 @@ static int iou_match_impl(const float* gt, int64_t N, const float* boxes, int64_
     if (M == 0) return COIN_OK;
     COIN_REQUIRE(matches && match_labels, "iou_match: null output");
     cudaStream_t s = as_stream(stream);
-    const unsigned blocks = (unsigned)ceil_div(M, 128);
     if (N == 0) {  // Matcher's empty-matrix rule
         empty_matcher_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, s>>>(M, cfg.labels[0], matches, match_labels, matched_vals);
         return check_launch("empty_matcher_kernel");
     }
     COIN_REQUIRE(gt && boxes && aligned16(gt) && aligned16(boxes), "iou_match: null or misaligned boxes");
+    const int G = match_groups(M);
+    const unsigned blocks = (unsigned)ceil_div(M, 256 / G);
+    const float4* g4 = reinterpret_cast<const float4*>(gt);
+    const float4* b4 = reinterpret_cast<const float4*>(boxes);
     if (allow_low_quality) {
         COIN_REQUIRE(row_max_ws, "iou_match: row_max_ws is required with allow_low_quality");
-        cudaMemsetAsync(row_max_ws, 0, N * sizeof(float), s);
-        iou_match_kernel<true><<<blocks, 128, 0, s>>>(reinterpret_cast<const float4*>(gt), N,
-                                                      reinterpret_cast<const float4*>(boxes), M, cfg, matches,
-                                                      match_labels, matched_vals, reinterpret_cast<int*>(row_max_ws),
-                                                      n_dev, m_dev);
-        if (int rc = check_launch("iou_match_kernel")) return rc;
-        iou_low_quality_kernel<<<blocks, 128, 0, s>>>(reinterpret_cast<const float4*>(gt), N,
-                                                      reinterpret_cast<const float4*>(boxes), M, row_max_ws, match_labels,
-                                                      n_dev, m_dev);
+        unsigned* row_max = reinterpret_cast<unsigned*>(row_max_ws);
+        unsigned* cta_rmax = row_max + N;
+        cudaMemsetAsync(row_max, 0, N * sizeof(float), s);
+        if (G == 1) {
+            iou_match_kernel<true, 1><<<blocks, 256, 0, s>>>(g4, N, b4, M, cfg, matches, match_labels, matched_vals, row_max,
+                                                             cta_rmax, n_dev, m_dev);
+            if (int rc = check_launch("iou_match_kernel")) return rc;
+            iou_low_quality_kernel<1><<<blocks, 256, 0, s>>>(g4, N, b4, M, row_max, cta_rmax, match_labels, n_dev, m_dev);
+        } else {
+            iou_match_kernel<true, 8><<<blocks, 256, 0, s>>>(g4, N, b4, M, cfg, matches, match_labels, matched_vals, row_max,
+                                                             cta_rmax, n_dev, m_dev);
+            if (int rc = check_launch("iou_match_kernel")) return rc;
+            iou_low_quality_kernel<8><<<blocks, 256, 0, s>>>(g4, N, b4, M, row_max, cta_rmax, match_labels, n_dev, m_dev);
+        }
         return check_launch("iou_low_quality_kernel");
     }
-    iou_match_kernel<false><<<blocks, 128, 0, s>>>(reinterpret_cast<const float4*>(gt), N,
-                                                   reinterpret_cast<const float4*>(boxes), M, cfg, matches,
-                                                   match_labels, matched_vals, nullptr, n_dev, m_dev);
+    if (G == 1)
+        iou_match_kernel<false, 1><<<blocks, 256, 0, s>>>(g4, N, b4, M, cfg, matches, match_labels, matched_vals, nullptr,
+                                                          nullptr, n_dev, m_dev);
+    else
+        iou_match_kernel<false, 8><<<blocks, 256, 0, s>>>(g4, N, b4, M, cfg, matches, match_labels, matched_vals, nullptr,
+                                                          nullptr, n_dev, m_dev);
     return check_launch("iou_match_kernel");
 }
 

@@ -104,6 +104,39 @@ __device__ int compact_append(int L, Pred pred, Map map, int32_t* out, int count
     return res;
 }
 
+// list(set(range(n)) - other), warp-cooperative; keep(i) = "i is not in other" (so len(other) = n - #kept). The common
+// case (the survivors sit in their own slots of the CPython table: ascending) is a ballot compaction; the rare remainder
+// (a few large survivors in a small table) is replayed by lane 0. Every lane must call; returns the count.
+template <class Keep>
+__device__ int difference_order_warp(int n, Keep keep, int32_t* out, int16_t* pool_base, int* pool_ctr) {
+    const int lane = threadIdx.x & 31;
+    int m = 0, mx = -1;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const unsigned b = __ballot_sync(0xffffffffu, i < n && keep(i));
+        m += __popc(b);
+        if (b) mx = base + 31 - __clz(b);
+    }
+    const int other_size = n - m;
+    if (((n >> 2) > other_size) || mx < pyset::table_size_after_adds(m)) {
+        int c = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool p = i < n && keep(i);
+            const unsigned b = __ballot_sync(0xffffffffu, p);
+            if (p) out[c + __popc(b & ((1u << lane) - 1u))] = i;
+            c += __popc(b);
+        }
+        return c;
+    }
+    int c = 0;
+    if (lane == 0) {
+        pyset::Pool pool{pool_base, kPoolDiff, pool_ctr, pool_ctr + 1};
+        c = pyset::difference_order(n, keep, other_size, out, pool);
+    }
+    return __shfl_sync(0xffffffffu, c, 0);
+}
+
 // util.py:434-457 grouping, one pass per row: rows sharing the fp32 sum of their coordinates form a candidate group;
 // it is a true duplicate group when the summed difference to its first row is exactly zero (the reference's test).
 // After the call: single[r] = 1 if row r is not part of a true group; isgrp[r] = 1 on the leader (lowest row) of a true
@@ -203,7 +236,7 @@ __device__ __forceinline__ void abc_use_shared(AbcArgs& b, unsigned char* sm, bo
 
 __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a_in) {
     extern __shared__ __align__(16) unsigned char abc_smem[];
-    __shared__ int s_tmp, s_flag[6], s_status;
+    __shared__ int s_tmp, s_flag[6], s_status, s_pc[6];   // s_pc: (used, overflow) of the three pyset pools
     AbcArgs a = a_in;   // mutable copy: scratch pointers may be redirected to shared memory
     const int nc = a.nc, nd = a.nd_dev ? min(max(*a.nd_dev, 0), a.nd) : a.nd;
     const bool small = a.use_smem && nc <= kAbcN && nd <= kAbcN;
@@ -222,6 +255,7 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a_in) {
     for (int i = threadIdx.x; i < nc; i += blockDim.x) a.oncls[i] = (int32_t)a.oncls64[i];
     for (int j = threadIdx.x; j < nd; j += blockDim.x) a.offcls[j] = (int32_t)a.offcls64[j];
     if (threadIdx.x == 0) s_status = 0;
+    if (threadIdx.x < 6) s_pc[threadIdx.x] = 0;
     __syncthreads();
     int status = 0;
     // In the empty-side branches both members of a pair come from the same detection set.
@@ -373,11 +407,17 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a_in) {
         }
         __syncthreads();
         P = min(P, a.cap);
-        // ---- E. three serial pieces on three warps:
-        //   warp 0: append the group pairs / unmatched groups (order of the groups), then list(set(range(nc)) - used)
-        //   warp 1: list(set(range(nu)) - matched) for the unique CLIP-detector boxes (trainer.py:369)
-        //   warp 2: filter_result / find_same over the 0.95 graph (util.py:459-482), in CPython set order
-        if (threadIdx.x == 0) {
+        // ---- E. order-carrying pieces (trainer.py:369,391; util.py:459-482), spread over the warps:
+        //   threads 0..nc-1 classify the nodes of the 0.95 graph and build the CPython sets that matter (pyset.cuh);
+        //   one thread of an otherwise idle warp appends the group pairs / unmatched groups, in group order
+        auto adjw = [&](int i, int w) { return a.abits[i * Wc + w]; };
+        pyset::Pool cpool{a.pool_cl, kPoolCl, &s_pc[0], &s_pc[1]};
+        for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+            const int kind = pyset::classify_node(i, Wc, adjw);
+            a.label[i] = kind;
+            if (kind == pyset::kPairLeader || kind == pyset::kActive) a.sets[i] = pyset::build_row_set(i, Wc, adjw, cpool);
+        }
+        if (threadIdx.x == blockDim.x - 32) {
             int p = P, extra = 0;
             for (int g = 0; g < ng; ++g) {
                 if (a.g_i0[g] >= 0) {
@@ -390,27 +430,50 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a_in) {
             }
             s_flag[0] = p;
             s_flag[1] = extra;
-            int used = 0;
-            for (int i = 0; i < nc; ++i) used += a.on_used[i] != 0;
-            pyset::Pool pool{a.pool_d0, kPoolDiff, 0, 0};
-            s_flag[3] = pyset::difference_order(nc, [&](int i) { return a.on_used[i] == 0; }, used, a.ord_on, pool);
-        } else if (threadIdx.x == 32) {
-            int matched = 0;
-            for (int w = 0; w < Wd; ++w) matched += __popc(a.matched[w] & a.uniqmask[w]);
-            pyset::Pool pool{a.pool_d1, kPoolDiff, 0, 0};
-            s_flag[2] = pyset::difference_order(
-                nu, [&](int u) { const int j = a.uniq[u]; return ((a.matched[j >> 5] >> (j & 31)) & 1u) == 0u; }, matched,
-                a.ord_off, pool);
-        } else if (threadIdx.x == 64) {
-            pyset::Pool pool{a.pool_cl, kPoolCl, 0, 0};
-            s_flag[4] = pyset::filter_clusters(
-                nc, [&](int i, int j) { return ((a.abits[i * Wc + (j >> 5)] >> (j & 31)) & 1u) != 0u; }, a.sets, a.frames, pool,
-                a.clusters, kAbcClusters);
         }
         __syncthreads();
+        //   warp 0: list(set(range(nc)) - used cloud boxes); warp 1: list(set(range(nu)) - matched unique boxes);
+        //   warp 2: the nodes that are neither isolated nor a plain pair are replayed serially (rare: chains, triples)
+        if (warp == 0) {
+            const int c = difference_order_warp(nc, [&](int i) { return a.on_used[i] == 0; }, a.ord_on, a.pool_d0, &s_pc[2]);
+            if (lane == 0) s_flag[3] = c;
+        } else if (warp == 1) {
+            const int c = difference_order_warp(
+                nu, [&](int u) { const int j = a.uniq[u]; return ((a.matched[j >> 5] >> (j & 31)) & 1u) == 0u; }, a.ord_off,
+                a.pool_d1, &s_pc[4]);
+            if (lane == 0) s_flag[2] = c;
+        } else if (warp == 2) {
+            int16_t* act = reinterpret_cast<int16_t*>(a.rowoff);      // rowoff is free by now
+            int na = 0;
+            for (int base = 0; base < nc; base += 32) {
+                const int i = base + lane;
+                const bool p = i < nc && a.label[i] == pyset::kActive;
+                const unsigned b = __ballot_sync(0xffffffffu, p);
+                if (p) act[na + __popc(b & ((1u << lane) - 1u))] = (int16_t)i;
+                na += __popc(b);
+            }
+            __syncwarp();
+            int rc = 0;
+            if (lane == 0 && na > 0 && !s_pc[1]) rc = pyset::filter_clusters_built(na, act, a.sets, a.frames, cpool);
+            if (lane == 0) s_flag[4] = (rc < 0 || s_pc[1]) ? -1 : 0;
+        }
+        __syncthreads();
+        // clusters in ascending order of their owner node: pair leaders and the replayed nodes that kept a set of len > 1
+        int ncl = s_flag[4];
+        if (ncl == 0) {
+            ncl = compact_append(nc,
+                                 [&](int i) {
+                                     const int kind = a.label[i];
+                                     return kind == pyset::kPairLeader ||
+                                            (kind == pyset::kActive && a.sets[i].off >= 0 && a.sets[i].used != 1);
+                                 },
+                                 [&](int i) { return i; }, a.rowcnt, 0, nc, &s_tmp);
+            if (ncl > kAbcClusters) ncl = -1;
+            for (int k = threadIdx.x; k < ncl; k += blockDim.x) a.clusters[k] = a.sets[a.rowcnt[k]];
+            __syncthreads();
+        }
         P = s_flag[0];
         const int n_unmatched_groups = s_flag[1], n_off_only = s_flag[2], n_on_only = s_flag[3];
-        int ncl = s_flag[4];
         // private rows: unmatched unique CLIP-detector boxes (set order), one box per unmatched group (group order), ...
         for (int r = threadIdx.x; r < n_off_only; r += blockDim.x) { a.c_off[r] = a.uniq[a.ord_off[r]]; a.c_on[r] = -1; }
         for (int g = threadIdx.x; g < ng; g += blockDim.x)

@@ -1,4 +1,16 @@
-// nms.cu -- greedy NMS / batched NMS as a sort + 64x64 bit-mask + single-CTA sweep.
+// nms.cu -- greedy NMS / batched NMS as a sort + 64x64 bit-mask + single-CTA sweep, with early exit on max_keep.
+//
+// Pipeline (all launches fixed by the host-known capacity; live counts and the early-exit flag stay on the device):
+//   sort      n <= 4096: one CTA, bitonic in shared memory. n <= 65536: every 4096-box chunk is sorted by its own CTA,
+//             then ONE kernel ranks each key across the other chunks by binary search (keys are unique: score, index) and
+//             gathers the boxes straight into sorted order - 2 launches instead of CUB's ~14. Above that: CUB radix sort.
+//   part 1    mask + sweep over the first R1 = max(1024, 2*max_keep rounded up to 256) sorted boxes only. Callers that
+//             ask for keep[:k] (detections: k = 100; RPN proposals: k = 2000; d2's find_top_rpn_proposals) are usually
+//             satisfied here: the mask shrinks from n^2/2 to R1^2/2 pairs and the sweep from n/64 to R1/64 tiles.
+//   part 2    only if part 1 neither filled max_keep nor covered all boxes (device flag): the kept rows of part 1 are
+//             OR-ed into the removed vector of the remaining columns without storing their mask words, the remaining rows
+//             get their upper-triangular mask, and the sweep continues where part 1 stopped. Its kernels return at once
+//             when the flag says done.
 //
 // Replaces torchvision::nms / torchvision.ops.boxes.batched_nms behind detectron2.layers.batched_nms,
 // reached from coin/modeling/roi_heads/fast_rcnn.py:164 (final detections, per class),
@@ -11,6 +23,8 @@
 // nearest float, which is equivalent for a strict '>'), keep list in descending-score order.
 // batched variants: TRICK adds idx*(max+1) to the coordinates in fp32 exactly as torchvision does
 // (so near-threshold roundings match), VANILLA restricts suppression to equal classes.
+#include <climits>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -27,6 +41,31 @@ __device__ __forceinline__ uint64_t sort_key(float s, uint32_t idx) {
     u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;        // ascending-orderable
     return ((uint64_t)(~u) << 32) | idx;
 }
+
+// In-place ascending bitonic sort of npow (a power of two) 64-bit keys in shared memory by a CTA of NT threads.
+// Every thread owns a compare-exchange in every stage (pair index t -> elements i = t with a zero inserted at bit
+// log2(j), and i | j). Stages with j <= 32 stay inside an aligned 64-key window that the same warp owns in every such
+// stage, so they are separated by __syncwarp only; the CTA barrier is paid where a stage crosses windows (j >= 64).
+template <int NT>
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* __restrict__ k, int npow) {
+    const int half = npow >> 1;
+    for (int kk = 2; kk <= npow; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < half; t += NT) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const uint64_t a = k[i], b = k[p];
+                const bool up = (i & kk) == 0;
+                if ((a > b) == up) { k[i] = b; k[p] = a; }
+            }
+            const int next_j = j > 1 ? (j >> 1) : kk;     // first stage of the next merge level has j = kk
+            if (j > 32 || next_j > 32) __syncthreads(); else __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+constexpr int kSortThreads = 512;
 
 // meta[0] = live box count n (<= n_cap), meta[1] = resolved strategy. Every kernel of the pipeline is
 // launched for the host-known capacity n_cap and reads the live n from `meta`, so a caller can chain
@@ -102,7 +141,7 @@ __global__ void gather_sorted_kernel(const uint32_t* __restrict__ sorted_idx, co
 }
 
 // Single-CTA path for n <= kSmallSort: key generation, bitonic sort, max-reduce and gather fused.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSortThreads)
 small_sort_gather_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes,
                          const int64_t* __restrict__ idxs, int n_cap, const int32_t* __restrict__ n_dev,
                          int strategy_in, float4* __restrict__ sboxes, int32_t* __restrict__ scls,
@@ -128,19 +167,7 @@ small_sort_gather_kernel(const float* __restrict__ scores, const float4* __restr
         if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
     }
     __syncthreads();
-    for (int k = 2; k <= npow; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < npow; i += blockDim.x) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const uint64_t a = skeys[i], b = skeys[p];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { skeys[i] = b; skeys[p] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    bitonic_sort_smem<kSortThreads>(skeys, npow);
     float mx = 0.0f;
     if (strategy == COIN_NMS_TRICK) {
         mx = smax[0];
@@ -160,23 +187,105 @@ small_sort_gather_kernel(const float* __restrict__ scores, const float4* __restr
     }
 }
 
+// ---- mid-size sort: 4096-box chunks sorted independently, then ranked against each other ---------------------
+constexpr int kChunk = 4096;
+constexpr int kMaxChunks = 16;   // n <= 65536 takes this path
+
+__global__ void __launch_bounds__(kSortThreads)
+chunk_sort_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes, int n_cap,
+                  const int32_t* __restrict__ n_dev, int strategy_in, uint64_t* __restrict__ ckeys,
+                  float* __restrict__ max_coord, int32_t* __restrict__ meta) {
+    extern __shared__ uint64_t skeys[];
+    const int n = resolve_n(n_cap, n_dev);
+    const int strategy = resolve_strategy(strategy_in, n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { meta[0] = n; meta[1] = strategy; }
+    const int base = blockIdx.x * kChunk;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < kChunk; i += blockDim.x) {
+        const int g = base + i;
+        skeys[i] = g < n ? sort_key(__ldg(scores + g), (uint32_t)g) : ~0ull;
+        if (strategy == COIN_NMS_TRICK && g < n) {
+            const float4 b = __ldg(boxes + g);
+            m = fmaxf(fmaxf(m, fmaxf(b.x, b.y)), fmaxf(b.z, b.w));
+        }
+    }
+    if (strategy == COIN_NMS_TRICK) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) {
+            int bits = __float_as_int(m);
+            bits = bits >= 0 ? bits : bits ^ 0x7fffffff;
+            atomicMax(reinterpret_cast<int*>(max_coord), bits);
+        }
+    }
+    __syncthreads();
+    if (base < n) {     // chunks beyond the live boxes hold only padding; a partly filled chunk sorts its live prefix
+        int npow = 2;
+        while (npow < min(n - base, kChunk)) npow <<= 1;
+        bitonic_sort_smem<kSortThreads>(skeys, npow);
+    }
+    for (int i = threadIdx.x; i < kChunk; i += blockDim.x) ckeys[base + i] = skeys[i];
+}
+
+// rank of a key = its position in its own chunk + the number of smaller keys in every other chunk (binary search;
+// keys are unique because they carry the box index). The gather of gather_sorted_kernel is fused in.
+__global__ void merge_rank_gather_kernel(const uint64_t* __restrict__ ckeys, int nchunks, const float4* __restrict__ boxes,
+                                         const int64_t* __restrict__ idxs, const int32_t* __restrict__ meta,
+                                         const float* __restrict__ max_coord, float4* __restrict__ sboxes,
+                                         int32_t* __restrict__ scls, int32_t* __restrict__ order) {
+    const int n = meta[0], strategy = meta[1];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nchunks * kChunk) return;
+    const uint64_t key = ckeys[e];
+    if (key == ~0ull) return;                       // padding
+    const int g = e / kChunk;
+    int rank = e - g * kChunk;
+    const int live_chunks = (n + kChunk - 1) / kChunk;
+    for (int h = 0; h < live_chunks; ++h) {
+        if (h == g) continue;
+        const uint64_t* c = ckeys + (size_t)h * kChunk;
+        int lo = 0, hi = kChunk;                    // first position with c[pos] >= key
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(c + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+    }
+    const uint32_t src = (uint32_t)(key & 0xffffffffu);
+    float4 b = __ldg(boxes + src);
+    const int64_t cls = idxs ? __ldg(idxs + src) : 0;
+    if (strategy == COIN_NMS_TRICK) {
+        const float off = (float)cls * (decode_max(max_coord) + 1.0f);
+        b.x += off; b.y += off; b.z += off; b.w += off;
+    }
+    sboxes[rank] = b;
+    scls[rank] = (int32_t)cls;
+    order[rank] = (int32_t)src;
+}
+
 // 64 x (4*64) tile of the upper-triangular suppression mask per CTA; row-major [n][colblocks] so
 // that the sweep reads whole rows coalesced. Bits are set only for j > i. For the diagonal tiles the
 // transposed word is emitted as well: lower[i] = { j < i in the same 64-row tile : IoU(j, i) > thr }
 // (IoU is bitwise symmetric), which lets the sweep resolve a tile by fixed-point iteration.
 // Pairs with an empty intersection are rejected before the division (their IoU is 0 or NaN, never > thr
 // for thr >= 0); FAST = false keeps the plain evaluation for negative thresholds.
+// Two-part operation (early exit on max_keep): part 1 is launched with n_limit = R1 and t1 = 0; part 2 with ct0 = t1 =
+// R1 / 64 and n_limit = INT_MAX: it returns at once when state[1] (done) is set; rows of part 1 (row tile < t1) that the
+// first sweep KEPT (keptbits) OR their words into removed_g[column tile] instead of storing them.
 template <bool FAST>
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ scls,
                 const int32_t* __restrict__ meta, int colblocks, float thr, uint64_t* __restrict__ mask,
-                uint64_t* __restrict__ lower, uint64_t* __restrict__ rowflags, int fw) {
-    const int n = meta[0];
+                uint64_t* __restrict__ lower, uint64_t* __restrict__ rowflags, int fw, int ct0, int n_limit,
+                const int32_t* __restrict__ state, const uint64_t* __restrict__ keptbits,
+                uint64_t* __restrict__ removed_g, int t1) {
+    if (t1 > 0 && state[1]) return;            // part 1 already delivered max_keep boxes (or covered every box)
+    const int n = min(meta[0], n_limit);
     const bool same_class_only = meta[1] == COIN_NMS_VANILLA;
     const int rt = blockIdx.y;                 // row tile
-    const int ct = blockIdx.x * 4 + threadIdx.y;  // col tile of this thread row
-    if (blockIdx.x * 4 + 3 < rt) return;       // whole CTA below the diagonal
-    if (rt * 64 >= n || blockIdx.x * 256 >= n) return;  // beyond the live boxes (capacity launch)
+    const int ct = ct0 + blockIdx.x * 4 + threadIdx.y;  // col tile of this thread row
+    if (ct0 + blockIdx.x * 4 + 3 < rt) return;       // whole CTA below the diagonal
+    if (rt * 64 >= n || (ct0 + blockIdx.x * 4) * 64 >= n) return;  // beyond the live boxes (capacity launch)
     __shared__ float4 cb[4][64];
     __shared__ float ca[4][64];
     __shared__ int32_t cc[4][64];
@@ -193,6 +302,8 @@ nms_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ s
     __syncthreads();
     const int i = rt * 64 + r;
     if (i >= n || ct >= colblocks || ct < rt) return;
+    const bool part1_row = rt < t1;
+    if (part1_row && !((keptbits[rt] >> r) & 1ull)) return;    // suppressed in part 1: suppresses nobody
     const float4 a = __ldg(sboxes + i);
     const float area_a = box_area(a);
     const int32_t cls_a = __ldg(scls + i);
@@ -216,6 +327,10 @@ nms_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ s
             if (!diag || j > r) word |= 1ull << j; else low |= 1ull << j;
         }
     }
+    if (part1_row) {
+        if (word) atomicOr(reinterpret_cast<unsigned long long*>(removed_g + ct), (unsigned long long)word);
+        return;
+    }
     mask[(size_t)i * colblocks + ct] = word;
     // rowflags[i]: bitmap of the column blocks with a non-zero word (zero-filled by the host side). Overlap is
     // sparse, so the sweep reads this bitmap and then only the few non-zero words of a kept row.
@@ -235,30 +350,35 @@ __global__ void __launch_bounds__(256)
 nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__ lower,
                  const uint64_t* __restrict__ rowflags, int fw, const int32_t* __restrict__ order,
                  const int32_t* __restrict__ meta, int stride, int64_t max_keep, int64_t* __restrict__ keep,
-                 int32_t* __restrict__ nkeep) {
+                 int32_t* __restrict__ nkeep, int t_begin, int n_limit, int32_t* __restrict__ state,
+                 uint64_t* __restrict__ keptbits, const uint64_t* __restrict__ removed_g) {
+    // two-part operation: part 1 = (t_begin 0, n_limit R1, state set): sweeps the first R1 boxes, records the kept rows
+    // of every tile and whether the job is done; part 2 = (t_begin R1/64, n_limit INT_MAX): continues unless done.
     extern __shared__ uint64_t removed[];  // colblocks words
-    const int n = meta[0];
+    if (t_begin > 0 && state[1]) return;
+    const int n_all = meta[0];
+    const int n = min(n_all, n_limit);
     const int colblocks = (n + 63) >> 6;   // live column blocks; `stride` is the row pitch of `mask`
     __shared__ uint64_t s_kept[2];
     __shared__ int s_krow[2][64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int c = tid; c < colblocks; c += blockDim.x) removed[c] = 0;
+    for (int c = tid; c < colblocks; c += blockDim.x) removed[c] = (t_begin > 0 && c >= t_begin) ? removed_g[c] : 0;
     if (tid < 2) s_kept[tid] = 0;
     __syncthreads();
-    int64_t nk = 0;
-    const int64_t limit = max_keep >= 0 ? max_keep : (int64_t)n;
+    int64_t nk = t_begin > 0 ? (int64_t)state[0] : 0;
+    const int64_t limit = max_keep >= 0 ? max_keep : (int64_t)n_all;
     const bool fast_flags = 64 * fw <= (int)blockDim.x - 32;   // one helper thread per (row, flag word) of a tile
     uint64_t myflag = 0;                    // helpers: the flag word loaded one iteration earlier
     uint64_t pref0 = 0, pref1 = 0;          // warp 0: mask[(t-1)*64 + lane (+32)][t]
     uint64_t low0 = 0, low1 = 0;            // warp 0: lower words of tile t
     if (warp == 0) {
-        if (lane < n) low0 = lower[lane];
-        if (lane + 32 < n) low1 = lower[lane + 32];
+        if (t_begin * 64 + lane < n) low0 = lower[t_begin * 64 + lane];
+        if (t_begin * 64 + lane + 32 < n) low1 = lower[t_begin * 64 + lane + 32];
     }
-    for (int t = 0; t < colblocks && nk < limit; ++t) {
+    for (int t = t_begin; t < colblocks && nk < limit; ++t) {
         const int buf = t & 1;
         if (warp == 0) {
-            const uint64_t prev = t > 0 ? s_kept[buf ^ 1] : 0ull;
+            const uint64_t prev = t > t_begin ? s_kept[buf ^ 1] : 0ull;
             uint64_t v = ((prev >> lane) & 1ull ? pref0 : 0ull) | ((prev >> (lane + 32)) & 1ull ? pref1 : 0ull);
             const uint32_t vlo = __reduce_or_sync(0xffffffffu, (uint32_t)v);
             const uint32_t vhi = __reduce_or_sync(0xffffffffu, (uint32_t)(v >> 32));
@@ -308,7 +428,7 @@ nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__
                 const int r = t * 64 + h / fw;
                 if (r < n) nflag = rowflags[(size_t)r * fw + h % fw];
             }
-            if (t > 0 && h < 64 * fw) {
+            if (t > t_begin && h < 64 * fw) {
                 const uint64_t prev = s_kept[buf ^ 1];
                 const int rr = h / fw, f = h - rr * fw;
                 if ((prev >> rr) & 1ull) {
@@ -333,7 +453,7 @@ nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__
                 }
             }
             myflag = nflag;
-        } else if (t > 0) {
+        } else if (t > t_begin) {
             // helpers, generic: tile t-1's kept rows -> removed[c] for c >= t+1 (column t was warp 0's prefetch)
             const uint64_t prev = s_kept[buf ^ 1];
             const int np = __popcll(prev);
@@ -356,11 +476,18 @@ nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__
         }
         __syncthreads();
         nk += __popcll(s_kept[buf]);
+        if (tid == 0 && state && t_begin == 0) keptbits[t] = s_kept[buf];
     }
-    if (tid == 0) *nkeep = (int32_t)nk;
+    if (tid == 0) {
+        const bool done = !state || t_begin > 0 || nk >= limit || n_all <= n_limit;
+        if (state) { state[0] = (int32_t)nk; state[1] = done ? 1 : 0; }
+        if (done) *nkeep = (int32_t)nk;
+    }
 }
 
 struct NmsWs {
+    uint64_t *ckeys, *keptbits, *removed_g;
+    int32_t* state;
     uint32_t *keys, *keys_alt, *vals, *vals_alt;
     void* cub_tmp;
     size_t cub_bytes;
@@ -395,7 +522,13 @@ static NmsWs carve_nms(void* ws, int64_t n) {
     w.keys = w.keys_alt = w.vals = w.vals_alt = nullptr;
     w.cub_tmp = nullptr;
     w.cub_bytes = 0;
-    if (n > kSmallSort) {
+    w.ckeys = nullptr;
+    w.state = c.take<int32_t>(64);
+    w.keptbits = c.take<uint64_t>((size_t)colblocks);
+    w.removed_g = c.take<uint64_t>((size_t)colblocks);
+    if (n > kSmallSort && n <= (int64_t)kChunk * kMaxChunks) {
+        w.ckeys = c.take<uint64_t>((size_t)ceil_div(n, kChunk) * kChunk);
+    } else if (n > kSmallSort) {
         w.keys = c.take<uint32_t>((size_t)n);
         w.keys_alt = c.take<uint32_t>((size_t)n);
         w.vals = c.take<uint32_t>((size_t)n);
@@ -431,9 +564,18 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
     if (n <= kSmallSort) {
         int npow = 1;
         while (npow < n) npow <<= 1;
-        small_sort_gather_kernel<<<1, 256, npow * sizeof(uint64_t), s>>>(scores, b4, idxs, n, n_dev, strategy, w.sboxes,
+        small_sort_gather_kernel<<<1, kSortThreads, npow * sizeof(uint64_t), s>>>(scores, b4, idxs, n, n_dev, strategy, w.sboxes,
                                                                           w.scls, w.order, w.meta);
         if (int rc = check_launch("small_sort_gather_kernel")) return rc;
+    } else if (w.ckeys) {
+        const int nchunks = (int)ceil_div(n, kChunk);
+        cudaMemsetAsync(w.max_coord, 0x80, sizeof(int), s);  // 0x80808080 decodes to ~ -3.4e38
+        chunk_sort_kernel<<<nchunks, kSortThreads, kChunk * sizeof(uint64_t), s>>>(scores, b4, n, n_dev, strategy, w.ckeys,
+                                                                           w.max_coord, w.meta);
+        if (int rc = check_launch("chunk_sort_kernel")) return rc;
+        merge_rank_gather_kernel<<<(unsigned)ceil_div((int64_t)nchunks * kChunk, 256), 256, 0, s>>>(
+            w.ckeys, nchunks, b4, idxs, w.meta, w.max_coord, w.sboxes, w.scls, w.order);
+        if (int rc = check_launch("merge_rank_gather_kernel")) return rc;
     } else {
         make_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(scores, n, n_dev, strategy, w.keys, w.vals, w.meta);
         if (int rc = check_launch("make_keys_kernel")) return rc;
@@ -451,21 +593,40 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
                                                                         w.sboxes, w.scls, w.order);
         if (int rc = check_launch("gather_sorted_kernel")) return rc;
     }
-    dim3 grid((unsigned)ceil_div(colblocks, 4), (unsigned)colblocks), block(64, 4);
     const float thr_f = round_down_to_float(thr);
     const int fw = (int)ceil_div(colblocks, 64);
     cudaMemsetAsync(w.rowflags, 0, (size_t)n * fw * sizeof(uint64_t), s);
-    if (thr_f >= 0.0f)
-        nms_mask_kernel<true><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower,
-                                                     w.rowflags, fw);
-    else
-        nms_mask_kernel<false><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower,
-                                                      w.rowflags, fw);
-    if (int rc = check_launch("nms_mask_kernel")) return rc;
     const size_t smem = (size_t)colblocks * sizeof(uint64_t);
     if (smem > 48 * 1024) cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nms_sweep_kernel<<<1, 256, smem, s>>>(w.mask, w.lower, w.rowflags, fw, w.order, w.meta, colblocks, max_keep, keep,
-                                          nkeep);
+    dim3 block(64, 4);
+    auto launch_mask = [&](dim3 grid, int ct0, int n_limit, int t1) {
+        if (thr_f >= 0.0f)
+            nms_mask_kernel<true><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower, w.rowflags,
+                                                         fw, ct0, n_limit, w.state, w.keptbits, w.removed_g, t1);
+        else
+            nms_mask_kernel<false><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.meta, colblocks, thr_f, w.mask, w.lower, w.rowflags,
+                                                          fw, ct0, n_limit, w.state, w.keptbits, w.removed_g, t1);
+        return check_launch("nms_mask_kernel");
+    };
+    // part 1 covers the first R1 sorted boxes; with no max_keep (or few boxes) it is the whole job
+    int64_t r1 = n;
+    if (max_keep >= 0) r1 = std::min<int64_t>(n, std::max<int64_t>(1024, (2 * max_keep + 255) / 256 * 256));
+    if (option("COIN_NMS_TWO_PART", 1) == 0) r1 = n;
+    const int t1 = (int)(r1 / 64);
+    if (r1 >= n) {
+        if (int rc = launch_mask(dim3((unsigned)ceil_div(colblocks, 4), (unsigned)colblocks), 0, INT_MAX, 0)) return rc;
+        nms_sweep_kernel<<<1, 256, smem, s>>>(w.mask, w.lower, w.rowflags, fw, w.order, w.meta, colblocks, max_keep, keep, nkeep,
+                                              0, INT_MAX, nullptr, nullptr, nullptr);
+        return check_launch("nms_sweep_kernel");
+    }
+    cudaMemsetAsync(w.removed_g, 0, (size_t)colblocks * sizeof(uint64_t), s);
+    if (int rc = launch_mask(dim3((unsigned)ceil_div(t1, 4), (unsigned)t1), 0, (int)r1, 0)) return rc;
+    nms_sweep_kernel<<<1, 256, smem, s>>>(w.mask, w.lower, w.rowflags, fw, w.order, w.meta, colblocks, max_keep, keep, nkeep, 0,
+                                          (int)r1, w.state, w.keptbits, w.removed_g);
+    if (int rc = check_launch("nms_sweep_kernel")) return rc;
+    if (int rc = launch_mask(dim3((unsigned)ceil_div(colblocks - t1, 4), (unsigned)colblocks), t1, INT_MAX, t1)) return rc;
+    nms_sweep_kernel<<<1, 256, smem, s>>>(w.mask, w.lower, w.rowflags, fw, w.order, w.meta, colblocks, max_keep, keep, nkeep, t1,
+                                          INT_MAX, w.state, w.keptbits, w.removed_g);
     return check_launch("nms_sweep_kernel");
 }
 

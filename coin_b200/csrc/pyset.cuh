@@ -29,10 +29,11 @@ constexpr int kLinearProbes = 9;
 constexpr int kPerturbShift = 5;
 constexpr int16_t kEmpty = -1;
 
-struct Pool {
+struct Pool {            // bump allocator; `used` / `overflow` live outside so that several threads can share one pool
     int16_t* base;
-    int cap, used;
-    int overflow;
+    int cap;
+    int* used;
+    int* overflow;
 };
 
 struct Set {        // tab == nullptr <=> no storage (only legal for used == 0)
@@ -41,9 +42,14 @@ struct Set {        // tab == nullptr <=> no storage (only legal for used == 0)
 };
 
 COIN_PYSET_HD int16_t* pool_alloc(Pool& p, int slots) {
-    if (p.used + slots > p.cap) { p.overflow = 1; return nullptr; }
-    int16_t* r = p.base + p.used;
-    p.used += slots;
+#if defined(__CUDA_ARCH__)
+    const int off = atomicAdd(p.used, slots);
+#else
+    const int off = *p.used;
+    *p.used += slots;
+#endif
+    if (off + slots > p.cap) { *p.overflow = 1; return nullptr; }
+    int16_t* r = p.base + off;
     for (int i = 0; i < slots; ++i) r[i] = kEmpty;
     return r;
 }
@@ -52,7 +58,7 @@ COIN_PYSET_HD Set make_empty(Pool& p) {
     Set s;
     s.tab = pool_alloc(p, 8);   // the object's smalltable
     s.mask = 7; s.fill = 0; s.used = 0;
-    return s;
+    return s;                   // tab == nullptr on overflow: every caller checks *p.overflow before touching it
 }
 
 // set_insert_clean: the key is known to be absent and the table has no dummies
@@ -83,7 +89,7 @@ COIN_PYSET_HD void resize(Set& s, int minused, Pool& p) {
 
 // set_add_entry (no dummies can be present in the sets this file builds)
 COIN_PYSET_HD void add(Set& s, int key, Pool& p) {
-    if (p.overflow) return;
+    if ((*p.overflow)) return;
     uint32_t perturb = (uint32_t)key, i = (uint32_t)key & (uint32_t)s.mask;
     uint32_t e;
     while (true) {
@@ -107,9 +113,9 @@ COIN_PYSET_HD void add(Set& s, int key, Pool& p) {
 
 // set_merge(so, other): so |= other
 COIN_PYSET_HD void merge(Set& so, const Set& other, Pool& p) {
-    if (p.overflow || other.used == 0) return;
+    if ((*p.overflow) || other.used == 0) return;
     if ((so.fill + other.used) * 5 >= so.mask * 3) resize(so, (so.used + other.used) * 2, p);
-    if (p.overflow) return;
+    if ((*p.overflow)) return;
     if (so.fill == 0 && so.mask == other.mask && other.fill == other.used) {   // same size, empty target: slot copy
         for (int i = 0; i <= other.mask; ++i) so.tab[i] = other.tab[i];
         so.fill = other.fill; so.used = other.used;
@@ -128,7 +134,7 @@ COIN_PYSET_HD void merge(Set& so, const Set& other, Pool& p) {
 // a | b  (set_or: set_copy(a) then set_update_internal(result, b))
 COIN_PYSET_HD Set set_union(const Set& a, const Set& b, Pool& p) {
     Set r = make_empty(p);
-    if (p.overflow) return r;
+    if ((*p.overflow)) return r;
     merge(r, a, p);
     merge(r, b, p);
     return r;
@@ -180,11 +186,11 @@ COIN_PYSET_HD int difference_order(int n, Keep keep, int other_size, int32_t* ou
             if (keep(i)) out[c++] = i;
         return c;
     }
-    pool.used = 0; pool.overflow = 0;
+    *pool.used = 0; *pool.overflow = 0;
     Set r = make_empty(pool);
-    for (int i = 0; i < n && !pool.overflow; ++i)
+    for (int i = 0; i < n && !(*pool.overflow); ++i)
         if (keep(i)) add(r, i, pool);
-    if (pool.overflow) {            // cannot happen within the documented sizes; stay deterministic
+    if ((*pool.overflow)) {            // cannot happen within the documented sizes; stay deterministic
         int c = 0;
         for (int i = 0; i < n; ++i)
             if (keep(i)) out[c++] = i;
@@ -198,7 +204,8 @@ COIN_PYSET_HD int difference_order(int n, Keep keep, int other_size, int32_t* ou
 
 // ----------------------------------------------------------------------------------------------------------------
 // filter_result / find_same (coin/utils/util.py:459-482), replayed literally.
-//   adj(i, j)  : IoU(box i, box j) >= thresh            (the reference's iou_matrix, diagonal included)
+//   adj_word(i, w) : bits [32w, 32w+32) of row i of `IoU(box i, box j) >= thresh` (the reference's iou_matrix, diagonal
+//                    included), W words per row - the rows are walked by set bit, never by an O(n^2) scan
 //   Output     : clusters[k] = handle of the k-th surviving set with len != 1 (len 0 sets are dropped first);
 //                their slot order is the order of `result[list(i)]`.
 // Node states: a handle per node (nodes whose set is exactly {i} never allocate: they take no part in anything).
@@ -224,24 +231,115 @@ COIN_PYSET_HD Handle handle_of(const Set& s, Pool& p) {
 
 // Returns the number of clusters (<= max_clusters) or -1 on overflow of the pool / recursion stack / cluster list
 // (the caller then falls back to its order-free policy and flags the result).
-template <class Adj>
-COIN_PYSET_HD int filter_clusters(int n, Adj adj, Handle* sets /*[n]*/, Frame* stack /*[kMaxDepth]*/, Pool& pool,
-                                  Handle* clusters, int max_clusters) {
-    pool.used = 0; pool.overflow = 0;
-    // sets[i] = set(iou_matrix[i].nonzero()[:,0].tolist())
-    for (int i = 0; i < n; ++i) {
-        int deg = 0, only = -1;
-        for (int j = 0; j < n; ++j)
-            if (adj(i, j)) { ++deg; only = j; }
-        if (deg == 0) { sets[i].off = kNone; sets[i].mask = 7; sets[i].used = 0; continue; }
-        if (deg == 1 && only == i) { sets[i].off = kSelf; sets[i].mask = 7; sets[i].used = 1; continue; }
-        Set s = make_empty(pool);
-        for (int j = 0; j < n && !pool.overflow; ++j)
-            if (adj(i, j)) add(s, j, pool);
-        if (pool.overflow) return -1;
-        sets[i] = handle_of(s, pool);
+COIN_PYSET_HD int popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+COIN_PYSET_HD int ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
+COIN_PYSET_HD int filter_clusters_built(int n, const int16_t* active, Handle* sets, Frame* stack, Pool& pool);
+
+// set(iou_matrix[i].nonzero()[:,0].tolist()) for one node: its neighbours added in ascending order
+template <class AdjWord>
+COIN_PYSET_HD Handle build_row_set(int i, int W, AdjWord adj_word, Pool& pool) {
+    Handle h;
+    int deg = 0, only = -1;
+    for (int w = 0; w < W; ++w) {
+        const uint32_t m = adj_word(i, w);
+        if (m) { deg += popc32(m); only = w * 32 + ctz32(m); }
     }
+    if (deg == 0) { h.off = kNone; h.mask = 7; h.used = 0; return h; }
+    if (deg == 1 && only == i) { h.off = kSelf; h.mask = 7; h.used = 1; return h; }
+    Set s = make_empty(pool);
+    for (int w = 0; w < W && !*pool.overflow; ++w) {
+        uint32_t m = adj_word(i, w);
+        while (m && !*pool.overflow) { add(s, w * 32 + ctz32(m), pool); m &= m - 1; }
+    }
+    if (*pool.overflow) { h.off = kNone; h.mask = 7; h.used = 0; return h; }
+    return handle_of(s, pool);
+}
+
+// Serial reference form: build every node's set, replay, list the clusters.
+template <class AdjWord>
+COIN_PYSET_HD int filter_clusters(int n, int W, AdjWord adj_word, Handle* sets /*[n]*/, Frame* stack /*[kMaxDepth]*/,
+                                  Pool& pool, Handle* clusters, int max_clusters) {
+    // sets[i] = set(iou_matrix[i].nonzero()[:,0].tolist())   (the caller resets the pool)
     for (int i = 0; i < n; ++i) {
+        sets[i] = build_row_set(i, W, adj_word, pool);
+        if (*pool.overflow) return -1;
+    }
+    if (filter_clusters_built(n, nullptr, sets, stack, pool) < 0) return -1;
+    int nc = 0;
+    for (int i = 0; i < n; ++i) {
+        if (sets[i].off < 0 || sets[i].used == 1) continue;    // len 0 dropped, len 1 skipped (util.py:480-481)
+        if (nc == max_clusters) return -1;
+        clusters[nc++] = sets[i];
+    }
+    return nc;
+}
+
+// Node classes for the parallel form. Near-duplicate detections almost always come in PAIRS: i ~ j and nothing else.
+// For such a component the replay is a fixed point: sets[i] | find_same(...) copies the 8-slot table of sets[i] slot by
+// slot and adds members it already has, so the cluster is the initial set of the lower node, as built. (From three
+// members on, set_merge pre-sizes the copy and re-lays it out, so larger components are replayed for real.)
+constexpr int kIdle = 0, kPairLeader = 1, kPairFollower = 2, kActive = 3;
+
+template <class AdjWord>
+COIN_PYSET_HD int classify_node(int i, int W, AdjWord adj_word) {
+    int deg = 0, lo = -1, hi = -1;
+    for (int w = 0; w < W; ++w) {
+        uint32_t m = adj_word(i, w);
+        deg += popc32(m);
+        while (m) { const int b = w * 32 + ctz32(m); if (lo < 0) lo = b; hi = b; m &= m - 1; }
+    }
+    if (deg == 0 || (deg == 1 && lo == i)) return kIdle;
+    if (deg == 2 && (lo == i || hi == i)) {
+        const int other = lo == i ? hi : lo;
+        bool same = true;
+        for (int w = 0; w < W; ++w) same = same && (adj_word(other, w) == adj_word(i, w));
+        if (same) return i < other ? kPairLeader : kPairFollower;
+    }
+    return kActive;
+}
+
+// Parallel-friendly form, written serially here (the kernel runs steps 1-2 with one thread per node and step 4 as a
+// ballot compaction; step 3 is the only serial part and visits the kActive nodes only). Same result as filter_clusters.
+template <class AdjWord>
+COIN_PYSET_HD int filter_clusters_fast(int n, int W, AdjWord adj_word, int* kind /*[n]*/, Handle* sets /*[n]*/,
+                                       int16_t* active /*[n]*/, Frame* stack, Pool& pool, Handle* clusters, int max_clusters) {
+    int n_active = 0;
+    for (int i = 0; i < n; ++i) {                                   // 1, 2: classify, build the sets that matter
+        kind[i] = classify_node(i, W, adj_word);
+        if (kind[i] == kPairLeader || kind[i] == kActive) sets[i] = build_row_set(i, W, adj_word, pool);
+        if (*pool.overflow) return -1;
+        if (kind[i] == kActive) active[n_active++] = (int16_t)i;
+    }
+    if (n_active && filter_clusters_built(n_active, active, sets, stack, pool) < 0) return -1;   // 3
+    int nc = 0;
+    for (int i = 0; i < n; ++i) {                                   // 4: clusters in ascending order of their owner
+        const bool is_cluster = kind[i] == kPairLeader || (kind[i] == kActive && sets[i].off >= 0 && sets[i].used != 1);
+        if (!is_cluster) continue;
+        if (nc == max_clusters) return -1;
+        clusters[nc++] = sets[i];
+    }
+    return nc;
+}
+
+// The replay proper (util.py:471-478 with find_same inlined as an explicit stack) over sets[] already built. `active`:
+// optional ascending list of the nodes to visit (nullptr: all of 0..n-1); results stay in sets[]. Returns 0, or -1 on
+// overflow of the pool / recursion stack.
+COIN_PYSET_HD int filter_clusters_built(int n, const int16_t* active, Handle* sets, Frame* stack, Pool& pool) {
+    for (int q = 0; q < n; ++q) {
+        const int i = active ? active[q] : q;
         if (sets[i].off < 0) continue;       // {} and {i}: both loops of util.py:471-478 do nothing
         // for j in sets[i]  (the object bound NOW; later rebinding of sets[i] does not affect this iteration)
         const Handle it = sets[i];
@@ -289,12 +387,12 @@ COIN_PYSET_HD int filter_clusters(int n, Adj adj, Handle* sets /*[n]*/, Frame* s
                 const int pi = stack[depth].node;
                 if (sets[pi].off == kSelf || ret.off == kSelf) return -1;   // unreachable for a symmetric adj; be safe
                 Set u = set_union(view(sets[pi], pool), view(ret, pool), pool);
-                if (pool.overflow) return -1;
+                if ((*pool.overflow)) return -1;
                 sets[pi] = handle_of(u, pool);
             }
             if (ret.off == kSelf) return -1;
             Set u = set_union(view(sets[i], pool), view(ret, pool), pool);
-            if (pool.overflow) return -1;
+            if ((*pool.overflow)) return -1;
             sets[i] = handle_of(u, pool);
         }
         // for j in sets[i]: if j != i: sets[j] = set()
@@ -304,14 +402,7 @@ COIN_PYSET_HD int filter_clusters(int n, Adj adj, Handle* sets /*[n]*/, Frame* s
             if (j != kEmpty && j != i) { sets[j].off = kNone; sets[j].mask = 7; sets[j].used = 0; }
         }
     }
-    int nc = 0;
-    for (int i = 0; i < n; ++i) {
-        if (sets[i].off < 0) continue;               // len 0 dropped, {i} has len 1
-        if (sets[i].used == 1) continue;
-        if (nc == max_clusters) return -1;
-        clusters[nc++] = sets[i];
-    }
-    return nc;
+    return 0;
 }
 
 }  // namespace pyset

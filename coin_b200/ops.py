@@ -271,7 +271,8 @@ def iou_match(gt: torch.Tensor, boxes: torch.Tensor, thresholds: Sequence[float]
     matches = torch.empty((m,), dtype=torch.int64, device=boxes.device)
     mlabels = torch.empty((m,), dtype=torch.int8, device=boxes.device)
     vals = torch.empty((m,), dtype=torch.float32, device=boxes.device) if return_vals else None
-    ws = torch.empty((max(n, 1),), dtype=torch.float32, device=boxes.device) if allow_low_quality else None
+    ws = (torch.empty((lib.coin_iou_match_workspace_floats(n, m),), dtype=torch.float32, device=boxes.device)
+          if allow_low_quality else None)
     thr, lab = _matcher_cfg(thresholds, labels)
     check(lib.coin_iou_match(_ptr(gt), n, _ptr(boxes), m, thr, len(thresholds), lab, int(bool(allow_low_quality)),
                              _ptr(matches), _ptr(mlabels), _ptr(vals), _ptr(ws), _stream()))
@@ -503,7 +504,8 @@ def iou_match_dev(gt: torch.Tensor, n_dev: Optional[torch.Tensor], boxes: torch.
     n, m = gt.shape[0], boxes.shape[0]
     matches = torch.empty((m,), dtype=torch.int64, device=boxes.device)
     mlabels = torch.empty((m,), dtype=torch.int8, device=boxes.device)
-    ws = torch.empty((max(n, 1),), dtype=torch.float32, device=boxes.device) if allow_low_quality else None
+    ws = (torch.empty((lib.coin_iou_match_workspace_floats(n, m),), dtype=torch.float32, device=boxes.device)
+          if allow_low_quality else None)
     thr, lab = _matcher_cfg(thresholds, labels)
     check(lib.coin_iou_match_dev(_ptr(gt), n, _ptr(None if n_dev is None else _count(n_dev)), _ptr(boxes), m,
                                  _ptr(None if m_dev is None else _count(m_dev)), thr, len(thresholds), lab,

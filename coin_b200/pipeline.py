@@ -56,10 +56,13 @@ class RoIPathStep:
     RPN_NMS_THRESH = 0.7
     MATCH_THRESH = 0.5                      # CLOUD.MATCHER.IOU_THRESHOLDS (config.py:143)
 
-    def __init__(self, shape: Shape, device, weight_for_box_a: float = 1.0, seed: int = 2024, share=None):
+    def __init__(self, shape: Shape, device, weight_for_box_a: float = 1.0, seed: int = 2024, share=None,
+                 io_dtype: torch.dtype = torch.float32):
         """share: another RoIPathStep of the same shape whose constants (anchors, head gradient) are reused
-        (a second graph instance for double buffering must not duplicate the 1.2 GB head gradient)."""
-        self.shape, self.device, self.w_a = shape, device, weight_for_box_a
+        (a second graph instance for double buffering must not duplicate the 1.2 GB head gradient).
+        io_dtype: dtype of the feature map coming in and of its gradient going out. The reference runs this path under
+        autocast (trainer.py:175,187), where both are fp16; the arithmetic stays fp32 either way."""
+        self.shape, self.device, self.w_a, self.io_dtype = shape, device, weight_for_box_a, io_dtype
         if share is not None:
             self.anchors, self.head_grad = share.anchors, share.head_grad
         else:
@@ -79,7 +82,7 @@ class RoIPathStep:
     # -- data movement -------------------------------------------------------------------------
     def host_inputs(self, batch) -> Dict[str, torch.Tensor]:
         """Flat dict of the per-step INPUT tensors (pinned host memory) for the end-to-end timing."""
-        flat = {"features": batch["features"]}
+        flat = {"features": batch["features"].to(self.io_dtype)}
         for i, img in enumerate(batch["images"]):
             for k in ("teacher_rois", "teacher_deltas", "teacher_probs", "proposals", "rois", "rpn_boxes",
                       "rpn_scores"):
@@ -153,7 +156,7 @@ class RoIPathStep:
             if backward:
                 n, c, h, w = d["features"].shape
                 out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
-                                                              0, True, [torch.float32],
+                                                              0, True, [self.io_dtype],
                                                               events=ev["bwd"] if ev else None)[0]
 
         # ---- teacher branch and RPN NMS: one stream per image and chain, no host sync inside the loop
@@ -328,7 +331,7 @@ class RoIPathStep:
             if backward:
                 n, c, h, w = d["features"].shape
                 out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
-                                                              0, True, [torch.float32],
+                                                              0, True, [self.io_dtype],
                                                               events=ev["bwd"] if ev else None)[0]
                 self._mark("roi.end_bwd")
 
@@ -526,7 +529,7 @@ class PipelinedSteps:
 
     def __init__(self, first: RoIPathStep, d_first: Dict[str, torch.Tensor], backward: bool = True):
         dev = first.device
-        self.slots = [first, RoIPathStep(first.shape, dev, first.w_a, share=first)]
+        self.slots = [first, RoIPathStep(first.shape, dev, first.w_a, share=first, io_dtype=first.io_dtype)]
         # One contiguous device buffer per dtype and slot holds all inputs of a step (the graphs' input tensors
         # are views into it), mirrored by one pinned host buffer per dtype: a step's inputs travel in one H2D
         # copy per dtype instead of ~40 small ones.

@@ -154,7 +154,10 @@ int coin_matcher(const float* quality, int64_t N, int64_t M, const float* thresh
                  const int8_t* labels_host, int allow_low_quality, int64_t* matches,
                  int8_t* match_labels, float* matched_vals, float* row_max_ws, coin_stream_t stream);
 
-/* pairwise_iou + Matcher fused: the [N,M] matrix is never written. gt: [N,4], boxes: [M,4]. */
+/* pairwise_iou + Matcher fused: the [N,M] matrix is never written. gt: [N,4], boxes: [M,4].
+ * row_max_ws (required iff allow_low_quality): fp32 [coin_iou_match_workspace_floats(N, M)] - the row maxima plus
+ * each CTA's own row maxima, so that the low-quality pass re-evaluates a row only where its maximum was reached. */
+size_t coin_iou_match_workspace_floats(int64_t N, int64_t M);
 int coin_iou_match(const float* gt, int64_t N, const float* boxes, int64_t M,
                    const float* thresholds_host, int nthr, const int8_t* labels_host,
                    int allow_low_quality, int64_t* matches, int8_t* match_labels,
@@ -289,7 +292,8 @@ int coin_roi_align_fwd_dev(const coin_level_t* levels_host, int nlevels, const f
 
 /* coin_iou_match with device-side live counts *n_dev <= N_cap (gt rows) and *m_dev <= M_cap (columns);
  * either may be NULL. A live N of 0 applies Matcher's empty-matrix rule on the device. Entries of the
- * outputs beyond the live M are left untouched. row_max_ws: fp32 [N_cap] iff allow_low_quality. */
+ * outputs beyond the live M are left untouched. row_max_ws: fp32 [coin_iou_match_workspace_floats(N_cap, M_cap)]
+ * iff allow_low_quality. */
 int coin_iou_match_dev(const float* gt, int64_t N_cap, const int32_t* n_dev, const float* boxes,
                        int64_t M_cap, const int32_t* m_dev, const float* thresholds_host, int nthr,
                        const int8_t* labels_host, int allow_low_quality, int64_t* matches,

@@ -400,6 +400,30 @@ def test_nms_sizes_vs_oracle(dev, n, thr):
     assert torch.equal(top.cpu(), ref[:7])
 
 
+@pytest.mark.parametrize("n,objects,max_keep", [(6000, 40, 1000), (6000, 40, 30), (12000, 3000, 2000), (12000, 100, 2000),
+                                                (5000, 5000, 100), (20000, 300, 500), (4097, 10, 2000), (70000, 2000, 300)])
+def test_nms_max_keep_two_part_early_exit(dev, n, objects, max_keep):
+    """keep[:max_keep] (fast_rcnn.py:165-166; d2 find_top_rpn_proposals): part 1 sweeps only the first
+    R1 = max(1024, 2 * max_keep) sorted boxes and part 2 continues when that did not fill max_keep. Heavily clustered
+    inputs (few objects) force part 2, sparse ones end in part 1; both must equal nms(...)[:max_keep] of the oracle.
+    Sizes cover the three sort paths (one CTA, chunked + ranked, radix)."""
+    g = synth.gen(300 + n + objects + max_keep)
+    base = synth.random_boxes(g, objects, 600, 1200)
+    boxes = synth.jitter(g, base[torch.randint(0, objects, (n,), generator=g)], 0.08, 600, 1200)
+    scores = torch.rand(n, generator=g)
+    scores[n // 3] = scores[5]
+    ref = d2_ref.nms(boxes, scores, 0.7)
+    out = ops.nms(boxes.to(dev), scores.to(dev), 0.7, max_keep=max_keep)
+    assert torch.equal(out.cpu(), ref[:max_keep]), (len(ref), max_keep)
+    with _lib.options(COIN_NMS_TWO_PART=0):       # the one-part pipeline is still reachable and agrees
+        assert torch.equal(ops.nms(boxes.to(dev), scores.to(dev), 0.7, max_keep=max_keep).cpu(), ref[:max_keep])
+    idxs = torch.randint(0, 5, (n,), generator=g)
+    sb = torch.randperm(n, generator=g).float() / n     # exactly distinct: torchvision's per-class path re-sorts unstably
+    refb = d2_ref.batched_nms(boxes, sb, idxs, 0.5)
+    outb, cnt = ops.batched_nms(boxes.to(dev), sb.to(dev), idxs.to(dev), 0.5, "vanilla", max_keep, sync=False)
+    assert torch.equal(outb[: int(cnt)].cpu(), refb[:max_keep])
+
+
 @pytest.mark.parametrize("n,k", [(900, 20), (1000, 8), (1001, 8), (4096, 8), (8000, 8)])
 def test_batched_nms_strategies_vs_oracle(dev, n, k):
     g = synth.gen(70 + n)

@@ -146,7 +146,9 @@ def test_static_step_equals_eager_step_full_size(dev):
             assert torch.equal(ge, ee)
         for ge, ee in zip(got["rpn_labels"][i], eager["rpn_labels"][i]):
             assert torch.equal(ge, ee)
-    assert torch.equal(got["pooled"], eager["pooled"]) and torch.equal(got["pooled_c"], eager["pooled_c"])
+    assert torch.equal(got["pooled"], eager["pooled"])
+    # the private-box call: device-side RoI count -> separable kernel in the graph, register-tile kernel in the eager step
+    torch.testing.assert_close(got["pooled_c"], eager["pooled_c"], rtol=1e-5, atol=1e-5 * float(d["features"].abs().max()))
 
 
 def test_pipelined_end_to_end_steps_match_oracle(dev):

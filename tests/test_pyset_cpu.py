@@ -136,6 +136,9 @@ def test_filter_clusters_matches_literal_python(lib):
         got = [list(members[offsets[k]: offsets[k + 1]]) for k in range(nc)]
         assert got == want, (trial, n, got, want)
         seen_reordered += any(c != sorted(c) for c in want)
+        # the form the kernel runs (pairs by closed form, the rest replayed) gives the same clusters in the same order
+        nc3 = lib.pyset_filter_clusters_fast(n, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), 1 << 22, members, offsets, n + 1)
+        assert nc3 >= 0 and [list(members[offsets[k]: offsets[k + 1]]) for k in range(nc3)] == want, (trial, n)
         # with the DEVICE's pool (4096 slots in shared memory) the answer is the same or an explicit overflow
         nc2 = lib.pyset_filter_clusters(n, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), 4096, members, offsets, n + 1)
         assert nc2 == -1 or [list(members[offsets[k]: offsets[k + 1]]) for k in range(nc2)] == want
@@ -151,6 +154,7 @@ def test_device_pool_suffices_for_detection_like_graphs(lib):
         flat = np.array(adj, dtype=np.uint8).reshape(-1)
         members, offsets = _i32(n * n + n), _i32(n + 2)
         assert lib.pyset_filter_clusters(n, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), 4096, members, offsets, n + 1) >= 0
+        assert lib.pyset_filter_clusters_fast(n, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), 4096, members, offsets, n + 1) >= 0
 
 
 def test_filter_clusters_reports_overflow_instead_of_guessing(lib):

@@ -15,16 +15,26 @@ img = (shape.height, shape.width)
 
 
 def timeit(name, fn, iters=30):
-    for _ in range(5):
+    """Device time of the op's launch chain: captured once in a CUDA graph (no host launch overhead), replayed."""
+    for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st):
+        keep = fn()
+    for _ in range(3):
+        g.replay()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(iters):
-        fn()
+        g.replay()
     e.record()
     torch.cuda.synchronize()
     print(f"{s.elapsed_time(e) / iters * 1e3:9.1f} us  {name}", flush=True)
+    del keep
 
 
 dec = ops.apply_deltas(d["0.teacher_deltas"], d["0.teacher_rois"], step.BBOX_WEIGHTS, clip_to=img)
@@ -38,6 +48,8 @@ cloud = {"gt_boxes": d["0.cloud.gt_boxes"] / pipeline.ORIG_SCALE, "gt_classes": 
 clip = {"gt_boxes": b, "gt_classes": c, "scores": s_, "probs": p}
 for tag in ("RCNN", "RPN"):
     timeit(f"match_abc_fields_dev tag {tag}", lambda: ops.match_abc_fields_dev(cloud, clip, nd, tag, 0.5, 1.0))
+timeit("match_abc_fields_both_dev (both tags: 1 match launch + 2 pack launches)",
+       lambda: ops.match_abc_fields_both_dev(cloud, clip, nd, 0.5, 1.0))
 a, bb, cc, cnt = ops.match_abc_fields_dev(cloud, clip, nd, "RCNN", 0.5, 1.0)
 n_a, n_b, n_c = cnt[0:1], cnt[1:2], cnt[2:3]
 gt, n_gt = ops.concat_rows([(a["gt_boxes"], n_a, 0.0), (bb["gt_boxes"], n_b, 0.0), (cc["gt_boxes"], n_c, 0.0)])
