@@ -1,6 +1,7 @@
 // capi.cu -- error reporting and version of the C ABI (include/coinops.h).
 #include "common.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -10,6 +11,23 @@ namespace coin {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// memset as a KERNEL. cudaMemsetAsync becomes a memset node when a stream is captured into a CUDA graph, and memset
+// nodes do not carry the stream's priority: inside the step (coin_b200/pipeline.py) every chain of short kernels that
+// contained one queued behind the whole ROIAlign grid of the normal-priority stream. A fill kernel inherits the priority.
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint32_t v, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+int fill_bytes(void* p, int byte_value, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return COIN_OK;
+    if ((reinterpret_cast<uintptr_t>(p) & 3) || (bytes & 3)) return fail(COIN_ERR_INVALID, "fill_bytes: unaligned");
+    const uint32_t b = (uint32_t)(byte_value & 0xff);
+    const size_t n = bytes / 4;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 4 * 148);
+    fill_u32_kernel<<<blocks, 256, 0, s>>>(static_cast<uint32_t*>(p), b * 0x01010101u, n);
+    return check_launch("fill_u32_kernel");
+}
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;

@@ -31,6 +31,9 @@ inline int check_launch(const char* what) {
         if (!(cond)) return ::coin::fail(COIN_ERR_INVALID, __VA_ARGS__); \
     } while (0)
 
+// memset as a kernel launch (capi.cu): keeps the launching stream's priority inside captured graphs
+int fill_bytes(void* p, int byte_value, size_t bytes, cudaStream_t s);
+
 inline cudaStream_t as_stream(coin_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

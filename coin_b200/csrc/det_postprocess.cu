@@ -157,7 +157,7 @@ extern "C" int coin_det_postprocess(const float* boxes, const float* scores, int
     COIN_REQUIRE(kreg == 1 || kreg == k1 - 1, "det_postprocess: kreg must be 1 or the number of foreground classes");
     cudaStream_t s = as_stream(stream);
     if (R == 0 || out_capacity == 0 || topk == 0) {
-        cudaMemsetAsync(out_count, 0, sizeof(int32_t), s);
+        fill_bytes(out_count, 0, sizeof(int32_t), s);
         return COIN_OK;
     }
     COIN_REQUIRE(boxes && scores && out_boxes && out_scores && out_probs && out_classes && out_roi_index && ws,

@@ -267,9 +267,9 @@ extern "C" int coin_fusion_nms(const float* boxes, const float* probs, const int
     COIN_REQUIRE(n >= 0 && k1 >= 1 && nkeep && status, "fusion_nms: bad arguments");
     COIN_REQUIRE(score_method >= 0 && score_method <= 2 && box_method >= 0 && box_method <= 2, "fusion_nms: bad method");
     cudaStream_t s = as_stream(stream);
-    cudaMemsetAsync(status, 0, sizeof(int32_t), s);
+    fill_bytes(status, 0, sizeof(int32_t), s);
     if (n == 0) {
-        cudaMemsetAsync(nkeep, 0, sizeof(int32_t), s);
+        fill_bytes(nkeep, 0, sizeof(int32_t), s);
         return COIN_OK;
     }
     if (n > kFusionMax) return fail(COIN_ERR_UNSUPPORTED, "fusion_nms: n=%lld exceeds %d boxes per call", (long long)n, kFusionMax);

@@ -412,7 +412,7 @@ static int iou_match_impl(const float* gt, int64_t N, const float* boxes, int64_
         COIN_REQUIRE(row_max_ws, "iou_match: row_max_ws is required with allow_low_quality");
         unsigned* row_max = reinterpret_cast<unsigned*>(row_max_ws);
         unsigned* cta_rmax = row_max + N;
-        cudaMemsetAsync(row_max, 0, N * sizeof(float), s);
+        fill_bytes(row_max, 0, N * sizeof(float), s);
         if (G == 1) {
             iou_match_kernel<true, 1><<<blocks, 256, 0, s>>>(g4, N, b4, M, cfg, matches, match_labels, matched_vals, row_max,
                                                              cta_rmax, n_dev, m_dev);
@@ -536,7 +536,7 @@ extern "C" int coin_iou_pairs_ge(const float* b1, int64_t N, const float* b2, in
     COIN_REQUIRE(N >= 0 && M >= 0 && capacity >= 0 && count, "iou_pairs_ge: bad arguments");
     cudaStream_t s = as_stream(stream);
     if (N == 0 || M == 0) {
-        cudaMemsetAsync(count, 0, sizeof(int32_t), s);
+        fill_bytes(count, 0, sizeof(int32_t), s);
         return COIN_OK;
     }
     COIN_REQUIRE(b1 && b2 && aligned16(b1) && aligned16(b2) && (pairs || capacity == 0), "iou_pairs_ge: null or misaligned pointer");

@@ -234,7 +234,9 @@ __device__ __forceinline__ void abc_use_shared(AbcArgs& b, unsigned char* sm, bo
     }
 }
 
-__global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a_in) {
+// <= 56 registers x 256 threads = 14336: the CTA fits into the register slot ONE retiring ROIAlign CTA frees (224 threads
+// x 72 registers = 16128), so inside the step it becomes resident at once instead of waiting for two slots on one SM.
+__global__ void __maxnreg__(56) match_abc_kernel(const AbcArgs a_in) {
     extern __shared__ __align__(16) unsigned char abc_smem[];
     __shared__ int s_tmp, s_flag[6], s_status, s_pc[6];   // s_pc: (used, overflow) of the three pyset pools
     AbcArgs a = a_in;   // mutable copy: scratch pointers may be redirected to shared memory
@@ -661,6 +663,7 @@ __global__ void __launch_bounds__(256) match_abc_kernel(const AbcArgs a_in) {
             o.counts[2] = nC;
             o.counts[3] = s_status;
             o.counts[4] = nC_off;
+            o.counts[5] = 0; o.counts[6] = 0; o.counts[7] = 0;
         }
     }
 }
@@ -721,7 +724,7 @@ static int match_abc_impl(const float* on_boxes, const int64_t* on_classes, cons
     for (const AbcHostOut* o : {rcnn, rpn})
         if (o) {
             COIN_REQUIRE(o->counts, "match_abc: counts is null");
-            cudaMemsetAsync(o->counts, 0, 8 * sizeof(int32_t), s);
+            if (nc == 0 && nd == 0) fill_bytes(o->counts, 0, 8 * sizeof(int32_t), s);   // otherwise the kernel writes all 8
         }
     if (nc == 0 && nd == 0) return COIN_OK;
     COIN_REQUIRE(cap_pairs >= nc * nd + nc + nd, "match_abc: cap_pairs must be >= nc*nd + nc + nd");

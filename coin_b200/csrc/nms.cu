@@ -65,7 +65,9 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* __restrict__ k, int 
     __syncthreads();
 }
 
+// 512 threads x 24 registers = 12288 registers: fits the register slot of one retiring ROIAlign CTA (16128) inside the step
 constexpr int kSortThreads = 512;
+#define COIN_SORT_BOUNDS __maxnreg__(24)
 
 // meta[0] = live box count n (<= n_cap), meta[1] = resolved strategy. Every kernel of the pipeline is
 // launched for the host-known capacity n_cap and reads the live n from `meta`, so a caller can chain
@@ -141,7 +143,7 @@ __global__ void gather_sorted_kernel(const uint32_t* __restrict__ sorted_idx, co
 }
 
 // Single-CTA path for n <= kSmallSort: key generation, bitonic sort, max-reduce and gather fused.
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void COIN_SORT_BOUNDS
 small_sort_gather_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes,
                          const int64_t* __restrict__ idxs, int n_cap, const int32_t* __restrict__ n_dev,
                          int strategy_in, float4* __restrict__ sboxes, int32_t* __restrict__ scls,
@@ -191,7 +193,7 @@ small_sort_gather_kernel(const float* __restrict__ scores, const float4* __restr
 constexpr int kChunk = 4096;
 constexpr int kMaxChunks = 16;   // n <= 65536 takes this path
 
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void COIN_SORT_BOUNDS
 chunk_sort_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes, int n_cap,
                   const int32_t* __restrict__ n_dev, int strategy_in, uint64_t* __restrict__ ckeys,
                   float* __restrict__ max_coord, int32_t* __restrict__ meta) {
@@ -569,7 +571,7 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
         if (int rc = check_launch("small_sort_gather_kernel")) return rc;
     } else if (w.ckeys) {
         const int nchunks = (int)ceil_div(n, kChunk);
-        cudaMemsetAsync(w.max_coord, 0x80, sizeof(int), s);  // 0x80808080 decodes to ~ -3.4e38
+        fill_bytes(w.max_coord, 0x80, sizeof(int), s);  // 0x80808080 decodes to ~ -3.4e38
         chunk_sort_kernel<<<nchunks, kSortThreads, kChunk * sizeof(uint64_t), s>>>(scores, b4, n, n_dev, strategy, w.ckeys,
                                                                            w.max_coord, w.meta);
         if (int rc = check_launch("chunk_sort_kernel")) return rc;
@@ -585,7 +587,7 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
         if (e != cudaSuccess) return fail(COIN_ERR_CUDA, "nms: radix sort failed: %s", cudaGetErrorString(e));
         count_launch();
         if (strategy == COIN_NMS_TRICK || strategy == COIN_NMS_AUTO) {
-            cudaMemsetAsync(w.max_coord, 0x80, sizeof(int), s);  // 0x80808080 decodes to ~ -3.4e38
+            fill_bytes(w.max_coord, 0x80, sizeof(int), s);  // 0x80808080 decodes to ~ -3.4e38
             max_coord_kernel<<<kNumSMs, 256, 0, s>>>(b4, w.meta, w.max_coord);
             if (int rc = check_launch("max_coord_kernel")) return rc;
         }
@@ -595,7 +597,7 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
     }
     const float thr_f = round_down_to_float(thr);
     const int fw = (int)ceil_div(colblocks, 64);
-    cudaMemsetAsync(w.rowflags, 0, (size_t)n * fw * sizeof(uint64_t), s);
+    fill_bytes(w.rowflags, 0, (size_t)n * fw * sizeof(uint64_t), s);
     const size_t smem = (size_t)colblocks * sizeof(uint64_t);
     if (smem > 48 * 1024) cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 block(64, 4);
@@ -619,7 +621,7 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
                                               0, INT_MAX, nullptr, nullptr, nullptr);
         return check_launch("nms_sweep_kernel");
     }
-    cudaMemsetAsync(w.removed_g, 0, (size_t)colblocks * sizeof(uint64_t), s);
+    fill_bytes(w.removed_g, 0, (size_t)colblocks * sizeof(uint64_t), s);
     if (int rc = launch_mask(dim3((unsigned)ceil_div(t1, 4), (unsigned)t1), 0, (int)r1, 0)) return rc;
     nms_sweep_kernel<<<1, 256, smem, s>>>(w.mask, w.lower, w.rowflags, fw, w.order, w.meta, colblocks, max_keep, keep, nkeep, 0,
                                           (int)r1, w.state, w.keptbits, w.removed_g);
@@ -643,7 +645,7 @@ extern "C" int coin_batched_nms(const float* boxes, const float* scores, const i
     COIN_REQUIRE(n < (1ll << 22), "batched_nms: n=%lld exceeds the supported 4M boxes", (long long)n);
     cudaStream_t s = as_stream(stream);
     if (n == 0 || max_keep == 0) {
-        cudaMemsetAsync(nkeep, 0, sizeof(int32_t), s);
+        fill_bytes(nkeep, 0, sizeof(int32_t), s);
         return COIN_OK;
     }
     COIN_REQUIRE(boxes && scores && keep && ws, "batched_nms: null pointer");

@@ -29,6 +29,27 @@ namespace coin {
 
 static inline int reg_env(const char* name, int dflt) { return option(name, dflt); }
 
+// COIN_ROI_CTAS_PER_SM = n > 0: pad the dynamic shared memory of the register-tile kernels so that at most n CTAs fit on
+// an SM. The step (coin_b200/pipeline.py) uses it to leave a quarter of every SM to the latency-bound kernels that run
+// beside ROIAlign on other streams: with 4 resident CTAs of 224 threads x 72 registers the register file is full, and a
+// short kernel's CTA has to wait for a ROIAlign CTA (~30 us) to retire on an SM with enough room.
+static inline size_t reg_occupancy_pad(size_t smem) {
+    const int occ = reg_env("COIN_ROI_CTAS_PER_SM", 0);
+    if (occ <= 0) return smem;
+    const size_t per_cta = ((size_t)228 * 1024) / (size_t)occ - 1024;   // 1 KB per CTA is reserved by the runtime
+    return std::max(smem, per_cta / 128 * 128);
+}
+
+// COIN_ROI_CARVEOUT = p in [0, 100]: preferred shared-memory carveout (percent of the unified L1 / shared array) of the
+// register-tile kernels. Left to the driver, the carveout is sized for the 4 resident ROIAlign CTAs (~138 KB), and a
+// kernel of another stream that needs > ~26 KB of shared memory (the single-CTA sort, knowledge separation) cannot
+// become resident on any SM until the ROIAlign grid has drained. The step asks for the maximum carveout instead.
+template <class K>
+static inline void reg_apply_carveout(K kern) {
+    const int pct = reg_env("COIN_ROI_CARVEOUT", -1);
+    if (pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+}
+
 constexpr int kRegTap = 128;    // x / y tap-table entries (PW*grid_w and PH*grid_h must fit)
 constexpr int kRegCols = 96;    // feature columns of one RoI handled by the tables
 constexpr int kRegYEnt = 16;    // merged y-table entries per unit
@@ -525,8 +546,9 @@ template <typename T, int PH, int PW, int CS, int OCC, int CPL, int MLP = 1>
 static int launch_fwd_reg(const RoiParams& p, T* out, int slabs, cudaStream_t s) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW, CC = 32 * CPL;
     auto kern = roi_align_fwd_reg_kernel<T, PH, PW, CS, OCC, CPL, MLP>;
-    const size_t smem = std::max<size_t>((size_t)CC * NB * sizeof(T), 2 * kRegTap * sizeof(RXTap));
+    const size_t smem = reg_occupancy_pad(std::max<size_t>((size_t)CC * NB * sizeof(T), 2 * kRegTap * sizeof(RXTap)));
     if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reg_apply_carveout(kern);
     slabs = std::max(1, std::min(slabs, p.C / CC));
     const int cgroups = (int)ceil_div(p.C, CC * slabs);
     kern<<<(unsigned)(p.K * cgroups), 32 * NU, smem, s>>>(p, out, cgroups, slabs);
@@ -737,7 +759,9 @@ template <typename T, int PH, int PW, int CS, int OCC>
 static int launch_bwd_reg(const RoiParams& p, const T* go, int slabs, cudaStream_t s) {
     constexpr int NU = (PH + 1) / 2, NB = PH * PW;
     auto kern = roi_align_bwd_reg_kernel<T, PH, PW, CS, OCC>;
-    const size_t smem = (size_t)32 * NB * sizeof(T) + 2 * kRegTap * sizeof(RXTap);
+    const size_t smem = reg_occupancy_pad((size_t)32 * NB * sizeof(T) + 2 * kRegTap * sizeof(RXTap));
+    if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reg_apply_carveout(kern);
     const int cgroups = (int)ceil_div(p.C, 32 * slabs);
     kern<<<(unsigned)(p.K * cgroups), 32 * NU, smem, s>>>(p, go, cgroups, slabs);
     return check_launch("roi_align_bwd_reg_kernel");

@@ -161,8 +161,8 @@ extern "C" int coin_rpn_proposals(const float* anchors, const float* deltas, con
     COIN_REQUIRE(A >= 0 && pre_nms_topk >= 0 && post_nms_topk >= 0 && out_count && status, "rpn_proposals: bad arguments");
     COIN_REQUIRE(A < (1ll << 31), "rpn_proposals: too many anchors");
     cudaStream_t s = as_stream(stream);
-    cudaMemsetAsync(out_count, 0, sizeof(int32_t), s);
-    cudaMemsetAsync(status, 0, sizeof(int32_t), s);
+    fill_bytes(out_count, 0, sizeof(int32_t), s);
+    fill_bytes(status, 0, sizeof(int32_t), s);
     const int64_t k = std::min(A, pre_nms_topk);
     if (k == 0 || post_nms_topk == 0) return COIN_OK;
     COIN_REQUIRE(anchors && deltas && logits && out_boxes && out_logits && ws, "rpn_proposals: null pointer");

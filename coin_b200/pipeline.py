@@ -25,7 +25,7 @@ from typing import Dict, List
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .synth import Shape
 
 ORIG_SCALE = 2048.0 / 1200.0  # Foggy-Cityscapes: 1024x2048 originals, 600x1200 network input
@@ -75,6 +75,13 @@ class RoIPathStep:
                                          generator=g).to(device)
         self._streams: List[torch.cuda.Stream] = []
         self.roi_gate = os.environ.get("COIN_ROI_GATE", "none")   # none | det | det+rpn (see _run_static)
+        # resident ROIAlign CTAs per SM inside the overlapped step (0: as many as fit = 4). With 4 the register file is
+        # full and every short kernel of the other streams waits for a ROIAlign CTA to retire; 3 leaves them a quarter SM.
+        self.roi_ctas_per_sm = int(os.environ.get("COIN_STEP_ROI_OCC", "0"))
+        # preferred shared-memory carveout (%) of the ROIAlign kernels inside the step, -1: the driver's choice. The
+        # driver sizes the carveout for the resident ROIAlign CTAs only, which keeps every kernel of the other streams
+        # that needs more than ~26 KB of shared memory (sort, knowledge separation) off the SMs until ROIAlign drains.
+        self.roi_carveout = int(os.environ.get("COIN_STEP_ROI_CARVEOUT", "86"))
         self.overlap = True         # issue independent stages on side streams (False: everything on the caller's stream)
         self.timeline = None        # tools/step_timeline.py: dict name -> external CUDA event recorded in the graph
         self.kernel_events = None   # bench.py: {"fwd": [], "bwd": []} to time the two dominant kernels live
@@ -322,7 +329,9 @@ class RoIPathStep:
         #      masks) have had the machine to themselves.
         for e in gate:
             s_roi.wait_event(e)
-        with torch.cuda.stream(s_roi):
+        occ = self.roi_ctas_per_sm if self.overlap else 0
+        with torch.cuda.stream(s_roi), _lib.options(COIN_ROI_CTAS_PER_SM=occ,
+                                                    COIN_ROI_CARVEOUT=self.roi_carveout if self.overlap else -1):
             self._mark("roi.begin_fwd")
             ev = self.kernel_events
             out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
@@ -451,7 +460,7 @@ class RoIPathStep:
                                    events=ev["bwd"])
 
     # -- CUDA graph ---------------------------------------------------------------------------------
-    def capture(self, d: Dict[str, torch.Tensor], backward: bool = True, warmup: int = 2):
+    def capture(self, d: Dict[str, torch.Tensor], backward: bool = True, warmup: int = 2, keep_graph: bool = False):
         """Captures run_static over the (static) input tensors ``d`` into a CUDA graph. Later steps copy
         new inputs into the same tensors (copy_inputs) and call replay()."""
         self._graph_in = d
@@ -464,7 +473,7 @@ class RoIPathStep:
         self.kernel_events = ev
         torch.cuda.current_stream().wait_stream(cap_stream)
         torch.cuda.synchronize(self.device)
-        self._graph = torch.cuda.CUDAGraph()
+        self._graph = torch.cuda.CUDAGraph(keep_graph=keep_graph) if keep_graph else torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph, stream=cap_stream):
             self._graph_out = self.run_static(d, backward)
         return self._graph_out
