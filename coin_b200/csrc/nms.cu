@@ -4,7 +4,7 @@
 //   sort      n <= 4096: one CTA, bitonic in shared memory. n <= 65536: every 4096-box chunk is sorted by its own CTA,
 //             then ONE kernel ranks each key across the other chunks by binary search (keys are unique: score, index) and
 //             gathers the boxes straight into sorted order - 2 launches instead of CUB's ~14. Above that: CUB radix sort.
-//   part 1    mask + sweep over the first R1 = max(1024, 2*max_keep rounded up to 256) sorted boxes only. Callers that
+//   part 1    mask + sweep over the first R1 = max(1024, 1.5*max_keep rounded up to 256) sorted boxes only (COIN_NMS_R1_PCT). Callers that
 //             ask for keep[:k] (detections: k = 100; RPN proposals: k = 2000; d2's find_top_rpn_proposals) are usually
 //             satisfied here: the mask shrinks from n^2/2 to R1^2/2 pairs and the sweep from n/64 to R1/64 tiles.
 //   part 2    only if part 1 neither filled max_keep nor covered all boxes (device flag): the kept rows of part 1 are
@@ -612,7 +612,10 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
     };
     // part 1 covers the first R1 sorted boxes; with no max_keep (or few boxes) it is the whole job
     int64_t r1 = n;
-    if (max_keep >= 0) r1 = std::min<int64_t>(n, std::max<int64_t>(1024, (2 * max_keep + 255) / 256 * 256));
+    // COIN_NMS_R1_PCT: size of part 1 in percent of max_keep (default 150; a smaller part 1 does less mask work when the
+    // input overlaps little, and hands over to part 2 earlier when it overlaps a lot - the result is the same)
+    const int64_t pct = std::max(100, option("COIN_NMS_R1_PCT", 150));
+    if (max_keep >= 0) r1 = std::min<int64_t>(n, std::max<int64_t>(1024, (max_keep * pct / 100 + 255) / 256 * 256));
     if (option("COIN_NMS_TWO_PART", 1) == 0) r1 = n;
     const int t1 = (int)(r1 / 64);
     if (r1 >= n) {

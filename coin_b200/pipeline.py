@@ -81,7 +81,9 @@ class RoIPathStep:
         # preferred shared-memory carveout (%) of the ROIAlign kernels inside the step, -1: the driver's choice. The
         # driver sizes the carveout for the resident ROIAlign CTAs only, which keeps every kernel of the other streams
         # that needs more than ~26 KB of shared memory (sort, knowledge separation) off the SMs until ROIAlign drains.
-        self.roi_carveout = int(os.environ.get("COIN_STEP_ROI_CARVEOUT", "86"))
+        self.roi_carveout = int(os.environ.get("COIN_STEP_ROI_CARVEOUT", "-1"))
+        self.c_mode = os.environ.get("COIN_STEP_C_MODE", "with_bwd")        # side | between | with_bwd (see _run_static)
+        self.c_reg_mink = int(os.environ.get("COIN_STEP_C_REG_MINK", "0"))  # 0: register-tile kernel for the C boxes
         self.overlap = True         # issue independent stages on side streams (False: everything on the caller's stream)
         self.timeline = None        # tools/step_timeline.py: dict name -> external CUDA event recorded in the graph
         self.kernel_events = None   # bench.py: {"fwd": [], "bwd": []} to time the two dominant kernels live
@@ -330,19 +332,24 @@ class RoIPathStep:
         for e in gate:
             s_roi.wait_event(e)
         occ = self.roi_ctas_per_sm if self.overlap else 0
-        with torch.cuda.stream(s_roi), _lib.options(COIN_ROI_CTAS_PER_SM=occ,
-                                                    COIN_ROI_CARVEOUT=self.roi_carveout if self.overlap else -1):
+        roi_opts = dict(COIN_ROI_CTAS_PER_SM=occ, COIN_ROI_CARVEOUT=self.roi_carveout if self.overlap else -1)
+        with torch.cuda.stream(s_roi), _lib.options(**roi_opts):
             self._mark("roi.begin_fwd")
             ev = self.kernel_events
             out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
                                                   events=ev["fwd"] if ev else None)
             self._mark("roi.end_fwd")
-            if backward:
+            fwd_done = s_roi.record_event()
+
+        def run_backward():
+            with torch.cuda.stream(s_roi), _lib.options(**roi_opts):
                 n, c, h, w = d["features"].shape
                 out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
                                                               0, True, [self.io_dtype],
                                                               events=ev["bwd"] if ev else None)[0]
                 self._mark("roi.end_bwd")
+        if backward and self.c_mode != "between":
+            run_backward()
 
         # ---- knowledge separation (T4) and labelling (S3, S2): tag RCNN continues on the teacher stream,
         #      tag RPN on the image's third stream
@@ -383,19 +390,26 @@ class RoIPathStep:
             out["abc"].append(per_tag)
             out.setdefault("_keepalive2", []).append(both)
 
-        # ---- ROIAlign forward on the private (C) boxes of every image: a high-priority stream, so it does
-        #      not wait for the big forward/backward to drain
-        s_c = s_img[0]
+        # ---- ROIAlign forward on the private (C) boxes of every image (known long before the big forward ends).
+        #      c_mode "side": on a high-priority stream as soon as the boxes exist (competes with the forward);
+        #      "between": on the ROIAlign stream between the forward and the backward; "with_bwd" (default, measured best:
+        #      profiles/r02_step_schedule.md): high-priority stream, released when the forward is through, so that it
+        #      shares the machine with the backward - two latency-bound kernels fill each other's gaps
+        s_c = s_roi if self.c_mode == "between" else s_img[0]
         for seg in c_segs:
             s_c.wait_event(seg[3])
         s_c.wait_event(nhwc_ready)
-        with torch.cuda.stream(s_c):
+        if self.c_mode == "with_bwd":      # high-priority stream, but only once the forward is through: shares the
+            s_c.wait_event(fwd_done)       # machine with the backward (two latency-bound kernels fill each other's gaps)
+        with torch.cuda.stream(s_c), _lib.options(COIN_ROI_REG_MINK=self.c_reg_mink, COIN_ROI_REG_CHANS_SMALL=256):
             c_rois, n_c_rois = ops.concat_rows([seg[:3] for seg in c_segs], width_out=5)
             out["pooled_c"] = ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32,
                                                     k_dev=n_c_rois)
             slot("c_rois", n_c_rois)
             self._mark("roi.pooled_c_done")
             cat_done = s_c.record_event()
+        if backward and self.c_mode == "between":
+            run_backward()
         torch.cuda.current_stream().wait_event(cat_done)
         for st in streams:
             if st is not torch.cuda.current_stream():

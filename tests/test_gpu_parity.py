@@ -404,7 +404,7 @@ def test_nms_sizes_vs_oracle(dev, n, thr):
                                                 (5000, 5000, 100), (20000, 300, 500), (4097, 10, 2000), (70000, 2000, 300)])
 def test_nms_max_keep_two_part_early_exit(dev, n, objects, max_keep):
     """keep[:max_keep] (fast_rcnn.py:165-166; d2 find_top_rpn_proposals): part 1 sweeps only the first
-    R1 = max(1024, 2 * max_keep) sorted boxes and part 2 continues when that did not fill max_keep. Heavily clustered
+    R1 = max(1024, 1.5 * max_keep) sorted boxes and part 2 continues when that did not fill max_keep. Heavily clustered
     inputs (few objects) force part 2, sparse ones end in part 1; both must equal nms(...)[:max_keep] of the oracle.
     Sizes cover the three sort paths (one CTA, chunked + ranked, radix)."""
     g = synth.gen(300 + n + objects + max_keep)
