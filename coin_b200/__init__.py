@@ -14,7 +14,8 @@ from . import _lib  # noqa: F401,E402  (raises ImportError when the extension is
 from .layers import (Box2BoxTransform, Matcher, MyNMS, ROIAlign, ROIPooler, batched_nms, mynms, nms,
                      pairwise_iou)
 from .structures import Boxes, Instances
+from .dispatch import is_patched, patch, unpatch
 
 __all__ = ["Box2BoxTransform", "Matcher", "MyNMS", "ROIAlign", "ROIPooler", "batched_nms", "mynms", "nms",
-           "pairwise_iou", "Boxes", "Instances"]
+           "pairwise_iou", "Boxes", "Instances", "patch", "unpatch", "is_patched"]
 __version__ = "0.1.0"
