@@ -17,7 +17,8 @@ SOURCES = ["capi.cu", "roi_align.cu", "roi_align_sep.cu", "roi_align_reg.cu", "b
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xcompiler", "-fPIC",
-    "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-diag-suppress", "128",
+    "-Wno-deprecated-gpu-targets",
 ]
 
 

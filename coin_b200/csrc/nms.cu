@@ -193,19 +193,50 @@ small_sort_gather_kernel(const float* __restrict__ scores, const float4* __restr
 constexpr int kChunk = 4096;
 constexpr int kMaxChunks = 16;   // n <= 65536 takes this path
 
+// ---- class-segmented pipeline (per-class NMS of many boxes: the 20-class operator sweep) --------------
+// Sorting by (class, score desc, index) puts every class in one contiguous segment, so (1) the suppression mask is only
+// evaluated for tile pairs whose class ranges meet (K classes: ~K times fewer IoUs and mask words), (2) every class is
+// swept by its own CTA, and (3) a last sort of the kept boxes by (score desc, index) restores the order batched_nms
+// returns. The 64-bit key packs class:10 | ~orderable(score):32 | index:22; class ids outside [0, 1024) or the
+// coordinate-trick strategy fold everything into one segment (correct, just not faster than the dense pipeline).
+constexpr int kSegBuckets = 1024;
+constexpr int kMaxChunksSeg = 64;             // n <= 262144
+constexpr int kSegMinAlloc = 1024;            // smallest n whose workspace holds the segmented pipeline's buffers
+constexpr uint64_t kSegIdxMask = (1ull << 22) - 1;
+constexpr uint64_t kSegOrderMask = (1ull << 54) - 1;
+
+__device__ __forceinline__ uint64_t seg_key(int bucket, float s, uint32_t idx) {
+    return ((uint64_t)bucket << 54) | ((sort_key(s, 0u) >> 32) << 22) | idx;
+}
+
+// meta[2] = 1 when a class id does not fit a bucket (then everything is one segment)
+__global__ void seg_class_range_kernel(const int64_t* __restrict__ idxs, int n_cap, const int32_t* __restrict__ n_dev,
+                                       int32_t* __restrict__ meta) {
+    const int n = resolve_n(n_cap, n_dev);
+    bool bad = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int64_t c = __ldg(idxs + i);
+        bad |= c < 0 || c >= kSegBuckets;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(meta + 2, 1);
+}
+
 __global__ void COIN_SORT_BOUNDS
 chunk_sort_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes, int n_cap,
                   const int32_t* __restrict__ n_dev, int strategy_in, uint64_t* __restrict__ ckeys,
-                  float* __restrict__ max_coord, int32_t* __restrict__ meta) {
+                  float* __restrict__ max_coord, int32_t* __restrict__ meta, const int64_t* __restrict__ seg_idxs) {
     extern __shared__ uint64_t skeys[];
     const int n = resolve_n(n_cap, n_dev);
     const int strategy = resolve_strategy(strategy_in, n);
     if (blockIdx.x == 0 && threadIdx.x == 0) { meta[0] = n; meta[1] = strategy; }
+    // class-major keys (segmented pipeline) unless a class id is out of range or the strategy is the coordinate trick
+    const bool seg = seg_idxs && strategy == COIN_NMS_VANILLA && meta[2] == 0;
     const int base = blockIdx.x * kChunk;
     float m = -INFINITY;
     for (int i = threadIdx.x; i < kChunk; i += blockDim.x) {
         const int g = base + i;
-        skeys[i] = g < n ? sort_key(__ldg(scores + g), (uint32_t)g) : ~0ull;
+        if (seg_idxs) skeys[i] = g < n ? seg_key(seg ? (int)__ldg(seg_idxs + g) : 0, __ldg(scores + g), (uint32_t)g) : ~0ull;
+        else skeys[i] = g < n ? sort_key(__ldg(scores + g), (uint32_t)g) : ~0ull;
         if (strategy == COIN_NMS_TRICK && g < n) {
             const float4 b = __ldg(boxes + g);
             m = fmaxf(fmaxf(m, fmaxf(b.x, b.y)), fmaxf(b.z, b.w));
@@ -234,7 +265,8 @@ chunk_sort_kernel(const float* __restrict__ scores, const float4* __restrict__ b
 __global__ void merge_rank_gather_kernel(const uint64_t* __restrict__ ckeys, int nchunks, const float4* __restrict__ boxes,
                                          const int64_t* __restrict__ idxs, const int32_t* __restrict__ meta,
                                          const float* __restrict__ max_coord, float4* __restrict__ sboxes,
-                                         int32_t* __restrict__ scls, int32_t* __restrict__ order) {
+                                         int32_t* __restrict__ scls, int32_t* __restrict__ order,
+                                         uint64_t* __restrict__ okeys) {
     const int n = meta[0], strategy = meta[1];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nchunks * kChunk) return;
@@ -253,7 +285,7 @@ __global__ void merge_rank_gather_kernel(const uint64_t* __restrict__ ckeys, int
         }
         rank += lo;
     }
-    const uint32_t src = (uint32_t)(key & 0xffffffffu);
+    const uint32_t src = okeys ? (uint32_t)(key & kSegIdxMask) : (uint32_t)(key & 0xffffffffu);
     float4 b = __ldg(boxes + src);
     const int64_t cls = idxs ? __ldg(idxs + src) : 0;
     if (strategy == COIN_NMS_TRICK) {
@@ -263,6 +295,202 @@ __global__ void merge_rank_gather_kernel(const uint64_t* __restrict__ ckeys, int
     sboxes[rank] = b;
     scls[rank] = (int32_t)cls;
     order[rank] = (int32_t)src;
+    if (okeys) okeys[rank] = key;
+}
+
+// Mask of the segmented pipeline: CTA (j, rt) owns row tile rt and walks the groups of 4 column tiles rt/4 + j,
+// rt/4 + j + gridDim.x, ... until the group's first class lies beyond the row tile's last class (the sequence is sorted
+// by class, so every later group does too). Same words as nms_mask_kernel: mask[i][ct] for ct >= rt (bits j > i only),
+// lower[i] = transposed diagonal word, rowflags[i] = bitmap of the non-zero words. Words of skipped tile pairs are never
+// written and never read (the sweep only follows rowflags).
+template <bool FAST>
+__global__ void __launch_bounds__(256)
+nms_seg_mask_kernel(const float4* __restrict__ sboxes, const int32_t* __restrict__ scls, const uint64_t* __restrict__ okeys,
+                    const int32_t* __restrict__ meta, int stride, float thr, uint64_t* __restrict__ mask,
+                    uint64_t* __restrict__ lower, uint64_t* __restrict__ rowflags, int fw) {
+    const int n = meta[0];
+    const bool same_class_only = meta[1] == COIN_NMS_VANILLA;
+    const int rt = blockIdx.y;
+    if (rt * 64 >= n) return;
+    const int colblocks = (n + 63) >> 6;
+    const int r = threadIdx.x;
+    const int i = rt * 64 + r;
+    const int row_last = (int)(__ldg(okeys + min(rt * 64 + 63, n - 1)) >> 54);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int32_t cls_a = -1;
+    if (i < n) { a = __ldg(sboxes + i); cls_a = __ldg(scls + i); }
+    const float area_a = box_area(a);
+    __shared__ float4 cb[4][64];
+    __shared__ float ca[4][64];
+    __shared__ int32_t cc[4][64];
+    for (int cg = (rt >> 2) + blockIdx.x; cg * 4 < colblocks; cg += gridDim.x) {
+        const int ctf = max(cg * 4, rt);                                      // first column tile of the group that matters
+        if ((int)(__ldg(okeys + ctf * 64) >> 54) > row_last) break;           // CTA-uniform: no common class from here on
+        const int ct = cg * 4 + threadIdx.y;
+        __syncthreads();
+        {
+            const int j = ct * 64 + r;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            int32_t c = -1;
+            if (j < n) { b = __ldg(sboxes + j); c = __ldg(scls + j); }
+            cb[threadIdx.y][r] = b;
+            ca[threadIdx.y][r] = box_area(b);
+            cc[threadIdx.y][r] = c;
+        }
+        __syncthreads();
+        if (i >= n || ct >= colblocks || ct < rt) continue;
+        const int jn = min(64, n - ct * 64);
+        const bool diag = ct == rt;
+        uint64_t word = 0, low = 0;
+        for (int j = 0; j < jn; ++j) {
+            if (diag && j == r) continue;
+            const float4 b = cb[threadIdx.y][j];
+            bool hit;
+            if (FAST) {
+                const float w = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+                const float h = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+                if (!(w > 0.0f && h > 0.0f)) continue;     // empty intersection (or NaN): IoU is 0 or NaN
+                const float inter = w * h;
+                hit = inter / (area_a + ca[threadIdx.y][j] - inter) > thr;
+            } else {
+                hit = iou_tv(a, area_a, b, ca[threadIdx.y][j]) > thr;
+            }
+            if (hit && (!same_class_only || cc[threadIdx.y][j] == cls_a)) {
+                if (!diag || j > r) word |= 1ull << j; else low |= 1ull << j;
+            }
+        }
+        mask[(size_t)i * stride + ct] = word;
+        if (word) atomicOr(reinterpret_cast<unsigned long long*>(rowflags + (size_t)i * fw + (ct >> 6)), 1ull << (ct & 63));
+        if (diag) lower[i] = low;
+    }
+}
+
+// One CTA per class bucket: finds its segment [lo, hi) of the class-sorted sequence by binary search and sweeps the
+// segment's 64-row tiles exactly like nms_sweep_kernel (fixed-point iteration on the transposed diagonal words, kept rows
+// OR their flagged mask words into the shared `removed` vector), restricted to the rows of the segment. Tiles shared with
+// a neighbouring segment are visited by both CTAs, each with its own rows. Output: keptbits[tile] (atomicOr).
+__global__ void __launch_bounds__(256)
+nms_seg_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__ lower,
+                     const uint64_t* __restrict__ rowflags, int fw, const uint64_t* __restrict__ okeys,
+                     const int32_t* __restrict__ meta, int stride, uint64_t* __restrict__ keptbits) {
+    extern __shared__ uint64_t removed[];       // one word per tile of the segment
+    __shared__ int s_lo, s_hi;
+    __shared__ uint64_t s_kept;
+    const int n = meta[0];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 2) {                              // first position whose bucket is >= blockIdx.x + tid
+        const uint64_t want = (uint64_t)(blockIdx.x + tid);
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((__ldg(okeys + mid) >> 54) < want) lo = mid + 1; else hi = mid;
+        }
+        if (tid == 0) s_lo = lo; else s_hi = lo;
+    }
+    __syncthreads();
+    const int lo = s_lo, hi = s_hi;
+    if (lo >= hi) return;
+    const int t0 = lo >> 6, t1 = (hi - 1) >> 6;
+    for (int c = tid; c <= t1 - t0; c += blockDim.x) removed[c] = 0;
+    __syncthreads();
+    uint64_t low0 = 0, low1 = 0;
+    if (warp == 0) {
+        if (t0 * 64 + lane < n) low0 = lower[t0 * 64 + lane];
+        if (t0 * 64 + lane + 32 < n) low1 = lower[t0 * 64 + lane + 32];
+    }
+    for (int t = t0; t <= t1; ++t) {
+        const int base = t * 64;
+        if (warp == 0) {
+            const int rlo = max(lo - base, 0), rhi = min(hi - base, 64);      // the segment's rows of this tile
+            uint64_t valid = rhi >= 64 ? ~0ull : ((1ull << rhi) - 1ull);
+            valid &= ~((1ull << rlo) - 1ull);
+            const uint64_t cur = removed[t - t0] | ~valid;
+            const bool a0 = !((cur >> lane) & 1ull), a1 = !((cur >> (lane + 32)) & 1ull);
+            uint64_t kept = (uint64_t)__ballot_sync(0xffffffffu, a1) << 32 | __ballot_sync(0xffffffffu, a0);
+            while (true) {
+                const bool k0 = a0 && !(low0 & kept), k1 = a1 && !(low1 & kept);
+                const uint64_t nxt = (uint64_t)__ballot_sync(0xffffffffu, k1) << 32 | __ballot_sync(0xffffffffu, k0);
+                if (nxt == kept) break;
+                kept = nxt;
+            }
+            if (lane == 0) {
+                s_kept = kept;
+                if (kept) atomicOr(reinterpret_cast<unsigned long long*>(keptbits + t), (unsigned long long)kept);
+            }
+            low0 = low1 = 0;                                                   // next tile's diagonal words
+            if (t < t1) {
+                if (base + 64 + lane < n) low0 = lower[base + 64 + lane];
+                if (base + 96 + lane < n) low1 = lower[base + 96 + lane];
+            }
+        }
+        __syncthreads();
+        if (t < t1) {
+            const uint64_t kept = s_kept;
+            const int f0 = (t + 1) >> 6, f1 = t1 >> 6, nf = f1 - f0 + 1;
+            for (int w = tid; w < 64 * nf; w += blockDim.x) {
+                const int rr = w / nf, f = f0 + (w - rr * nf);
+                if (!((kept >> rr) & 1ull)) continue;
+                const size_t row = (size_t)base + rr;
+                uint64_t bits = rowflags[row * fw + f];
+                const int shift = t - f * 64 + 1;                              // clear the columns <= t
+                if (shift >= 64) bits = 0; else if (shift > 0) bits &= ~0ull << shift;
+                while (bits) {
+                    const int c = f * 64 + __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    if (c <= t1)
+                        atomicOr(reinterpret_cast<unsigned long long*>(&removed[c - t0]), (unsigned long long)mask[row * stride + c]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// kept positions -> keys ordered by (score desc, index) for the final sort; everything else becomes padding
+__global__ void seg_final_keys_kernel(const uint64_t* __restrict__ okeys, const uint64_t* __restrict__ keptbits,
+                                      const int32_t* __restrict__ meta, int total, uint64_t* __restrict__ ckeys,
+                                      int32_t* __restrict__ nkeep) {
+    const int n = meta[0];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool kept = false;
+    if (p < n) kept = (keptbits[p >> 6] >> (p & 63)) & 1ull;
+    if (p < total) ckeys[p] = kept ? (okeys[p] & kSegOrderMask) : ~0ull;
+    const int cnt = __popc(__ballot_sync(0xffffffffu, kept));
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(nkeep, cnt);
+}
+
+__global__ void COIN_SORT_BOUNDS
+chunk_sort_keys_kernel(uint64_t* __restrict__ ckeys, const int32_t* __restrict__ meta) {
+    extern __shared__ uint64_t skeys[];
+    const int base = blockIdx.x * kChunk;
+    if (base >= meta[0]) return;                 // only padding
+    for (int i = threadIdx.x; i < kChunk; i += blockDim.x) skeys[i] = ckeys[base + i];
+    __syncthreads();
+    bitonic_sort_smem<kSortThreads>(skeys, kChunk);
+    for (int i = threadIdx.x; i < kChunk; i += blockDim.x) ckeys[base + i] = skeys[i];
+}
+
+__global__ void merge_rank_keep_kernel(const uint64_t* __restrict__ ckeys, int nchunks, const int32_t* __restrict__ meta,
+                                       int64_t* __restrict__ keep) {
+    const int n = meta[0];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nchunks * kChunk) return;
+    const uint64_t key = ckeys[e];
+    if (key == ~0ull) return;                       // not kept / padding
+    const int g = e / kChunk;
+    int rank = e - g * kChunk;
+    const int live_chunks = (n + kChunk - 1) / kChunk;
+    for (int h = 0; h < live_chunks; ++h) {
+        if (h == g) continue;
+        const uint64_t* c = ckeys + (size_t)h * kChunk;
+        int lo = 0, hi = kChunk;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(c + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+    }
+    keep[rank] = (int64_t)(key & kSegIdxMask);
 }
 
 // 64 x (4*64) tile of the upper-triangular suppression mask per CTA; row-major [n][colblocks] so
@@ -488,7 +716,7 @@ nms_sweep_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__
 }
 
 struct NmsWs {
-    uint64_t *ckeys, *keptbits, *removed_g;
+    uint64_t *ckeys, *okeys, *keptbits, *removed_g;
     int32_t* state;
     uint32_t *keys, *keys_alt, *vals, *vals_alt;
     void* cub_tmp;
@@ -524,13 +752,15 @@ static NmsWs carve_nms(void* ws, int64_t n) {
     w.keys = w.keys_alt = w.vals = w.vals_alt = nullptr;
     w.cub_tmp = nullptr;
     w.cub_bytes = 0;
-    w.ckeys = nullptr;
+    w.ckeys = w.okeys = nullptr;
     w.state = c.take<int32_t>(64);
     w.keptbits = c.take<uint64_t>((size_t)colblocks);
     w.removed_g = c.take<uint64_t>((size_t)colblocks);
-    if (n > kSmallSort && n <= (int64_t)kChunk * kMaxChunks) {
+    if (n >= kSegMinAlloc && n <= (int64_t)kChunk * kMaxChunksSeg) {
         w.ckeys = c.take<uint64_t>((size_t)ceil_div(n, kChunk) * kChunk);
-    } else if (n > kSmallSort) {
+        w.okeys = c.take<uint64_t>((size_t)n);
+    }
+    if (n > (int64_t)kChunk * kMaxChunks) {
         w.keys = c.take<uint32_t>((size_t)n);
         w.keys_alt = c.take<uint32_t>((size_t)n);
         w.vals = c.take<uint32_t>((size_t)n);
@@ -563,20 +793,60 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
     const int n = (int)n_cap;
     const int colblocks = (int)ceil_div(n_cap, 64);
     const float4* b4 = reinterpret_cast<const float4*>(boxes);
+    const float thr_f = round_down_to_float(thr);
+    const int fw = (int)ceil_div(colblocks, 64);
+    // class-segmented pipeline: per-class NMS of many boxes with no keep[:k] cut (COIN_NMS_SEG_MIN: smallest n that takes it)
+    const bool segmented = idxs && strategy != COIN_NMS_PLAIN && max_keep < 0 && w.okeys &&
+                           n >= option("COIN_NMS_SEG_MIN", 3500);
+    if (segmented) {
+        const int nchunks = (int)ceil_div(n, kChunk);
+        fill_bytes(w.meta, 0, 64 * sizeof(int32_t), s);
+        fill_bytes(w.max_coord, 0x80, sizeof(int), s);
+        fill_bytes(w.keptbits, 0, (size_t)colblocks * sizeof(uint64_t), s);
+        fill_bytes(w.rowflags, 0, (size_t)n * fw * sizeof(uint64_t), s);
+        fill_bytes(nkeep, 0, sizeof(int32_t), s);
+        seg_class_range_kernel<<<kNumSMs, 256, 0, s>>>(idxs, n, n_dev, w.meta);
+        if (int rc = check_launch("seg_class_range_kernel")) return rc;
+        chunk_sort_kernel<<<nchunks, kSortThreads, kChunk * sizeof(uint64_t), s>>>(scores, b4, n, n_dev, strategy, w.ckeys,
+                                                                           w.max_coord, w.meta, idxs);
+        if (int rc = check_launch("chunk_sort_kernel")) return rc;
+        merge_rank_gather_kernel<<<(unsigned)ceil_div((int64_t)nchunks * kChunk, 256), 256, 0, s>>>(
+            w.ckeys, nchunks, b4, idxs, w.meta, w.max_coord, w.sboxes, w.scls, w.order, w.okeys);
+        if (int rc = check_launch("merge_rank_gather_kernel")) return rc;
+        const dim3 grid((unsigned)std::min(8, (int)ceil_div(colblocks, 4)), (unsigned)colblocks), block(64, 4);
+        if (thr_f >= 0.0f)
+            nms_seg_mask_kernel<true><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.okeys, w.meta, colblocks, thr_f, w.mask, w.lower,
+                                                             w.rowflags, fw);
+        else
+            nms_seg_mask_kernel<false><<<grid, block, 0, s>>>(w.sboxes, w.scls, w.okeys, w.meta, colblocks, thr_f, w.mask, w.lower,
+                                                              w.rowflags, fw);
+        if (int rc = check_launch("nms_seg_mask_kernel")) return rc;
+        const size_t smem = (size_t)colblocks * sizeof(uint64_t);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(nms_seg_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        nms_seg_sweep_kernel<<<kSegBuckets, 256, smem, s>>>(w.mask, w.lower, w.rowflags, fw, w.okeys, w.meta, colblocks, w.keptbits);
+        if (int rc = check_launch("nms_seg_sweep_kernel")) return rc;
+        const int total = nchunks * kChunk;
+        seg_final_keys_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(w.okeys, w.keptbits, w.meta, total, w.ckeys, nkeep);
+        if (int rc = check_launch("seg_final_keys_kernel")) return rc;
+        chunk_sort_keys_kernel<<<nchunks, kSortThreads, kChunk * sizeof(uint64_t), s>>>(w.ckeys, w.meta);
+        if (int rc = check_launch("chunk_sort_keys_kernel")) return rc;
+        merge_rank_keep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(w.ckeys, nchunks, w.meta, keep);
+        return check_launch("merge_rank_keep_kernel");
+    }
     if (n <= kSmallSort) {
         int npow = 1;
         while (npow < n) npow <<= 1;
         small_sort_gather_kernel<<<1, kSortThreads, npow * sizeof(uint64_t), s>>>(scores, b4, idxs, n, n_dev, strategy, w.sboxes,
                                                                           w.scls, w.order, w.meta);
         if (int rc = check_launch("small_sort_gather_kernel")) return rc;
-    } else if (w.ckeys) {
+    } else if (n <= kChunk * kMaxChunks) {
         const int nchunks = (int)ceil_div(n, kChunk);
         fill_bytes(w.max_coord, 0x80, sizeof(int), s);  // 0x80808080 decodes to ~ -3.4e38
         chunk_sort_kernel<<<nchunks, kSortThreads, kChunk * sizeof(uint64_t), s>>>(scores, b4, n, n_dev, strategy, w.ckeys,
-                                                                           w.max_coord, w.meta);
+                                                                           w.max_coord, w.meta, nullptr);
         if (int rc = check_launch("chunk_sort_kernel")) return rc;
         merge_rank_gather_kernel<<<(unsigned)ceil_div((int64_t)nchunks * kChunk, 256), 256, 0, s>>>(
-            w.ckeys, nchunks, b4, idxs, w.meta, w.max_coord, w.sboxes, w.scls, w.order);
+            w.ckeys, nchunks, b4, idxs, w.meta, w.max_coord, w.sboxes, w.scls, w.order, nullptr);
         if (int rc = check_launch("merge_rank_gather_kernel")) return rc;
     } else {
         make_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(scores, n, n_dev, strategy, w.keys, w.vals, w.meta);
@@ -595,8 +865,6 @@ int nms_sorted_pipeline(const float* boxes, const float* scores, const int64_t* 
                                                                         w.sboxes, w.scls, w.order);
         if (int rc = check_launch("gather_sorted_kernel")) return rc;
     }
-    const float thr_f = round_down_to_float(thr);
-    const int fw = (int)ceil_div(colblocks, 64);
     fill_bytes(w.rowflags, 0, (size_t)n * fw * sizeof(uint64_t), s);
     const size_t smem = (size_t)colblocks * sizeof(uint64_t);
     if (smem > 48 * 1024) cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -460,9 +460,10 @@ roi_align_fwd_reg_kernel(const RoiParams p, T* __restrict__ out, const int cgrou
     T* tile = reinterpret_cast<T*>(tile_raw);            // (>= 4 KB: it doubles as tap-table scratch while the tables are built)
     __shared__ RegTables<NU> tb;
 
-    const int k = blockIdx.x / cgroups;
-    if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
-    const int cg0 = (blockIdx.x - k * cgroups) * (CC * slabs);
+    const int kk = blockIdx.x / cgroups;
+    if (p.k_dev && kk >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
+    const int k = p.perm ? __ldg(p.perm + kk) : kk;   // launch order (coin_roi_launch_order): small RoIs last
+    const int cg0 = (blockIdx.x - kk * cgroups) * (CC * slabs);
     const int lane = threadIdx.x & 31, u = threadIdx.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
     const coin_level_t L = p.lv[lvl];
@@ -641,9 +642,10 @@ roi_align_bwd_reg_kernel(const RoiParams p, const T* __restrict__ go, const int 
     __shared__ RegTables<NU> tb;
     __shared__ __align__(8) uint64_t bar_full;
 
-    const int k = blockIdx.x / cgroups;
-    if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
-    const int cg0 = (blockIdx.x - k * cgroups) * (32 * slabs);
+    const int kk = blockIdx.x / cgroups;
+    if (p.k_dev && kk >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
+    const int k = p.perm ? __ldg(p.perm + kk) : kk;   // launch order (coin_roi_launch_order): small RoIs last
+    const int cg0 = (blockIdx.x - kk * cgroups) * (32 * slabs);
     const int lane = threadIdx.x & 31, u = threadIdx.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
     const coin_level_t L = p.lv[lvl];

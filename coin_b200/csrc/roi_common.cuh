@@ -11,6 +11,7 @@ struct RoiParams {
     const float* rois;
     const int32_t* roi_level;
     const int32_t* k_dev;   // optional device-side live RoI count (<= K): CTAs of RoIs beyond it exit
+    const int32_t* perm;    // optional launch order (coin_roi_launch_order): CTA group i works on RoI perm[i]
     int C, K, PH, PW, sampling_ratio, aligned;
     int flags;              // bit 0: L2-prefetch the next unit's grad_out rows (backward)
 };

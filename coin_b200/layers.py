@@ -31,19 +31,22 @@ class _ROIAlignFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rois, levels, output_size, scales, sampling_ratio, aligned, *feats):
         nhwc = [ops.to_nhwc_f32(f) for f in feats]
-        out = ops.roi_align_forward(nhwc, scales, rois, levels, output_size, sampling_ratio, aligned, feats[0].dtype)
-        ctx.save_for_backward(rois, levels if levels is not None else torch.empty(0))
-        ctx.has_levels = levels is not None
+        perm = ops.roi_launch_order(rois)     # scheduling only: the smallest RoIs are launched last
+        out = ops.roi_align_forward(nhwc, scales, rois, levels, output_size, sampling_ratio, aligned, feats[0].dtype,
+                                    perm=perm)
+        ctx.save_for_backward(rois, levels if levels is not None else torch.empty(0),
+                              perm if perm is not None else torch.empty(0))
+        ctx.has_levels, ctx.has_perm = levels is not None, perm is not None
         ctx.meta = (output_size, tuple(scales), sampling_ratio, aligned, [tuple(f.shape) for f in feats],
                     [f.dtype for f in feats])
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        rois, levels = ctx.saved_tensors
+        rois, levels, perm = ctx.saved_tensors
         output_size, scales, sampling_ratio, aligned, shapes, dtypes = ctx.meta
         grads = ops.roi_align_backward(grad_out, shapes, scales, rois, levels if ctx.has_levels else None, output_size,
-                                       sampling_ratio, aligned, dtypes)
+                                       sampling_ratio, aligned, dtypes, perm=perm if ctx.has_perm else None)
         return (None, None, None, None, None, None, *grads)
 
 

@@ -107,12 +107,30 @@ def _levels(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float]):
     return arr
 
 
+ORDER_MAX_ROIS = 8192          # coin_roi_launch_order's limit
+ORDER_MIN_ROIS = 512           # below ~1 wave of CTAs there is no tail to fill
+
+
+def roi_launch_order(rois: torch.Tensor, k_dev: Optional[torch.Tensor] = None, small_pct: int = 20) -> Optional[torch.Tensor]:
+    """Launch order for roi_align_forward / roi_align_backward over the same ``rois`` (scheduling only): the smallest
+    ``small_pct`` % of the RoIs go last. Returns None where ordering does not pay (few or very many RoIs)."""
+    rois = _f32c(rois, "rois")
+    k = rois.shape[0]
+    if k < ORDER_MIN_ROIS or k > ORDER_MAX_ROIS or small_pct <= 0:
+        return None
+    perm = torch.empty((k,), dtype=torch.int32, device=rois.device)
+    check(lib.coin_roi_launch_order(_ptr(rois), k, _ptr(None if k_dev is None else _count(k_dev)), int(small_pct),
+                                    _ptr(perm), _stream()))
+    return perm
+
+
 def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
                       roi_level: Optional[torch.Tensor], output_size: Tuple[int, int], sampling_ratio: int,
                       aligned: bool, out_dtype: torch.dtype, events: Optional[list] = None,
-                      k_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      k_dev: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """events: optional list; a (start, end) CUDA-event pair bracketing the kernel launch is appended.
-    k_dev: optional device int32 live RoI count (<= K): rows of the result beyond it are not written."""
+    k_dev: optional device int32 live RoI count (<= K): rows of the result beyond it are not written.
+    perm: optional launch order from ``roi_launch_order`` (same rois)."""
     rois = _f32c(rois, "rois")
     if rois.dim() != 2 or rois.shape[1] != 5:
         raise ValueError(f"coin_b200: rois must have shape [K, 5], got {tuple(rois.shape)}")
@@ -122,7 +140,12 @@ def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float
     if roi_level is not None:
         roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
     pair = _event_pair(events)
-    if k_dev is None:
+    if perm is not None:
+        check(lib.coin_roi_align_fwd_ord(_levels(feats_nhwc, scales), len(feats_nhwc), _ptr(rois), _ptr(roi_level),
+                                         _ptr(out), _dtype_code(out_dtype), c, k, ph, pw, int(sampling_ratio),
+                                         int(bool(aligned)), _ptr(None if k_dev is None else _count(k_dev)),
+                                         _ptr(perm), _stream()))
+    elif k_dev is None:
         check(lib.coin_roi_align_fwd(_levels(feats_nhwc, scales), len(feats_nhwc), _ptr(rois), _ptr(roi_level),
                                      _ptr(out), _dtype_code(out_dtype), c, k, ph, pw, int(sampling_ratio),
                                      int(bool(aligned)), _stream()))
@@ -137,7 +160,7 @@ def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float
 def roi_align_backward(grad_out: torch.Tensor, shapes: Sequence[Tuple[int, int, int, int]], scales: Sequence[float],
                        rois: torch.Tensor, roi_level: Optional[torch.Tensor], output_size: Tuple[int, int],
                        sampling_ratio: int, aligned: bool, out_dtypes: Sequence[torch.dtype],
-                       events: Optional[list] = None) -> List[torch.Tensor]:
+                       events: Optional[list] = None, perm: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
     """Returns one NCHW gradient per level (shape ``shapes[i]`` = (N,C,H,W), dtype ``out_dtypes[i]``)."""
     grad_out = _cuda(grad_out, "grad_out").contiguous()
     rois = _f32c(rois, "rois")
@@ -147,9 +170,9 @@ def roi_align_backward(grad_out: torch.Tensor, shapes: Sequence[Tuple[int, int, 
     if roi_level is not None:
         roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
     pair = _event_pair(events)
-    check(lib.coin_roi_align_bwd(_levels(bufs, scales), len(bufs), _ptr(rois), _ptr(roi_level), _ptr(grad_out),
-                                 _dtype_code(grad_out.dtype), c, k, ph, pw, int(sampling_ratio), int(bool(aligned)),
-                                 _stream()))
+    check(lib.coin_roi_align_bwd_ord(_levels(bufs, scales), len(bufs), _ptr(rois), _ptr(roi_level), _ptr(grad_out),
+                                     _dtype_code(grad_out.dtype), c, k, ph, pw, int(sampling_ratio), int(bool(aligned)),
+                                     _ptr(perm), _stream()))
     _event_close(pair)
     outs = []
     for buf, (n, cc, h, w), dt in zip(bufs, shapes, out_dtypes):

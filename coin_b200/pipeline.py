@@ -84,6 +84,8 @@ class RoIPathStep:
         self.roi_carveout = int(os.environ.get("COIN_STEP_ROI_CARVEOUT", "-1"))
         self.c_mode = os.environ.get("COIN_STEP_C_MODE", "with_bwd")        # side | between | with_bwd (see _run_static)
         self.c_reg_mink = int(os.environ.get("COIN_STEP_C_REG_MINK", "0"))  # 0: register-tile kernel for the C boxes
+        # launch order of the two big ROIAlign grids: the smallest p % of the RoIs go last (ops.roi_launch_order), 0: off
+        self.roi_tail_pct = int(os.environ.get("COIN_STEP_ROI_TAIL_PCT", "20"))
         self.overlap = True         # issue independent stages on side streams (False: everything on the caller's stream)
         self.timeline = None        # tools/step_timeline.py: dict name -> external CUDA event recorded in the graph
         self.kernel_events = None   # bench.py: {"fwd": [], "bwd": []} to time the two dominant kernels live
@@ -160,13 +162,14 @@ class RoIPathStep:
             nhwc = ops.to_nhwc_f32(d["features"])
             rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
                               for i in range(n_img)])
+            perm = ops.roi_launch_order(rois, small_pct=self.roi_tail_pct)
             out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
-                                                  events=ev["fwd"] if ev else None)
+                                                  events=ev["fwd"] if ev else None, perm=perm)
             if backward:
                 n, c, h, w = d["features"].shape
                 out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
                                                               0, True, [self.io_dtype],
-                                                              events=ev["bwd"] if ev else None)[0]
+                                                              events=ev["bwd"] if ev else None, perm=perm)[0]
 
         # ---- teacher branch and RPN NMS: one stream per image and chain, no host sync inside the loop
         dets, cloud_boxes, rpn = [None] * n_img, [None] * n_img, [None] * n_img
@@ -287,11 +290,15 @@ class RoIPathStep:
             counts.append(t.view(-1))
 
         self._mark("start")
-        with torch.cuda.stream(s_roi):
-            nhwc = ops.to_nhwc_f32(d["features"])
+        with torch.cuda.stream(s_img[2 * n_img]):     # (this stream's chain starts only after knowledge separation)
             rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
                               for i in range(n_img)])
+            perm = ops.roi_launch_order(rois, small_pct=self.roi_tail_pct)   # beside the layout transform below
+            rois_ready = s_img[2 * n_img].record_event()
+        with torch.cuda.stream(s_roi):
+            nhwc = ops.to_nhwc_f32(d["features"])
             nhwc_ready = s_roi.record_event()
+            s_roi.wait_event(rois_ready)
 
         # ---- teacher detections (T1-T3) and RPN NMS (S1): one stream per image and chain
         clouds, clips, ndets, det_done, gate = [], [], [], [], []
@@ -337,7 +344,7 @@ class RoIPathStep:
             self._mark("roi.begin_fwd")
             ev = self.kernel_events
             out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
-                                                  events=ev["fwd"] if ev else None)
+                                                  events=ev["fwd"] if ev else None, perm=perm)
             self._mark("roi.end_fwd")
             fwd_done = s_roi.record_event()
 
@@ -346,7 +353,7 @@ class RoIPathStep:
                 n, c, h, w = d["features"].shape
                 out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
                                                               0, True, [self.io_dtype],
-                                                              events=ev["bwd"] if ev else None)[0]
+                                                              events=ev["bwd"] if ev else None, perm=perm)[0]
                 self._mark("roi.end_bwd")
         if backward and self.c_mode != "between":
             run_backward()
@@ -467,11 +474,12 @@ class RoIPathStep:
                           for i in range(sh.images)])
         n, c, h, w = d["features"].shape
         size, scale = (sh.pooled, sh.pooled), (1.0 / sh.stride,)
+        perm = ops.roi_launch_order(rois, small_pct=self.roi_tail_pct)     # as in the step (its own small launch)
         for it in range(warmup + iters):
             ev = events if it >= warmup else {"fwd": None, "bwd": None}
-            ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32, events=ev["fwd"])
+            ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32, events=ev["fwd"], perm=perm)
             ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size, 0, True, [torch.float32],
-                                   events=ev["bwd"])
+                                   events=ev["bwd"], perm=perm)
 
     # -- CUDA graph ---------------------------------------------------------------------------------
     def capture(self, d: Dict[str, torch.Tensor], backward: bool = True, warmup: int = 2, keep_graph: bool = False):

@@ -6,7 +6,7 @@ import torch
 import torchvision
 
 import coin_b200
-from coin_b200 import ops, pipeline, synth
+from coin_b200 import _lib, ops, pipeline, synth
 from oracle import clib, d2_ref, pipeline_ref
 
 pytestmark = pytest.mark.gpu
@@ -49,7 +49,7 @@ def _clipart_boxes(n, seed):
     return boxes, scores, idxs
 
 
-@pytest.mark.parametrize("n", [1000, 3000, 10000, 30000])
+@pytest.mark.parametrize("n", [1000, 3000, 10000, 30000, 100000])
 def test_sweep_batched_nms_20_classes_vs_oracle(dev, n):
     """configs[4]: batched NMS, 20 classes (Clipart), thr 0.5, against the torchvision-CPU restatement."""
     boxes, scores, idxs = _clipart_boxes(n, 100 + n)
@@ -58,6 +58,42 @@ def test_sweep_batched_nms_20_classes_vs_oracle(dev, n):
     assert torch.equal(out.cpu(), ref)
     plain = coin_b200.nms(boxes.to(dev), scores.to(dev), 0.5)
     assert torch.equal(plain.cpu(), clib.nms(boxes, scores, 0.5))
+
+
+@pytest.mark.parametrize("case", ["wide_ids", "negative_ids", "trick", "one_class", "ragged", "ties"])
+def test_segmented_batched_nms_edge_cases(dev, case):
+    """The class-segmented pipeline (nms.cu, n >= 6000, no max_keep): class ids that do not fit a bucket and the
+    coordinate-trick strategy fold into one segment; classes of very different sizes; segments that share 64-row tiles;
+    exact score ties inside a class (stable: lower index first, the oracle's policy)."""
+    n = 9000
+    boxes, scores, idxs = _clipart_boxes(n, 4242)
+    strategy = "auto"
+    if case == "wide_ids":
+        idxs = idxs * 977 + 1500                                   # >= 1024: no bucket
+    elif case == "negative_ids":
+        idxs = idxs - 7
+    elif case == "trick":
+        strategy = "trick"
+    elif case == "one_class":
+        idxs = torch.full_like(idxs, 3)
+    elif case == "ragged":                                         # 1 huge class, many tiny ones (several per 64-row tile)
+        g = synth.gen(5)
+        idxs = torch.where(torch.rand(n, generator=g) < 0.7, torch.zeros(n, dtype=torch.int64),
+                           torch.randint(1, 1000, (n,), generator=g))
+    elif case == "ties":
+        scores = (scores * 50).floor() / 50
+    if strategy == "trick":
+        ref = clib.nms(boxes + idxs[:, None].float() * (boxes.max() + 1), scores, 0.5)
+    elif case == "ties":
+        ref = None      # torchvision's per-class path sorts the kept scores unstably: the dense pipeline below is the check
+    else:
+        ref = d2_ref.batched_nms(boxes, scores, idxs, 0.5)
+    out = ops.batched_nms(boxes.to(dev), scores.to(dev), idxs.to(dev), 0.5, strategy)
+    if ref is not None:
+        assert torch.equal(out.cpu(), ref)
+    with _lib.options(COIN_NMS_SEG_MIN=1 << 30):
+        dense = ops.batched_nms(boxes.to(dev), scores.to(dev), idxs.to(dev), 0.5, strategy)
+    assert torch.equal(out, dense)
 
 
 def test_sweep_nms_100k_properties(dev):

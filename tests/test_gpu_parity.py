@@ -184,6 +184,44 @@ def test_roi_align_register_tile_full_size(dev):
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
 
 
+@pytest.mark.parametrize("k,live", [(1536, None), (700, 523), (8192, None)])
+def test_roi_launch_order_is_a_permutation_and_changes_nothing(dev, k, live):
+    """coin_roi_launch_order: perm is a permutation of the live RoIs with the smallest 20 % (by area) last, both parts in
+    input order; entries beyond a device-side live count are the identity; the register-tile kernels launched in that
+    order return the same forward bit for bit and the same backward up to the order of the fp32 atomics."""
+    g = synth.gen(311 + k)
+    boxes = synth.random_boxes(g, k, 600, 1200)
+    boxes[5] = boxes[9]                                    # exact area tie
+    boxes[11, 2] = boxes[11, 0] - 3.0                      # inverted box: counts as the smallest
+    rois = torch.cat((torch.randint(0, 2, (k, 1), generator=g).float(), boxes), 1).to(dev)
+    kd = None if live is None else torch.tensor([live], dtype=torch.int32, device=dev)
+    perm = ops.roi_launch_order(rois, kd, 20)
+    n = k if live is None else live
+    p = perm.cpu().long()
+    assert torch.equal(p[n:], torch.arange(n, k))
+    assert torch.equal(p[:n].sort().values, torch.arange(n))
+    w, h = boxes[:n, 2] - boxes[:n, 0], boxes[:n, 3] - boxes[:n, 1]
+    area = torch.where((w > 0) & (h > 0), w * h, torch.zeros(()))
+    want = n * 20 // 100
+    thr = area.sort().values[want - 1]
+    small = area <= thr
+    idx = torch.arange(n)
+    assert torch.equal(p[:n], torch.cat((idx[~small], idx[small])))
+    if k > 2048:
+        return
+    x = torch.randn(2, 64, 37, 75, generator=g).to(dev)
+    nhwc = ops.to_nhwc_f32(x)
+    a = ops.roi_align_forward([nhwc], (1 / 16,), rois, None, (14, 14), 0, True, torch.float32, k_dev=kd)
+    b = ops.roi_align_forward([nhwc], (1 / 16,), rois, None, (14, 14), 0, True, torch.float32, k_dev=kd, perm=perm)
+    assert torch.equal(a[:n], b[:n])
+    if live is None:
+        go = torch.randn(a.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+        ga = ops.roi_align_backward(go, [tuple(x.shape)], (1 / 16,), rois, None, (14, 14), 0, True, [torch.float32])[0]
+        gb = ops.roi_align_backward(go, [tuple(x.shape)], (1 / 16,), rois, None, (14, 14), 0, True, [torch.float32],
+                                    perm=perm)[0]
+        assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max())
+
+
 def test_roi_align_non_finite_features(dev):
     """Inf / NaN cells in the feature map (fp16 overflow under AMP). torchvision multiplies a cell only when it is one of
     the 4 taps of a sample, so only RoIs that sample the cell turn non-finite. Contract of this library:
