@@ -31,15 +31,36 @@ FORMAT_VERSION = 1
 
 class _D2Unpickler(pickle.Unpickler):
     """Maps the two detectron2 classes inside the reference's files onto their mirrors (same attribute layout:
-    ``Instances._image_size / _fields``, ``Boxes.tensor``); everything else resolves as usual."""
+    ``Instances._image_size / _fields``, ``Boxes.tensor``). Everything else must be on a short allowlist - the tensor
+    rebuild helpers ``torch.save`` emits and plain containers / scalars: a pickle can name ANY importable callable, and a
+    collected-detections file is data, so an unknown global is refused instead of imported."""
     _MAP = {("detectron2.structures.instances", "Instances"): Instances,
             ("detectron2.structures.boxes", "Boxes"): Boxes,
             ("detectron2.structures", "Instances"): Instances,
             ("detectron2.structures", "Boxes"): Boxes}
+    _ALLOWED = {
+        "collections": {"OrderedDict", "defaultdict"},
+        "builtins": {"dict", "list", "tuple", "set", "frozenset", "int", "float", "bool", "str", "bytes", "complex",
+                     "slice", "range", "bytearray"},
+        "torch._utils": {"_rebuild_tensor_v2", "_rebuild_tensor", "_rebuild_parameter", "_rebuild_qtensor"},
+        "torch": {"Size", "device", "dtype", "float32", "float64", "float16", "bfloat16", "int64", "int32", "int16",
+                  "int8", "uint8", "bool", "FloatStorage", "DoubleStorage", "HalfStorage", "BFloat16Storage",
+                  "LongStorage", "IntStorage", "ShortStorage", "CharStorage", "ByteStorage", "BoolStorage"},
+        "torch.storage": {"_load_from_bytes", "TypedStorage", "UntypedStorage"},
+        "numpy": {"dtype", "ndarray"},
+        "numpy.core.multiarray": {"_reconstruct", "scalar"},
+        "numpy._core.multiarray": {"_reconstruct", "scalar"},
+    }
 
     def find_class(self, module: str, name: str):
         hit = self._MAP.get((module, name))
-        return hit if hit is not None else super().find_class(module, name)
+        if hit is not None:
+            return hit
+        if name in self._ALLOWED.get(module, ()):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(
+            f"coin_b200.cache: refusing to load global {module}.{name} from a detections file "
+            "(only tensors, plain containers and detectron2 Instances / Boxes are expected)")
 
 
 class _D2Pickle:
@@ -74,21 +95,27 @@ def load_reference_results(path: str) -> Dict[str, Dict[str, dict]]:
 class _TagStore:
     """Flat arrays of one tag: image i owns rows offsets[i] : offsets[i + 1]."""
 
-    def __init__(self, offsets, boxes, scores, classes, probs, image_sizes, present):
+    def __init__(self, offsets, boxes, scores, classes, probs, image_sizes, present, probs_width=None):
         self.offsets, self.boxes, self.scores, self.classes, self.probs = offsets, boxes, scores, classes, probs
         self.image_sizes, self.present = image_sizes, present   # [n, 2] (h, w) of the Instances; [n] bool
+        # [n] width of the image's own `probs` field (0: the Instances had none): the flat array is padded to the widest
+        # one, and a lookup must not hand out columns (or a whole field) the collector never wrote
+        self.probs_width = (probs_width if probs_width is not None
+                            else torch.where(present, int(probs.shape[1]), 0).to(torch.int64))
 
     def to(self, device) -> "_TagStore":
         return _TagStore(self.offsets, self.boxes.to(device), self.scores.to(device), self.classes.to(device),
-                         self.probs.to(device), self.image_sizes, self.present)
+                         self.probs.to(device), self.image_sizes, self.present, self.probs_width)
 
     def state(self) -> Dict[str, torch.Tensor]:
         return {"offsets": self.offsets, "boxes": self.boxes.cpu(), "scores": self.scores.cpu(), "classes": self.classes.cpu(),
-                "probs": self.probs.cpu(), "image_sizes": self.image_sizes, "present": self.present}
+                "probs": self.probs.cpu(), "image_sizes": self.image_sizes, "present": self.present,
+                "probs_width": self.probs_width}
 
     @classmethod
     def from_state(cls, st: Dict[str, torch.Tensor]) -> "_TagStore":
-        return cls(st["offsets"], st["boxes"], st["scores"], st["classes"], st["probs"], st["image_sizes"], st["present"])
+        return cls(st["offsets"], st["boxes"], st["scores"], st["classes"], st["probs"], st["image_sizes"], st["present"],
+                   st.get("probs_width"))
 
 
 class DetectionCache:
@@ -127,7 +154,9 @@ class DetectionCache:
         for i in insts:
             if i is not None and i.has("probs") and i.probs.dim() == 2:
                 k1 = max(k1, i.probs.shape[1])
-        counts = [0 if i is None else len(i) for i in insts]
+        def _len(i):      # an Instances without any field has no length (len() raises): it holds no detections
+            return 0 if i is None or not i.get_fields() else len(i)
+        counts = [_len(i) for i in insts]
         offsets = torch.zeros(len(insts) + 1, dtype=torch.int64)
         offsets[1:] = torch.tensor(counts, dtype=torch.int64).cumsum(0) if insts else offsets[1:]
         total = int(offsets[-1])
@@ -137,21 +166,26 @@ class DetectionCache:
         probs = torch.zeros((total, k1), dtype=torch.float32)
         image_sizes = torch.zeros((len(insts), 2), dtype=torch.int64)
         present = torch.zeros((len(insts),), dtype=torch.bool)
+        probs_width = torch.zeros((len(insts),), dtype=torch.int64)
         for j, inst in enumerate(insts):
             if inst is None:
                 continue
             present[j] = True
             image_sizes[j] = torch.tensor([int(inst.image_size[0]), int(inst.image_size[1])])
+            if not inst.get_fields():
+                continue
             a, b = int(offsets[j]), int(offsets[j + 1])
+            if inst.has("probs") and inst.probs.dim() == 2:
+                probs_width[j] = int(inst.probs.shape[1])
             if b == a:
                 continue
             bx = inst.pred_boxes.tensor if isinstance(inst.pred_boxes, Boxes) else inst.pred_boxes
             boxes[a:b] = bx.detach().to("cpu", torch.float32)
             scores[a:b] = inst.scores.detach().to("cpu", torch.float32)
             classes[a:b] = inst.pred_classes.detach().to("cpu", torch.int64)
-            if k1 and inst.has("probs"):
+            if int(probs_width[j]):
                 probs[a:b, : inst.probs.shape[1]] = inst.probs.detach().to("cpu", torch.float32)
-        return _TagStore(offsets, boxes, scores, classes, probs, image_sizes, present)
+        return _TagStore(offsets, boxes, scores, classes, probs, image_sizes, present, probs_width)
 
     @classmethod
     def load_reference(cls, path: str, dataset_name: Optional[str] = None, device=None) -> "DetectionCache":
@@ -216,8 +250,9 @@ class DetectionCache:
         inst.pred_boxes = Boxes(st.boxes[a:b])
         inst.scores = st.scores[a:b]
         inst.pred_classes = st.classes[a:b]
-        if st.probs.shape[1]:
-            inst.probs = st.probs[a:b]
+        kw = int(st.probs_width[i])
+        if kw:
+            inst.probs = st.probs[a:b] if kw == st.probs.shape[1] else st.probs[a:b, :kw]
         return inst
 
     def entry(self, file_name: str) -> Dict[str, Any]:
@@ -262,8 +297,9 @@ class DetectionCache:
         inst.pred_boxes = Boxes(st.boxes[a:b].cpu())
         inst.scores = st.scores[a:b].cpu()
         inst.pred_classes = st.classes[a:b].cpu()
-        if st.probs.shape[1]:
-            inst.probs = st.probs[a:b].cpu()
+        kw = int(st.probs_width[i])
+        if kw:
+            inst.probs = st.probs[a:b, :kw].cpu()
         return inst
 
     def nbytes(self) -> int:

@@ -9,6 +9,11 @@
 //
 // Order of the members of a cluster is the reference's: matched boxes in sweep order, the pivot
 // last (nms.py:130-133); sums run sequentially in that order.
+//
+// Up to 4096 boxes (every call COIN makes: <= 900 GDINO queries per pass) the working set lives in shared memory. Above
+// that - the reference takes up to 39 999 boxes in one batched call and unbounded per-class subsets beyond (nms.py:213-238)
+// - the same kernel runs with its arrays in the caller's workspace (template parameter): still one launch and one CTA,
+// tens of milliseconds at 40 000 boxes, where the reference's Python loop needs seconds.
 #include "common.cuh"
 
 namespace coin {
@@ -29,6 +34,13 @@ struct FusionArgs {
     int64_t* out_classes;
     int32_t* nkeep;
     int32_t* status;
+    // working set of the large-n variant (the small one keeps these in shared memory)
+    uint64_t* g_keys;    // [npow]
+    float4* g_nbox;      // [n]
+    float* g_area;       // [n]
+    float* g_sscore;     // [n]
+    int32_t* g_src;      // [n]
+    int32_t* g_alive;    // [n]
     // global scratch
     int32_t* cid;        // [n] sorted position of the pivot owning each sorted position
     int32_t* pivots;     // [n] sorted positions of the pivots, sweep order
@@ -61,17 +73,18 @@ __device__ void bitonic_sort_smem(uint64_t* keys, int npow) {
     }
 }
 
+template <bool GLOBAL>
 __global__ void __launch_bounds__(1024) fusion_nms_kernel(const FusionArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const int n = a.n, k1 = a.k1;
     int npow = 2;
     while (npow < n) npow <<= 1;
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);            // [npow]
-    float4* nbox = reinterpret_cast<float4*>(keys + npow);             // [n] offset boxes, sorted order
-    float* area = reinterpret_cast<float*>(nbox + n);                  // [n]
-    float* sscore = area + n;                                          // [n] score, sorted order
-    int32_t* src = reinterpret_cast<int32_t*>(sscore + n);             // [n] original index
-    int32_t* alive = src + n;                                          // [n]
+    uint64_t* keys = GLOBAL ? a.g_keys : reinterpret_cast<uint64_t*>(smem_raw);       // [npow]
+    float4* nbox = GLOBAL ? a.g_nbox : reinterpret_cast<float4*>(keys + npow);         // [n] offset boxes, sorted order
+    float* area = GLOBAL ? a.g_area : reinterpret_cast<float*>(nbox + n);              // [n]
+    float* sscore = GLOBAL ? a.g_sscore : area + n;                                    // [n] score, sorted order
+    int32_t* src = GLOBAL ? a.g_src : reinterpret_cast<int32_t*>(sscore + n);          // [n] original index
+    volatile int32_t* alive = GLOBAL ? a.g_alive : src + n;                            // [n]
     __shared__ float s_red[32];
     __shared__ int s_next, s_npiv;
 
@@ -143,18 +156,25 @@ __global__ void __launch_bounds__(1024) fusion_nms_kernel(const FusionArgs a) {
     __syncthreads();
     const int npiv = s_npiv;
 
-    // 4. fuse every cluster: one thread per pivot walks the sorted positions (members in sweep order)
-    for (int c = threadIdx.x; c < npiv; c += blockDim.x) {
+    // 4. fuse every cluster: one warp per pivot. The lanes scan the sorted positions behind the pivot 32 at a time
+    //    (ballot of cid == pivot), lane 0 visits the members in sweep order - sequential sums, the reference's order
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int c = threadIdx.x >> 5; c < npiv; c += nwarps) {
         const int pv = a.pivots[c];
         float* fp = a.f_prob + (size_t)c * k1;
         int members = 0;
-        for (int q = pv + 1; q < n; ++q) members += (a.cid[q] == pv);
+        for (int q0 = pv + 1; q0 < n; q0 += 32) {
+            const int q = q0 + lane;
+            members += __popc(__ballot_sync(0xffffffffu, q < n && a.cid[q] == pv));
+        }
         const int64_t cls = a.labels[src[pv]];
         if (members == 0) {
-            a.f_box[c] = a.boxes[src[pv]];
-            a.f_score[c] = sscore[pv];
-            for (int k = 0; k < k1; ++k) fp[k] = a.probs[(size_t)src[pv] * k1 + k];
-            a.f_cls[c] = cls;
+            if (lane == 0) {
+                a.f_box[c] = a.boxes[src[pv]];
+                a.f_score[c] = sscore[pv];
+                a.f_cls[c] = cls;
+            }
+            for (int k = lane; k < k1; k += 32) fp[k] = a.probs[(size_t)src[pv] * k1 + k];
             continue;
         }
         const float count = (float)(members + 1);
@@ -162,7 +182,21 @@ __global__ void __launch_bounds__(1024) fusion_nms_kernel(const FusionArgs a) {
         float ssum = 0.0f, best = -INFINITY;
         int best_q = pv;
         bool mixed = false, bad_argmax = false;
-        for (int k = 0; k < k1; ++k) fp[k] = 0.0f;
+        // every lane runs the (identical) sequential fusion below on the same data; only lane 0 stores
+        float* acc = fp;
+        if (lane == 0) for (int k = 0; k < k1; ++k) acc[k] = 0.0f;
+        __syncwarp();
+        auto for_members = [&](auto&& fn) {     // ascending sorted position, then the pivot
+            for (int q0 = pv + 1; q0 < n; q0 += 32) {
+                const int q = q0 + lane;
+                uint32_t bits = __ballot_sync(0xffffffffu, q < n && a.cid[q] == pv);
+                while (bits) {
+                    fn(q0 + __ffs((int)bits) - 1);
+                    bits &= bits - 1;
+                }
+            }
+            fn(pv);
+        };
         auto visit = [&](int q) {
             const int o = src[q];
             const float sc = sscore[q];
@@ -175,31 +209,33 @@ __global__ void __launch_bounds__(1024) fusion_nms_kernel(const FusionArgs a) {
                 for (int k = 0; k < k1; ++k) {
                     const float pr = a.probs[(size_t)o * k1 + k];
                     if (pr > av) { av = pr; am = k; }
-                    fp[k] += logf(pr);
+                    if (lane == 0) acc[k] += logf(pr);
                 }
                 bad_argmax |= (am != (int)a.labels[o]);
             } else if (a.score_method == COIN_SCORE_AVG) {
-                for (int k = 0; k < k1; ++k) fp[k] += a.probs[(size_t)o * k1 + k];
+                if (lane == 0) for (int k = 0; k < k1; ++k) acc[k] += a.probs[(size_t)o * k1 + k];
             }
         };
-        for (int q = pv + 1; q < n; ++q) if (a.cid[q] == pv) visit(q);
-        visit(pv);
-        if (mixed) atomicOr(a.status, 1);
-        if (bad_argmax) atomicOr(a.status, 2);
+        for_members(visit);
+        if (lane == 0 && mixed) atomicOr(a.status, 1);
+        if (lane == 0 && bad_argmax) atomicOr(a.status, 2);
+        __syncwarp();
 
-        float fscore;
-        if (a.score_method == COIN_SCORE_PROBEN) {
-            float esum = 0.0f;
-            for (int k = 0; k < k1; ++k) { fp[k] = expf(fp[k]); esum += fp[k]; }
-            for (int k = 0; k < k1; ++k) fp[k] = fp[k] / esum;
-            fscore = fp[(int)cls];
-        } else if (a.score_method == COIN_SCORE_AVG) {
-            for (int k = 0; k < k1; ++k) fp[k] = fp[k] / count;
-            fscore = ssum / count;
-        } else {
-            const int o = src[best_q];
-            for (int k = 0; k < k1; ++k) fp[k] = a.probs[(size_t)o * k1 + k];
-            fscore = best;
+        float fscore = 0.0f;
+        if (lane == 0) {
+            if (a.score_method == COIN_SCORE_PROBEN) {
+                float esum = 0.0f;
+                for (int k = 0; k < k1; ++k) { fp[k] = expf(fp[k]); esum += fp[k]; }
+                for (int k = 0; k < k1; ++k) fp[k] = fp[k] / esum;
+                fscore = fp[(int)cls];
+            } else if (a.score_method == COIN_SCORE_AVG) {
+                for (int k = 0; k < k1; ++k) fp[k] = fp[k] / count;
+                fscore = ssum / count;
+            } else {
+                const int o = src[best_q];
+                for (int k = 0; k < k1; ++k) fp[k] = a.probs[(size_t)o * k1 + k];
+                fscore = best;
+            }
         }
 
         float4 fb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -215,13 +251,14 @@ __global__ void __launch_bounds__(1024) fusion_nms_kernel(const FusionArgs a) {
                     fb.x += b.x; fb.y += b.y; fb.z += b.z; fb.w += b.w;
                 }
             };
-            for (int q = pv + 1; q < n; ++q) if (a.cid[q] == pv) add(q);
-            add(pv);
+            for_members(add);
             if (a.box_method == COIN_BOX_AVG) { fb.x /= count; fb.y /= count; fb.z /= count; fb.w /= count; }
         }
-        a.f_box[c] = fb;
-        a.f_score[c] = fscore;
-        a.f_cls[c] = cls;
+        if (lane == 0) {
+            a.f_box[c] = fb;
+            a.f_score[c] = fscore;
+            a.f_cls[c] = cls;
+        }
     }
     __syncthreads();
 
@@ -252,11 +289,33 @@ static size_t fusion_smem_bytes(int n) {
 }  // namespace coin
 using namespace coin;
 
+static void carve_fusion(FusionArgs& a, void* ws, int64_t n, int k1, size_t* used) {
+    Carver c(ws);
+    a.cid = c.take<int32_t>((size_t)n);
+    a.pivots = c.take<int32_t>((size_t)n);
+    a.f_box = c.take<float4>((size_t)n);
+    a.f_score = c.take<float>((size_t)n);
+    a.f_prob = c.take<float>((size_t)n * k1);
+    a.f_cls = c.take<int64_t>((size_t)n);
+    a.g_keys = nullptr; a.g_nbox = nullptr; a.g_area = a.g_sscore = nullptr; a.g_src = a.g_alive = nullptr;
+    if (n > kFusionMax || option("COIN_FUSION_FORCE_GLOBAL", 0)) {      // large-n variant: the working set moves to the workspace
+        size_t npow = 2;
+        while ((int64_t)npow < n) npow <<= 1;
+        a.g_keys = c.take<uint64_t>(npow);
+        a.g_nbox = c.take<float4>((size_t)n);
+        a.g_area = c.take<float>((size_t)n);
+        a.g_sscore = c.take<float>((size_t)n);
+        a.g_src = c.take<int32_t>((size_t)n);
+        a.g_alive = c.take<int32_t>((size_t)n);
+    }
+    *used = c.used();
+}
+
 extern "C" size_t coin_fusion_nms_workspace_bytes(int64_t n, int k1) {
-    Carver c(nullptr);
-    c.take<int32_t>((size_t)n); c.take<int32_t>((size_t)n); c.take<float4>((size_t)n);
-    c.take<float>((size_t)n); c.take<float>((size_t)n * k1); c.take<int64_t>((size_t)n);
-    return c.used() + 256;
+    FusionArgs a;
+    size_t used = 0;
+    carve_fusion(a, nullptr, n, k1, &used);
+    return used + 256;
 }
 
 extern "C" int coin_fusion_nms(const float* boxes, const float* probs, const int64_t* labels, int64_t n, int k1,
@@ -272,7 +331,7 @@ extern "C" int coin_fusion_nms(const float* boxes, const float* probs, const int
         fill_bytes(nkeep, 0, sizeof(int32_t), s);
         return COIN_OK;
     }
-    if (n > kFusionMax) return fail(COIN_ERR_UNSUPPORTED, "fusion_nms: n=%lld exceeds %d boxes per call", (long long)n, kFusionMax);
+    COIN_REQUIRE(n < (1ll << 24), "fusion_nms: n=%lld exceeds the supported 16M boxes", (long long)n);
     COIN_REQUIRE(boxes && probs && labels && keep && out_boxes && out_scores && out_probs && out_classes && ws,
                  "fusion_nms: null pointer");
     COIN_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_boxes) & 15) == 0,
@@ -280,21 +339,20 @@ extern "C" int coin_fusion_nms(const float* boxes, const float* probs, const int
     if (ws_bytes < coin_fusion_nms_workspace_bytes(n, k1))
         return fail(COIN_ERR_CAPACITY, "fusion_nms: workspace too small");
     FusionArgs a;
-    Carver c(ws);
-    a.cid = c.take<int32_t>((size_t)n);
-    a.pivots = c.take<int32_t>((size_t)n);
-    a.f_box = c.take<float4>((size_t)n);
-    a.f_score = c.take<float>((size_t)n);
-    a.f_prob = c.take<float>((size_t)n * k1);
-    a.f_cls = c.take<int64_t>((size_t)n);
+    size_t used = 0;
+    carve_fusion(a, ws, n, k1, &used);
     a.boxes = reinterpret_cast<const float4*>(boxes);
     a.probs = probs; a.labels = labels; a.n = (int)n; a.k1 = k1; a.thr = iou_threshold;
     a.score_method = score_method; a.box_method = box_method; a.per_class_offset = per_class_offset;
     a.keep = keep; a.out_boxes = reinterpret_cast<float4*>(out_boxes); a.out_scores = out_scores;
     a.out_probs = out_probs; a.out_classes = out_classes; a.nkeep = nkeep; a.status = status;
+    if (a.g_keys) {
+        fusion_nms_kernel<true><<<1, 1024, 0, s>>>(a);
+        return check_launch("fusion_nms_kernel");
+    }
     const size_t smem = fusion_smem_bytes((int)n);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(fusion_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fusion_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int threads = n <= 128 ? 128 : (n <= 512 ? 256 : 1024);
-    fusion_nms_kernel<<<1, threads, smem, s>>>(a);
+    fusion_nms_kernel<false><<<1, threads, smem, s>>>(a);
     return check_launch("fusion_nms_kernel");
 }

@@ -663,6 +663,7 @@ extern "C" int coin_roi_pooler_levels(const float* boxes, int64_t n, int min_lev
     COIN_REQUIRE(n >= 0 && min_level <= max_level && canonical_box_size > 0, "roi_pooler_levels: bad arguments");
     if (n == 0) return COIN_OK;
     COIN_REQUIRE(boxes && out_levels, "roi_pooler_levels: null pointer");
+    COIN_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "roi_pooler_levels: boxes must be 16-byte aligned");
     pooler_levels_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
         boxes, n, min_level, max_level, (float)canonical_box_size, (float)canonical_level, out_levels);
     return check_launch("pooler_levels_kernel");

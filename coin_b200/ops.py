@@ -127,16 +127,21 @@ def roi_launch_order(rois: torch.Tensor, k_dev: Optional[torch.Tensor] = None, s
 def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
                       roi_level: Optional[torch.Tensor], output_size: Tuple[int, int], sampling_ratio: int,
                       aligned: bool, out_dtype: torch.dtype, events: Optional[list] = None,
-                      k_dev: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      k_dev: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """events: optional list; a (start, end) CUDA-event pair bracketing the kernel launch is appended.
     k_dev: optional device int32 live RoI count (<= K): rows of the result beyond it are not written.
-    perm: optional launch order from ``roi_launch_order`` (same rois)."""
+    perm: optional launch order from ``roi_launch_order`` (same rois).
+    out: optional preallocated contiguous [K, C, PH, PW] result (e.g. a row range of a larger buffer)."""
     rois = _f32c(rois, "rois")
     if rois.dim() != 2 or rois.shape[1] != 5:
         raise ValueError(f"coin_b200: rois must have shape [K, 5], got {tuple(rois.shape)}")
     k, c = rois.shape[0], int(feats_nhwc[0].shape[3])
     ph, pw = output_size
-    out = torch.empty((k, c, ph, pw), dtype=out_dtype, device=rois.device)
+    if out is None:
+        out = torch.empty((k, c, ph, pw), dtype=out_dtype, device=rois.device)
+    elif tuple(out.shape) != (k, c, ph, pw) or out.dtype != out_dtype or not out.is_contiguous():
+        raise ValueError("coin_b200: `out` must be a contiguous [K, C, PH, PW] tensor of the output dtype")
     if roi_level is not None:
         roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
     pair = _event_pair(events)

@@ -130,3 +130,39 @@ def test_detection_cache_reads_trainer_checkpoint_key(tmp_path):
     _same(cache.lookup("img.png"), per_file["img.png"]["RCNN"])
     with pytest.raises(ValueError):
         DetectionCache.from_state_dict({"format": "something else"})
+
+
+def test_probs_presence_and_width_are_per_image_and_empty_instances_load():
+    """images without a `probs` field (or a narrower one) must not come back with fabricated zero columns, and
+    an Instances without any field (len() raises) is an image with no detections, not a load error."""
+    def inst(n, k1):
+        i = Instances((600, 1200))
+        i.pred_boxes = Boxes(torch.rand(n, 4) * 100)
+        i.scores = torch.rand(n)
+        i.pred_classes = torch.randint(0, 8, (n,))
+        if k1:
+            i.probs = torch.rand(n, k1)
+        return i
+    per_file = {"a.png": {"file_name": "a.png", "image_id": 0, "height": 1024, "width": 2048, "RCNN": {"instances": inst(3, 9)}},
+                "b.png": {"file_name": "b.png", "image_id": 1, "height": 1024, "width": 2048, "RCNN": {"instances": inst(2, 0)}},
+                "c.png": {"file_name": "c.png", "image_id": 2, "height": 1024, "width": 2048, "RCNN": {"instances": inst(4, 5)}},
+                "d.png": {"file_name": "d.png", "image_id": 3, "height": 1024, "width": 2048,
+                          "RCNN": {"instances": Instances((600, 1200))}}}
+    cache = DetectionCache.from_reference_dict(per_file)
+    assert cache.lookup("a.png").probs.shape == (3, 9)
+    assert not cache.lookup("b.png").has("probs")
+    assert cache.lookup("c.png").probs.shape == (4, 5)
+    assert torch.equal(cache.lookup("c.png").probs, per_file["c.png"]["RCNN"]["instances"].probs)
+    assert len(cache.lookup("d.png").scores) == 0
+    again = DetectionCache.from_state_dict(cache.state_dict())
+    assert not again.lookup("b.png").has("probs") and again.lookup("c.png").probs.shape == (4, 5)
+
+
+def test_reference_loader_refuses_unknown_globals(tmp_path):
+    """a detections file is data; a pickle that names any other importable callable is refused."""
+    import os
+    import pickle
+    path = os.path.join(tmp_path, "evil.pth")
+    torch.save({"results": {"ds": {}}, "hook": os.path.join}, path)
+    with pytest.raises(pickle.UnpicklingError):
+        load_reference_results(path)
