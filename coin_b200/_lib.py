@@ -104,6 +104,17 @@ _SIGNATURES = {
     "coin_abc_pack": (c_int, [POINTER(CoinDets), c_int64, POINTER(CoinDets), c_int64, P, c_int, c_int,
                               P, P, P, P, P, P, P, POINTER(CoinPseudo), POINTER(CoinPseudo), POINTER(CoinPseudo),
                               c_int64, P]),
+    # sampling and loss-side reductions
+    "coin_proposal_classes": (c_int, [P, P, P, c_int64, P, c_int64, P, c_int64, P, P]),
+    "coin_subsample_labels_workspace_bytes": (c_size_t, [c_int64]),
+    "coin_subsample_labels": (c_int, [P, c_int, c_int64, P, c_int, c_int, c_int64, P, P, ctypes.c_uint64, ctypes.c_uint64,
+                                      c_int, P, P, P, P, c_size_t, P]),
+    "coin_rpn_teacher_probs": (c_int, [P, c_int64, P, c_int, P, c_int64, P, P]),
+    "coin_kl_workspace_bytes": (c_size_t, []),
+    "coin_kl_distill_roi_fwd": (c_int, [P, P, c_int64, P, c_int, P, P, P]),
+    "coin_kl_distill_roi_bwd": (c_int, [P, P, c_int64, P, c_int, P, P, P]),
+    "coin_kl_distill_rpn_fwd": (c_int, [P, P, P, c_int64, P, P, P, P]),
+    "coin_kl_distill_rpn_bwd": (c_int, [P, P, P, c_int64, P, P, P, P]),
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())

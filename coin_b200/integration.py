@@ -11,6 +11,7 @@ Same names / argument meaning as the reference so the parity tests read like cal
 The reference moves the teacher detections to the CPU for the matching (trainer.py:469) and back
 (:457-459); here everything stays on the device and each function is one or a few launches.
 """
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -169,11 +170,112 @@ def label_proposals(matcher: Matcher, a_boxes: Boxes, b_boxes: Boxes, c_boxes: B
     return idx, lab
 
 
+def sample_proposals(matched_idxs: torch.Tensor, matched_labels: torch.Tensor, gt_classes: torch.Tensor, num_classes: int,
+                     batch_size_per_image: int, positive_fraction: float, generator="torch", seed: int = 0, offset: int = 0):
+    """detectron2 ``ROIHeads._sample_proposals`` (<- clip_roi_heads.py:317,363): proposal classes (background / ignore rules)
+    and the fg / bg subsample, both on the device. Returns (sampled_idxs, gt_classes[sampled_idxs]).
+
+    generator="torch": the reference's draw - two ``torch.randperm`` calls on the global generator, over the positive and
+    the negative count (one count read-back), replayed on the device: bit-exact against a seeded reference run.
+    generator="device": Philox4x32-10 keyed by (seed, offset) on the device, no host round trip."""
+    cls = ops.proposal_classes(matched_idxs, matched_labels, gt_classes, num_classes)
+    perms = None
+    if generator == "torch":
+        n_pos, n_neg = ops.subsample_labels(cls, batch_size_per_image, positive_fraction, num_classes, count_only=True)
+        perms = (torch.randperm(n_pos).to(cls.device), torch.randperm(n_neg).to(cls.device))   # same order as subsample_labels
+    elif generator != "device":
+        raise ValueError(generator)
+    fg, bg = ops.subsample_labels(cls, batch_size_per_image, positive_fraction, num_classes, perms, seed, offset)
+    sampled = torch.cat([fg, bg], dim=0)
+    return sampled, cls[sampled]
+
+
+def subsample_anchor_labels(label: torch.Tensor, batch_size_per_image: int, positive_fraction: float, generator="torch",
+                            seed: int = 0, offset: int = 0) -> torch.Tensor:
+    """detectron2 ``RPN._subsample_labels`` (<- rpn.py:231): keeps a random subset of the positive (1) and negative (0)
+    anchor labels and sets every other anchor to ignore (-1), in place like the original."""
+    perms = None
+    if generator == "torch":
+        n_pos, n_neg = ops.subsample_labels(label, batch_size_per_image, positive_fraction, 0, count_only=True)
+        perms = (torch.randperm(n_pos).to(label.device), torch.randperm(n_neg).to(label.device))
+    pos_idx, neg_idx = ops.subsample_labels(label, batch_size_per_image, positive_fraction, 0, perms, seed, offset)
+    label.fill_(-1)
+    label.scatter_(0, pos_idx, 1)
+    label.scatter_(0, neg_idx, 0)
+    return label
+
+
+def label_and_sample_proposals(proposals: list, targets, matcher: Matcher, num_classes: int, batch_size_per_image: int,
+                               positive_fraction: float, proposal_append_gt: bool = True, bg_train: bool = True,
+                               generator="torch", seed: int = 0, offset: int = 0) -> list:
+    """``OpenVocabularyRes5ROIHeads.label_and_sample_proposals`` for the 'step_one' / 'step_two' branches
+    (clip_roi_heads.py:342-399). ``proposals``: one Instances(proposal_boxes, ...) per image; ``targets`` = (A, B, C) lists
+    of pseudo-label Instances as ``match_dual_teacher`` returns them. Returns one (proposals_a, proposals_b, proposals_bg)
+    triple per image with the reference's fields: the fused IoU + Matcher + private-box rule (A6-A8), the class assignment
+    and the subsample run in kernels; the per-group field gathers are index selections."""
+    a_targets, b_targets, c_targets = targets
+    out = []
+    for i, (p, a, b, c) in enumerate(zip(proposals, a_targets, b_targets, c_targets)):
+        boxes = p.proposal_boxes
+        logits = p.objectness_logits if p.has("objectness_logits") else None
+        if proposal_append_gt:       # add_ground_truth_to_proposals(a), then (b): their boxes join the proposal list
+            boxes = Boxes.cat([boxes, a.gt_boxes, b.gt_boxes])
+            if logits is not None:   # ... with the logit of probability 1 - 1e-10 (d2 proposal_utils.py)
+                gt_logit = math.log((1.0 - 1e-10) / (1 - (1.0 - 1e-10)))
+                logits = torch.cat([logits, torch.full((len(a) + len(b),), gt_logit, dtype=logits.dtype, device=logits.device)])
+        len_a, len_b = len(a), len(b)
+        idx, lab = label_proposals(matcher, a.gt_boxes, b.gt_boxes, c.gt_boxes, boxes)
+        gt_cat = torch.cat([a.gt_classes, b.gt_classes_online, c.gt_classes])
+        sampled, temp = sample_proposals(idx, lab, gt_cat, num_classes, batch_size_per_image, positive_fraction, generator,
+                                         seed, offset + i)
+        m = idx[sampled]
+        bg = temp == num_classes
+        mask_a = (m >= 0) & (m < len_a) & ~bg
+        mask_b = (m >= len_a) & (m < len_a + len_b) & ~bg
+        size = p.image_size
+        pa, pb, pbg = Instances(size), Instances(size), Instances(size)
+        pa.proposal_boxes, pb.proposal_boxes = Boxes(boxes.tensor[sampled[mask_a]]), Boxes(boxes.tensor[sampled[mask_b]])
+        pbg.proposal_boxes = Boxes(boxes.tensor[sampled[bg]])
+        if logits is not None:
+            pa.objectness_logits, pb.objectness_logits = logits[sampled[mask_a]], logits[sampled[mask_b]]
+            pbg.objectness_logits = logits[sampled[bg]]
+        pbg.gt_classes = temp[bg]
+        if not bg_train:
+            pbg = pbg[0:0]
+        for name, val in a.get_fields().items():
+            if name.startswith("gt_"):
+                pa.set(name, val[m[mask_a]])
+        for name, val in b.get_fields().items():
+            if name.startswith("gt_"):
+                pb.set(name, val[m[mask_b] - len_a])
+        out.append((pa, pb, pbg))
+    return out
+
+
 def label_anchors(matcher: Matcher, a_boxes: Boxes, c_boxes: Boxes, anchors: Boxes):
     """rpn.py:209-228: returns (gt_labels, matched_idxs, distillation_idxs, distillation_labels)."""
     gt = Boxes.cat([a_boxes, c_boxes])
     idx, lab = matcher.match_boxes(gt, anchors)
     return ops.relabel_rpn_(idx, lab, len(a_boxes), len(c_boxes))
+
+
+def label_and_sample_anchors(matcher: Matcher, a_boxes: Boxes, c_boxes: Boxes, anchors: Boxes, batch_size_per_image: int,
+                             positive_fraction: float, generator="torch", seed: int = 0, offset: int = 0):
+    """``DualTeacherRPN.label_and_sample_anchors`` for one image of the 'step_one' / 'step_two' branches (rpn.py:199-254,
+    anchor_boundary_thresh < 0): returns (gt_labels, matched_gt_boxes, all_matched_idxs, distillation_labels)."""
+    lab, idx, didx, dlab = label_anchors(matcher, a_boxes, c_boxes, anchors)
+    before = lab.clone() if len(a_boxes) == 0 else None
+    lab = subsample_anchor_labels(lab, batch_size_per_image, positive_fraction, generator, seed, offset)
+    if len(a_boxes) == 0:
+        # rpn.py:244-248: without consistent boxes only the anchors that matched a private box as background keep a label
+        matched_gt_boxes = torch.zeros_like(anchors.tensor)
+        if len(c_boxes) == 0:
+            lab.fill_(-1)
+        else:
+            lab[before != 0] = -1
+    else:
+        matched_gt_boxes = a_boxes.tensor[idx]
+    return lab, matched_gt_boxes, didx, dlab
 
 
 def rpn_predict_proposals(anchors: Boxes, pred_objectness_logits: torch.Tensor, pred_anchor_deltas: torch.Tensor,

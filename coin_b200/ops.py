@@ -654,3 +654,116 @@ def match_abc_fields_both_dev(on: dict, off: dict, nd_dev: torch.Tensor, iou_thr
                                 ctypes.byref(b_st) if b_st is not None else None, ctypes.byref(c_st), cap, _stream()))
         out[tag] = (a, b, c, t["counts"])
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling and loss-side reductions
+# ------------------------------------------------------------------------------------------------
+def proposal_classes(matched_idxs: torch.Tensor, matched_labels: torch.Tensor, gt_classes: torch.Tensor, num_classes: int,
+                     m_dev: Optional[torch.Tensor] = None, n_gt_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """detectron2 ROIHeads._sample_proposals, first half: the class of every proposal (num_classes = background, -1 = ignore)."""
+    idx = _i64c(matched_idxs, "matched_idxs")
+    lab = _cuda(matched_labels, "matched_labels").to(torch.int8).contiguous()
+    gt = _i64c(gt_classes, "gt_classes")
+    out = torch.empty_like(idx)
+    check(lib.coin_proposal_classes(_ptr(idx), _ptr(lab), _ptr(gt), gt.numel(), _ptr(None if n_gt_dev is None else _count(n_gt_dev)),
+                                    idx.numel(), _ptr(None if m_dev is None else _count(m_dev)), int(num_classes), _ptr(out),
+                                    _stream()))
+    return out
+
+
+def subsample_labels(labels: torch.Tensor, num_samples: int, positive_fraction: float, bg_label: int,
+                     perms: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, seed: int = 0, offset: int = 0,
+                     m_dev: Optional[torch.Tensor] = None, count_only: bool = False, sync: bool = True):
+    """detectron2 subsample_labels. perms=(perm_pos, perm_neg): replay of the reference's two torch.randperm draws;
+    None: the device generator (Philox4x32-10 keyed by seed / offset). Returns (pos_idx, neg_idx) - or, with sync=False,
+    the capacity buffers and the device counts [num_pos, num_neg, P, N, status]; count_only returns (P, N)."""
+    _cuda(labels, "labels")
+    if labels.dtype not in (torch.int64, torch.int8):
+        raise TypeError("coin_b200: labels must be int64 or int8")
+    labels = labels.contiguous()
+    m = labels.numel()
+    dev = labels.device
+    num_pos_target = int(num_samples * positive_fraction)
+    pos = torch.empty((max(num_samples, 1),), dtype=torch.int64, device=dev)
+    neg = torch.empty((max(num_samples, 1),), dtype=torch.int64, device=dev)
+    counts = torch.zeros((8,), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.coin_subsample_labels_workspace_bytes(m), dev)
+    pp = pn = None
+    if perms is not None:
+        # (an empty permutation has no storage: hand the library a valid pointer anyway, NULL means "device generator")
+        pp, pn = (_i64c(p, "perm") if p.numel() else torch.zeros((1,), dtype=torch.int64, device=dev) for p in perms)
+    check(lib.coin_subsample_labels(_ptr(labels), int(labels.dtype == torch.int8), m,
+                                    _ptr(None if m_dev is None else _count(m_dev)), int(num_samples), num_pos_target,
+                                    int(bg_label), _ptr(pp), _ptr(pn), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
+                                    int(bool(count_only)), _ptr(pos), _ptr(neg), _ptr(counts), _ptr(ws), ws.numel(), _stream()))
+    if count_only:
+        c = counts.tolist()
+        return c[2], c[3]
+    if not sync:
+        return pos, neg, counts
+    c = counts.tolist()
+    if c[4]:
+        raise ValueError("coin_b200: subsample_labels: a permutation entry is out of range")
+    return pos[: c[0]], neg[: c[1]]
+
+
+def rpn_teacher_probs(gt_probs: torch.Tensor, matched_idxs: torch.Tensor, nc_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rpn.py:95-98: gt_probs[:, :-1].sum(1)[matched_idxs]; zeros when there are no C boxes."""
+    idx = _i64c(matched_idxs, "matched_idxs")
+    out = torch.empty(idx.shape, dtype=torch.float32, device=idx.device)
+    gp = _f32c(gt_probs, "gt_probs") if gt_probs is not None and gt_probs.numel() else None
+    nc = 0 if gp is None else gp.shape[0]
+    k1 = 1 if gp is None else int(gp.shape[1])
+    check(lib.coin_rpn_teacher_probs(_ptr(gp), nc, _ptr(None if nc_dev is None else _count(nc_dev)), k1, _ptr(idx), idx.numel(),
+                                     _ptr(out), _stream()))
+    return out
+
+
+def kl_distill_roi_fwd(scores: torch.Tensor, gt_probs: torch.Tensor, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    scores, gt_probs = _f32c(scores, "scores"), _f32c(gt_probs, "gt_probs")
+    if scores.shape != gt_probs.shape or scores.dim() != 2:
+        raise ValueError("coin_b200: scores and gt_probs must both be [n, K+1]")
+    loss = torch.empty((), dtype=torch.float32, device=scores.device)
+    ws = _workspace(lib.coin_kl_workspace_bytes(), scores.device)
+    check(lib.coin_kl_distill_roi_fwd(_ptr(scores), _ptr(gt_probs), scores.shape[0],
+                                      _ptr(None if n_dev is None else _count(n_dev)), int(scores.shape[1]), _ptr(loss), _ptr(ws),
+                                      _stream()))
+    return loss
+
+
+def kl_distill_roi_bwd(scores, gt_probs, grad_loss, n_dev=None) -> torch.Tensor:
+    scores, gt_probs = _f32c(scores, "scores"), _f32c(gt_probs, "gt_probs")
+    g = torch.empty_like(scores)
+    go = _f32c(grad_loss, "grad_loss").reshape(1)
+    check(lib.coin_kl_distill_roi_bwd(_ptr(scores), _ptr(gt_probs), scores.shape[0],
+                                      _ptr(None if n_dev is None else _count(n_dev)), int(scores.shape[1]), _ptr(go), _ptr(g),
+                                      _stream()))
+    return g
+
+
+def kl_distill_rpn_fwd(logits: torch.Tensor, distillation_labels: torch.Tensor, teacher_probs: torch.Tensor):
+    """Returns (loss, n_valid device int32)."""
+    logits = _f32c(logits, "logits").reshape(-1)
+    labels = _cuda(distillation_labels, "distillation_labels").to(torch.int8).contiguous().reshape(-1)
+    teacher = _f32c(teacher_probs, "teacher_probs").reshape(-1)
+    if not (logits.numel() == labels.numel() == teacher.numel()):
+        raise ValueError("coin_b200: logits, labels and teacher_probs disagree in length")
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    n_valid = torch.zeros((1,), dtype=torch.int32, device=logits.device)
+    ws = _workspace(lib.coin_kl_workspace_bytes(), logits.device)
+    check(lib.coin_kl_distill_rpn_fwd(_ptr(logits), _ptr(labels), _ptr(teacher), logits.numel(), _ptr(loss), _ptr(n_valid),
+                                      _ptr(ws), _stream()))
+    return loss, n_valid
+
+
+def kl_distill_rpn_bwd(logits, distillation_labels, teacher_probs, n_valid, grad_loss) -> torch.Tensor:
+    shape = logits.shape
+    logits = _f32c(logits, "logits").reshape(-1)
+    labels = _cuda(distillation_labels, "distillation_labels").to(torch.int8).contiguous().reshape(-1)
+    teacher = _f32c(teacher_probs, "teacher_probs").reshape(-1)
+    g = torch.empty_like(logits)
+    go = _f32c(grad_loss, "grad_loss").reshape(1)
+    check(lib.coin_kl_distill_rpn_bwd(_ptr(logits), _ptr(labels), _ptr(teacher), logits.numel(), _ptr(_count(n_valid)), _ptr(go),
+                                      _ptr(g), _stream()))
+    return g.reshape(shape)

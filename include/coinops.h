@@ -411,6 +411,51 @@ int coin_rpn_proposals(const float* anchors, const float* deltas, const float* l
                        float* out_boxes, float* out_logits, int32_t* out_count, int32_t* status, void* ws,
                        size_t ws_bytes, coin_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Sampling and loss-side reductions
+ * ------------------------------------------------------------------------------------------- */
+
+/* detectron2 ROIHeads._sample_proposals, first half (<- coin/modeling/roi_heads/clip_roi_heads.py:317,363):
+ * out[i] = num_classes where matched_labels[i] == 0, -1 where it is -1, else gt_classes[matched_idxs[i]]; num_classes for
+ * every row when there is no ground truth. Rows beyond the live count *m_dev get -1 (the sampler ignores them). */
+int coin_proposal_classes(const int64_t* matched_idxs, const int8_t* matched_labels, const int64_t* gt_classes,
+                          int64_t n_gt_cap, const int32_t* n_gt_dev, int64_t m_cap, const int32_t* m_dev,
+                          int64_t num_classes, int64_t* out_classes, coin_stream_t stream);
+
+/* detectron2 modeling/sampling.py::subsample_labels (<- clip_roi_heads.py:363 via _sample_proposals, rpn.py:231 via
+ * _subsample_labels). labels: int64 (label_is_int8 = 0) or int8 [m_cap]; positives = labels != -1 && != bg_label,
+ * negatives = labels == bg_label. num_pos_target = int(num_samples * positive_fraction), computed by the caller.
+ * The random draw: perm_pos / perm_neg non-NULL -> pos_idx = positive[perm_pos[:num_pos]], neg_idx = negative[perm_neg[:num_neg]]
+ * (replay of the reference's two torch.randperm draws; they must be permutations of [0, P) and [0, N), which a first call
+ * with count_only = 1 reports in counts[2], counts[3]); NULL -> device generator Philox4x32-10 keyed by `seed`, counter
+ * (element, set, offset): the num smallest (key, element) pairs of each set, in key order.
+ * counts: int32 [5] = {num_pos, num_neg, P, N, status (1: a permutation entry out of range)}. num_samples <= 4096. */
+size_t coin_subsample_labels_workspace_bytes(int64_t m_cap);
+int coin_subsample_labels(const void* labels, int label_is_int8, int64_t m_cap, const int32_t* m_dev, int num_samples,
+                          int num_pos_target, int64_t bg_label, const int64_t* perm_pos, const int64_t* perm_neg,
+                          uint64_t seed, uint64_t offset, int count_only, int64_t* pos_idx, int64_t* neg_idx,
+                          int32_t* counts, void* ws, size_t ws_bytes, coin_stream_t stream);
+
+/* coin/modeling/proposal_generator/rpn.py:95-98: out[i] = sum(gt_probs[matched[i], :-1]) (0 when there are no C boxes). */
+int coin_rpn_teacher_probs(const float* gt_probs, int64_t nc_cap, const int32_t* nc_dev, int k1, const int64_t* matched,
+                           int64_t n, float* out, coin_stream_t stream);
+
+/* coin/modeling/roi_heads/fast_rcnn.py:541-545: loss = mean over [n, k1] of q * (log q - log(softmax(scores) + 1e-7))
+ * (torch.nn.KLDivLoss, reduction 'mean'); n may be a device count. ws: coin_kl_workspace_bytes() bytes.
+ * _bwd: grad_scores = d loss / d scores * *grad_loss (rows beyond the live count are zero-filled). */
+size_t coin_kl_workspace_bytes(void);
+int coin_kl_distill_roi_fwd(const float* scores, const float* gt_probs, int64_t n_cap, const int32_t* n_dev, int k1,
+                            float* loss, void* ws, coin_stream_t stream);
+int coin_kl_distill_roi_bwd(const float* scores, const float* gt_probs, int64_t n_cap, const int32_t* n_dev, int k1,
+                            const float* grad_loss, float* grad_scores, coin_stream_t stream);
+/* coin/modeling/proposal_generator/rpn.py:326-340: the two-column KL between (sigmoid(logit), 1 - sigmoid(logit)) and
+ * (teacher, 1 - teacher) over the anchors whose distillation label is > 0, reduction 'mean' (sum / (2 * n_valid));
+ * n_valid (device int32) is written by _fwd and read by _bwd; loss = 0 when no anchor is valid. */
+int coin_kl_distill_rpn_fwd(const float* logits, const int8_t* distillation_labels, const float* teacher_probs, int64_t n,
+                            float* loss, int32_t* n_valid, void* ws, coin_stream_t stream);
+int coin_kl_distill_rpn_bwd(const float* logits, const int8_t* distillation_labels, const float* teacher_probs, int64_t n,
+                            const int32_t* n_valid, const float* grad_loss, float* grad_logits, coin_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

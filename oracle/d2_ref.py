@@ -271,3 +271,62 @@ def detector_postprocess(boxes: torch.Tensor, image_size, output_height: int, ou
     b = box_clip(box_scale(boxes, sx, sy), (output_height, output_width))
     keep = box_nonempty(b)
     return b[keep], keep
+
+
+# ------------------------------------------------------------------------------------------------
+# detectron2 0.5 modeling/sampling.py::subsample_labels and ROIHeads._sample_proposals
+# (<- coin/modeling/roi_heads/clip_roi_heads.py:317,363; coin/modeling/proposal_generator/rpn.py:231)
+# ------------------------------------------------------------------------------------------------
+def philox_keys(elements, stream_set: int, seed: int, offset: int):
+    """Philox4x32-10, first output word, counter = (element, set, offset lo, offset hi), key = (seed lo, seed hi): the
+    device generator of coin_subsample_labels restated with numpy integers (the random draw is a policy of the
+    replacement, not of the reference, which uses torch.randperm; DESIGN.md 'Determinism policy')."""
+    import numpy as np
+    e = np.asarray(elements, dtype=np.uint64)
+    c0 = e & np.uint64(0xFFFFFFFF)
+    c1 = np.full_like(c0, np.uint64(stream_set))
+    c2 = np.full_like(c0, np.uint64(offset & 0xFFFFFFFF))
+    c3 = np.full_like(c0, np.uint64((offset >> 32) & 0xFFFFFFFF))
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    return c0.astype(np.uint64)
+
+
+def subsample_labels(labels: torch.Tensor, num_samples: int, positive_fraction: float, bg_label: int, perms=None,
+                     seed: int = 0, offset: int = 0):
+    """[d2] subsample_labels. perms = (perm1, perm2): the two torch.randperm draws of the original; None: the device
+    policy - the num smallest (Philox key, element) pairs of each set, in key order."""
+    positive = torch.nonzero((labels != -1) & (labels != bg_label), as_tuple=True)[0]
+    negative = torch.nonzero(labels == bg_label, as_tuple=True)[0]
+    num_pos = min(positive.numel(), int(num_samples * positive_fraction))
+    num_neg = min(negative.numel(), num_samples - num_pos)
+    if perms is not None:
+        return positive[perms[0][:num_pos]], negative[perms[1][:num_neg]]
+    import numpy as np
+    out = []
+    for s, (cand, num) in enumerate(((positive, num_pos), (negative, num_neg))):
+        keys = philox_keys(cand.numpy(), s, seed, offset)
+        order = np.lexsort((cand.numpy(), keys))          # by key, ties by element
+        out.append(cand[torch.from_numpy(order[:num].copy())])
+    return out[0], out[1]
+
+
+def sample_proposals(matched_idxs, matched_labels, gt_classes, num_classes: int, batch_size_per_image: int,
+                     positive_fraction: float, perms=None, seed: int = 0, offset: int = 0):
+    """[d2] ROIHeads._sample_proposals -> (sampled_idxs, gt_classes[sampled_idxs])."""
+    if gt_classes.numel() > 0:
+        gt_classes = gt_classes[matched_idxs]
+        gt_classes[matched_labels == 0] = num_classes
+        gt_classes[matched_labels == -1] = -1
+    else:
+        gt_classes = torch.zeros_like(matched_idxs) + num_classes
+    fg, bg = subsample_labels(gt_classes, batch_size_per_image, positive_fraction, num_classes, perms, seed, offset)
+    sampled = torch.cat([fg, bg], dim=0)
+    return sampled, gt_classes[sampled]
