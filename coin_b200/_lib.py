@@ -100,6 +100,9 @@ _SIGNATURES = {
     "coin_rpn_proposals_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "coin_rpn_proposals": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_double, c_float, c_float, c_float, c_float,
                                    c_float, c_float, c_float, c_float, P, P, P, P, P, c_size_t, P]),
+    "coin_rpn_proposals_grid": (c_int, [POINTER(c_float), c_int, c_int, c_int, c_float, c_float, P, P, c_int64, c_int64, c_double,
+                                        c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P, P, P,
+                                        c_size_t, P]),
     "coin_concat_rows": (c_int, [POINTER(CoinSeg), c_int, c_int, c_int, P, c_int64, P, P]),
     "coin_abc_pack": (c_int, [POINTER(CoinDets), c_int64, POINTER(CoinDets), c_int64, P, c_int, c_int,
                               P, P, P, P, P, P, P, POINTER(CoinPseudo), POINTER(CoinPseudo), POINTER(CoinPseudo),

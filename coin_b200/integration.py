@@ -278,7 +278,37 @@ def label_and_sample_anchors(matcher: Matcher, a_boxes: Boxes, c_boxes: Boxes, a
     return lab, matched_gt_boxes, didx, dlab
 
 
-def rpn_predict_proposals(anchors: Boxes, pred_objectness_logits: torch.Tensor, pred_anchor_deltas: torch.Tensor,
+class AnchorGrid(tuple):
+    """One level of detectron2's ``DefaultAnchorGenerator`` (<- rpn.py:64) in closed form: (cell_anchors [ncell,4], Hf, Wf,
+    stride, offset). ``rpn_predict_proposals`` accepts it in place of the materialised ``Boxes`` of all anchors."""
+
+    def __new__(cls, cell_anchors, hf: int, wf: int, stride: int, offset: float = 0.0):
+        return super().__new__(cls, (torch.as_tensor(cell_anchors, dtype=torch.float32).reshape(-1, 4), int(hf), int(wf),
+                                     float(stride), float(offset)))
+
+    @staticmethod
+    def cell_anchors(sizes=(32, 64, 128, 256, 512), ratios=(0.5, 1.0, 2.0)) -> torch.Tensor:
+        """DefaultAnchorGenerator.generate_cell_anchors (Base-Cloud.yaml:22-23: 5 sizes x 3 ratios)."""
+        out = []
+        for s in sizes:
+            area = s ** 2.0
+            for r in ratios:
+                w = math.sqrt(area / r)
+                h = r * w
+                out.append([-w / 2.0, -h / 2.0, w / 2.0, h / 2.0])
+        return torch.tensor(out, dtype=torch.float32)
+
+    def materialise(self) -> torch.Tensor:
+        """The [Hf*Wf*ncell, 4] array grid_anchors builds (for callers that still want it, e.g. anchor labelling)."""
+        cell, hf, wf, stride, offset = self
+        sx = torch.arange(offset * stride, wf * stride, step=stride, dtype=torch.float32)
+        sy = torch.arange(offset * stride, hf * stride, step=stride, dtype=torch.float32)
+        yy, xx = torch.meshgrid(sy, sx, indexing="ij")
+        shifts = torch.stack((xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)), dim=1)
+        return (shifts.view(-1, 1, 4) + cell.view(1, -1, 4)).reshape(-1, 4)
+
+
+def rpn_predict_proposals(anchors, pred_objectness_logits: torch.Tensor, pred_anchor_deltas: torch.Tensor,
                           image_size: Tuple[int, int], nms_thresh: float, pre_nms_topk: int, post_nms_topk: int,
                           min_box_size: float = 0.0, training: bool = False,
                           weights=(1.0, 1.0, 1.0, 1.0)) -> Instances:
@@ -286,9 +316,13 @@ def rpn_predict_proposals(anchors: Boxes, pred_objectness_logits: torch.Tensor, 
     coin/modeling/proposal_generator/rpn.py:64,113: ``_decode_proposals`` + ``find_top_rpn_proposals``. Returns
     ``Instances(image_size)`` with ``proposal_boxes`` and ``objectness_logits`` like the reference. One launch chain on
     the device (coin_rpn_proposals) and a single 8-byte read-back of (count, status)."""
-    boxes, logits, status = ops.rpn_proposals(anchors.tensor if isinstance(anchors, Boxes) else anchors, pred_anchor_deltas,
-                                              pred_objectness_logits, image_size, pre_nms_topk, post_nms_topk, nms_thresh,
-                                              min_box_size, weights)
+    if isinstance(anchors, AnchorGrid):     # DefaultAnchorGenerator's grid, generated inside the decode kernel
+        boxes, logits, status = ops.rpn_proposals(None, pred_anchor_deltas, pred_objectness_logits, image_size, pre_nms_topk,
+                                                  post_nms_topk, nms_thresh, min_box_size, weights, grid=tuple(anchors))
+    else:
+        boxes, logits, status = ops.rpn_proposals(anchors.tensor if isinstance(anchors, Boxes) else anchors, pred_anchor_deltas,
+                                                  pred_objectness_logits, image_size, pre_nms_topk, post_nms_topk, nms_thresh,
+                                                  min_box_size, weights)
     if status & 1 and training:
         raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
     res = Instances(image_size)

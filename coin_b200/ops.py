@@ -361,29 +361,41 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: Optional[torch.
     return keep[: int(nkeep.item())]
 
 
-def rpn_proposals(anchors: torch.Tensor, deltas: torch.Tensor, logits: torch.Tensor, image_size: Tuple[float, float],
+def rpn_proposals(anchors: Optional[torch.Tensor], deltas: torch.Tensor, logits: torch.Tensor, image_size: Tuple[float, float],
                   pre_nms_topk: int, post_nms_topk: int, nms_thresh: float, min_box_size: float = 0.0,
-                  weights=(1.0, 1.0, 1.0, 1.0), scale_clamp: float = _SCALE_CLAMP, sync: bool = True):
+                  weights=(1.0, 1.0, 1.0, 1.0), scale_clamp: float = _SCALE_CLAMP, sync: bool = True, grid=None):
     """One image, one level of d2 RPN.predict_proposals (decode + find_top_rpn_proposals) in one launch chain.
+    anchors: [A,4] - or None with grid = (cell_anchors [ncell,4] (CPU tensor or list), Hf, Wf, stride, offset): the anchors of
+    DefaultAnchorGenerator are then generated inside the decode instead of being read.
     Returns (boxes[n,4], logits[n], status) - or, with sync=False, the capacity buffers, the device count and the
     device status word (bit 0: a selected row was non-finite)."""
-    anchors = _boxes(anchors, "anchors")
     deltas = _boxes(deltas, "deltas")
     logits = _f32c(logits, "logits").reshape(-1)
-    a = anchors.shape[0]
+    dev = deltas.device
+    if grid is not None:
+        cell, hf, wf, stride, offset = grid
+        cell = torch.as_tensor(cell, dtype=torch.float32).cpu().reshape(-1, 4).contiguous()
+        a = int(hf) * int(wf) * cell.shape[0]
+    else:
+        anchors = _boxes(anchors, "anchors")
+        a = anchors.shape[0]
     if deltas.shape[0] != a or logits.numel() != a:
         raise ValueError("coin_b200: anchors, deltas and logits disagree in length")
     cap = max(min(a, int(pre_nms_topk), int(post_nms_topk)), 1)
-    out_boxes = torch.empty((cap, 4), dtype=torch.float32, device=anchors.device)
-    out_logits = torch.empty((cap,), dtype=torch.float32, device=anchors.device)
-    count = torch.zeros((2,), dtype=torch.int32, device=anchors.device)   # [live rows, status]
-    ws = _workspace(lib.coin_rpn_proposals_workspace_bytes(a, int(pre_nms_topk)), anchors.device)
+    out_boxes = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+    out_logits = torch.empty((cap,), dtype=torch.float32, device=dev)
+    count = torch.zeros((2,), dtype=torch.int32, device=dev)   # [live rows, status]
+    ws = _workspace(lib.coin_rpn_proposals_workspace_bytes(a, int(pre_nms_topk)), dev)
     h, w = image_size
-    check(lib.coin_rpn_proposals(_ptr(anchors), _ptr(deltas), _ptr(logits), a, int(pre_nms_topk), int(post_nms_topk),
-                                 float(nms_thresh), float(min_box_size), float(h), float(w), float(weights[0]),
-                                 float(weights[1]), float(weights[2]), float(weights[3]), float(scale_clamp),
-                                 _ptr(out_boxes), _ptr(out_logits), _ptr(count), ctypes.c_void_p(count.data_ptr() + 4),
-                                 _ptr(ws), ws.numel(), _stream()))
+    tail = (int(pre_nms_topk), int(post_nms_topk), float(nms_thresh), float(min_box_size), float(h), float(w), float(weights[0]),
+            float(weights[1]), float(weights[2]), float(weights[3]), float(scale_clamp), _ptr(out_boxes), _ptr(out_logits),
+            _ptr(count), ctypes.c_void_p(count.data_ptr() + 4), _ptr(ws), ws.numel(), _stream())
+    if grid is not None:
+        carr = (ctypes.c_float * cell.numel())(*cell.flatten().tolist())
+        check(lib.coin_rpn_proposals_grid(carr, cell.shape[0], int(hf), int(wf), float(stride), float(offset), _ptr(deltas),
+                                          _ptr(logits), *tail))
+    else:
+        check(lib.coin_rpn_proposals(_ptr(anchors), _ptr(deltas), _ptr(logits), a, *tail))
     if not sync:
         return out_boxes, out_logits, count
     n, status = count.tolist()

@@ -411,6 +411,16 @@ int coin_rpn_proposals(const float* anchors, const float* deltas, const float* l
                        float* out_boxes, float* out_logits, int32_t* out_count, int32_t* status, void* ws,
                        size_t ws_bytes, coin_stream_t stream);
 
+/* coin_rpn_proposals with the anchors of detectron2's DefaultAnchorGenerator (<- rpn.py:64) generated on the fly:
+ * anchor(i) = cell_anchors[i % ncell] + (x, y, x, y) * stride (+ offset * stride), i = (y * Wf + x) * ncell + c, the order
+ * and the single fp32 addition of grid_anchors - bit-identical to passing the materialised [Hf*Wf*ncell, 4] array, which
+ * is never read. cell_anchors_host: HOST pointer to [ncell, 4] floats (ncell <= 32). Workspace: as coin_rpn_proposals. */
+int coin_rpn_proposals_grid(const float* cell_anchors_host, int ncell, int Hf, int Wf, float stride, float offset,
+                            const float* deltas, const float* logits, int64_t pre_nms_topk, int64_t post_nms_topk,
+                            double nms_thresh, float min_box_size, float img_h, float img_w, float wx, float wy,
+                            float ww, float wh, float scale_clamp, float* out_boxes, float* out_logits,
+                            int32_t* out_count, int32_t* status, void* ws, size_t ws_bytes, coin_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Sampling and loss-side reductions
  * ------------------------------------------------------------------------------------------- */

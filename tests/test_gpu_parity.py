@@ -634,7 +634,8 @@ def test_match_dual_teacher_empty_sides(dev):
 
 
 @pytest.mark.parametrize("hw,pre,post,min_size,seed", [((37, 75), 12000, 2000, 0.0, 1), ((37, 75), 6000, 1000, 0.0, 2),
-                                                      ((10, 12), 300, 50, 4.0, 3), ((37, 66), 12000, 2000, 0.0, 4)])
+                                                      ((10, 12), 300, 50, 4.0, 3), ((37, 66), 12000, 2000, 0.0, 4),
+                                                      ((136, 136), 2000, 300, 0.0, 5)])
 def test_rpn_predict_proposals_vs_oracle(dev, hw, pre, post, min_size, seed):
     """d2 RPN.predict_proposals (decode + find_top_rpn_proposals, <- rpn.py:64,113) for one image
     and one level, 41 625 anchors at the Foggy shape: the kept logits (copies: bit-exact, descending, ties by anchor
@@ -658,6 +659,13 @@ def test_rpn_predict_proposals_vs_oracle(dev, hw, pre, post, min_size, seed):
     assert got_s.shape == want_s.shape
     assert torch.equal(got_s, want_s)
     close(got_b, want_b, scale=float(max(size)))
+    # anchors generated on the fly from DefaultAnchorGenerator's cell anchors and grid: the same bits as the array
+    # (seed 5: 277 440 anchors, beyond the chunked selection - the radix-sort path)
+    grid = integration.AnchorGrid(integration.AnchorGrid.cell_anchors(), hf, wf, 16)
+    assert torch.equal(grid.materialise(), anchors)
+    res_g = integration.rpn_predict_proposals(grid, logits.to(dev), deltas.to(dev), size, 0.7, pre, post, min_size)
+    assert torch.equal(res_g.proposal_boxes.tensor, res.proposal_boxes.tensor)
+    assert torch.equal(res_g.objectness_logits, res.objectness_logits)
     if seed == 3:
         with pytest.raises(FloatingPointError):
             integration.rpn_predict_proposals(anchors.to(dev), logits.to(dev), deltas.to(dev), size, 0.7, pre, post,
