@@ -118,6 +118,11 @@ _SIGNATURES = {
     "coin_kl_distill_roi_bwd": (c_int, [P, P, c_int64, P, c_int, P, P, P]),
     "coin_kl_distill_rpn_fwd": (c_int, [P, P, P, c_int64, P, P, P, P]),
     "coin_kl_distill_rpn_bwd": (c_int, [P, P, P, c_int64, P, P, P, P]),
+    # evaluation
+    "coin_argsort_desc_workspace_bytes": (c_size_t, [c_int64]),
+    "coin_argsort_desc": (c_int, [P, c_int64, P, P, c_size_t, P]),
+    "coin_voc_match_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "coin_voc_match": (c_int, [P, P, P, c_int64, P, P, P, c_int64, c_double, P, P, P, c_size_t, P]),
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())

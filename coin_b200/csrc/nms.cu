@@ -869,6 +869,52 @@ using namespace coin;
 
 extern "C" size_t coin_nms_workspace_bytes(int64_t n) { return nms_pipeline_workspace_bytes(n); }
 
+// ---- stable descending argsort (the sort stage of the pipeline on its own) ------------------------------------------
+namespace coin {
+__global__ void merge_rank_order_kernel(const uint64_t* __restrict__ ckeys, int nchunks, int n, int64_t* __restrict__ order) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nchunks * kChunk) return;
+    const uint64_t key = ckeys[e];
+    if (key == ~0ull) return;
+    const int g = e / kChunk;
+    int rank = e - g * kChunk;
+    for (int h = 0; h < nchunks; ++h) {
+        if (h == g) continue;
+        const uint64_t* c = ckeys + (size_t)h * kChunk;
+        int lo = 0, hi = kChunk;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(c + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+    }
+    order[rank] = (int64_t)(key & 0xffffffffu);
+}
+}  // namespace coin
+
+extern "C" size_t coin_argsort_desc_workspace_bytes(int64_t n) {
+    return (size_t)ceil_div(std::max<int64_t>(n, 1), kChunk) * kChunk * sizeof(uint64_t) + 1024;
+}
+
+extern "C" int coin_argsort_desc(const float* scores, int64_t n, int64_t* order, void* ws, size_t ws_bytes, coin_stream_t stream) {
+    COIN_REQUIRE(n >= 0, "argsort_desc: bad n");
+    if (n == 0) return COIN_OK;
+    COIN_REQUIRE(scores && order && ws, "argsort_desc: null pointer");
+    if (n > (int64_t)kChunk * kMaxChunksSeg)
+        return fail(COIN_ERR_UNSUPPORTED, "argsort_desc: n=%lld exceeds %d keys", (long long)n, kChunk * kMaxChunksSeg);
+    if (ws_bytes < coin_argsort_desc_workspace_bytes(n)) return fail(COIN_ERR_CAPACITY, "argsort_desc: workspace too small");
+    Carver c(ws);
+    int32_t* meta = c.take<int32_t>(64);
+    const int nchunks = (int)ceil_div(n, kChunk);
+    uint64_t* ckeys = c.take<uint64_t>((size_t)nchunks * kChunk);
+    cudaStream_t s = as_stream(stream);
+    chunk_sort_kernel<<<nchunks, kSortThreads, kChunk * sizeof(uint64_t), s>>>(scores, nullptr, (int)n, nullptr, COIN_NMS_PLAIN, ckeys,
+                                                                       nullptr, meta, nullptr);
+    if (int rc = check_launch("chunk_sort_kernel")) return rc;
+    merge_rank_order_kernel<<<(unsigned)ceil_div((int64_t)nchunks * kChunk, 256), 256, 0, s>>>(ckeys, nchunks, (int)n, order);
+    return check_launch("merge_rank_order_kernel");
+}
+
 extern "C" int coin_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n,
                                 double iou_threshold, int strategy, int64_t max_keep, int64_t* keep,
                                 int32_t* nkeep, void* ws, size_t ws_bytes, coin_stream_t stream) {

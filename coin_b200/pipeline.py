@@ -50,6 +50,22 @@ def anchors_for(shape: Shape) -> torch.Tensor:
     return (shifts.view(-1, 1, 4) + base.view(1, -1, 4)).reshape(-1, 4)
 
 
+def cloud_inputs_from_cache(cache, file_names, tag: str = "RCNN") -> Dict[str, torch.Tensor]:
+    """The step's cloud-detection inputs (``{i}.cloud.gt_boxes / gt_classes / scores / probs``, boxes in the ORIGINAL image
+    frame) taken from a device-resident ``coin_b200.cache.DetectionCache``: every tensor is a VIEW into the cache's flat
+    arrays - no pickle, no deepcopy, no host-to-device copy (the reference: gdino_collector.py:86 deepcopy per lookup,
+    trainer.py:457-459 ``.to(device)`` per step). ``update(d)`` the dict of ``RoIPathStep.h2d`` with it: the step's own T3
+    stage (``process``, base.py:80-126) and knowledge separation then run on the cached rows directly."""
+    out: Dict[str, torch.Tensor] = {}
+    for i, name in enumerate(file_names):
+        inst = cache.lookup(name, tag)
+        out[f"{i}.cloud.gt_boxes"] = inst.pred_boxes.tensor
+        out[f"{i}.cloud.gt_classes"] = inst.pred_classes
+        out[f"{i}.cloud.scores"] = inst.scores
+        out[f"{i}.cloud.probs"] = inst.probs
+    return out
+
+
 class RoIPathStep:
     BBOX_WEIGHTS = (10.0, 10.0, 5.0, 5.0)   # ROI_BOX_HEAD.BBOX_REG_WEIGHTS (fast_rcnn.py:297)
     SCORE_THRESH, NMS_THRESH, TOPK = 0.05, 0.5, 100

@@ -466,6 +466,24 @@ int coin_kl_distill_rpn_fwd(const float* logits, const int8_t* distillation_labe
 int coin_kl_distill_rpn_bwd(const float* logits, const int8_t* distillation_labels, const float* teacher_probs, int64_t n,
                             const int32_t* n_valid, const float* grad_loss, float* grad_logits, coin_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Evaluation
+ * ------------------------------------------------------------------------------------------- */
+
+/* order = stable descending argsort of fp32 scores (ties: lower index first; NaN first): what np.argsort(-confidence)
+ * (cloud_pascal_voc_evaluation.py:252) and torch's descending sorts on this path compute. n <= 262144. */
+size_t coin_argsort_desc_workspace_bytes(int64_t n);
+int coin_argsort_desc(const float* scores, int64_t n, int64_t* order, void* ws, size_t ws_bytes, coin_stream_t stream);
+
+/* The TP / FP marking loop of voc_eval for one class (coin/evaluation/cloud_pascal_voc_evaluation.py:259-308).
+ * det_image: int32 [nd] image index of every detection; det_boxes: float64 [nd,4]; order: int64 [nd] detections by
+ * descending confidence; ground truth of the class as CSR: gt_boxes float64 [ng,4], gt_offsets int32 [n_images+1],
+ * gt_difficult uint8 [ng]. tp / fp: float64 [nd] in `order` (0 or 1), ready for the cumulative sums. */
+size_t coin_voc_match_workspace_bytes(int64_t nd, int64_t ng);
+int coin_voc_match(const int32_t* det_image, const double* det_boxes, const int64_t* order, int64_t nd,
+                   const double* gt_boxes, const int32_t* gt_offsets, const uint8_t* gt_difficult, int64_t ng,
+                   double ovthresh, double* tp, double* fp, void* ws, size_t ws_bytes, coin_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -460,3 +460,64 @@ def box_reg_loss(weights, proposal_boxes, gt_boxes, pred_deltas, gt_classes, num
     if normalizer is not None:
         return loss / normalizer
     return loss / max(gt_classes.numel(), 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8(f) rank 4  coin/evaluation/cloud_pascal_voc_evaluation.py:173-319  VOC AP for one class
+# ------------------------------------------------------------------------------------------------
+def voc_ap(rec, prec, use_07_metric: bool = False) -> float:
+    """cloud_pascal_voc_evaluation.py:173-202."""
+    import numpy as np
+    if use_07_metric:
+        ap = 0.0
+        for t in np.arange(0.0, 1.1, 0.1):
+            p = 0 if np.sum(rec >= t) == 0 else np.max(prec[rec >= t])
+            ap = ap + p / 11.0
+        return float(ap)
+    mrec = np.concatenate(([0.0], rec, [1.0]))
+    mpre = np.concatenate(([0.0], prec, [0.0]))
+    for i in range(mpre.size - 1, 0, -1):
+        mpre[i - 1] = np.maximum(mpre[i - 1], mpre[i])
+    i = np.where(mrec[1:] != mrec[:-1])[0]
+    return float(np.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1]))
+
+
+def voc_eval_class(det_image, det_conf, det_boxes, gt_boxes_per_image, gt_difficult_per_image, ovthresh: float = 0.5,
+                   use_07_metric: bool = False, order=None):
+    """voc_eval (cloud_pascal_voc_evaluation.py:205-319) for one class on arrays instead of files: det_image[i] indexes the
+    per-image ground-truth lists; legacy '+1' IoU in float64; a detection is a true positive when its best ground-truth box
+    (first maximum) overlaps it by more than ovthresh, is not 'difficult' and has not been claimed by a more confident one.
+    order: the np.argsort(-confidence) of the original (unstable on ties); None: stable (lower index first)."""
+    import numpy as np
+    det_conf = np.asarray(det_conf, dtype=np.float64)
+    bb_all = np.asarray(det_boxes, dtype=np.float64).reshape(-1, 4)
+    npos = int(sum(int((~np.asarray(d, dtype=bool)).sum()) for d in gt_difficult_per_image))
+    claimed = [np.zeros(len(d), dtype=bool) for d in gt_difficult_per_image]
+    sorted_ind = np.argsort(-det_conf, kind="stable") if order is None else np.asarray(order)
+    nd = len(sorted_ind)
+    tp, fp = np.zeros(nd), np.zeros(nd)
+    for d in range(nd):
+        img = int(det_image[sorted_ind[d]])
+        bb = bb_all[sorted_ind[d]]
+        bbgt = np.asarray(gt_boxes_per_image[img], dtype=np.float64).reshape(-1, 4)
+        ovmax, jmax = -np.inf, -1
+        if bbgt.size > 0:
+            iw = np.maximum(np.minimum(bbgt[:, 2], bb[2]) - np.maximum(bbgt[:, 0], bb[0]) + 1.0, 0.0)
+            ih = np.maximum(np.minimum(bbgt[:, 3], bb[3]) - np.maximum(bbgt[:, 1], bb[1]) + 1.0, 0.0)
+            inters = iw * ih
+            uni = (bb[2] - bb[0] + 1.0) * (bb[3] - bb[1] + 1.0) + (bbgt[:, 2] - bbgt[:, 0] + 1.0) * (bbgt[:, 3] - bbgt[:, 1] + 1.0) - inters
+            overlaps = inters / uni
+            ovmax, jmax = np.max(overlaps), int(np.argmax(overlaps))
+        if ovmax > ovthresh:
+            if not gt_difficult_per_image[img][jmax]:
+                if not claimed[img][jmax]:
+                    tp[d] = 1.0
+                    claimed[img][jmax] = True
+                else:
+                    fp[d] = 1.0
+        else:
+            fp[d] = 1.0
+    fp, tp = np.cumsum(fp), np.cumsum(tp)
+    rec = tp / float(npos)
+    prec = tp / np.maximum(tp + fp, np.finfo(np.float64).eps)
+    return rec, prec, voc_ap(rec, prec, use_07_metric)
