@@ -16,8 +16,10 @@ nhwc = ops.to_nhwc_f32(x)
 go = torch.randn(k, c, pooled, pooled, device=dev)
 buf = torch.zeros((n, h, w, c), device=dev)
 lv = ops._levels([buf], (1 / 16,))
+perm = ops.roi_launch_order(rois)      # as in the step: the smallest 20 % of the RoIs are launched last
 for _ in range(int(os.environ.get("ITERS", "2"))):
-    out = ops.roi_align_forward([nhwc], (1 / 16,), rois, None, (pooled, pooled), 0, True, torch.float32)
-    check(lib.coin_roi_align_bwd(lv, 1, ops._ptr(rois), ops._ptr(None), ops._ptr(go), 0, c, k, pooled, pooled, 0, 1, ops._stream()))
+    out = ops.roi_align_forward([nhwc], (1 / 16,), rois, None, (pooled, pooled), 0, True, torch.float32, perm=perm)
+    check(lib.coin_roi_align_bwd_ord(lv, 1, ops._ptr(rois), ops._ptr(None), ops._ptr(go), 0, c, k, pooled, pooled, 0, 1, ops._ptr(perm),
+                                     ops._stream()))
 torch.cuda.synchronize()
 print("ok", float(out.abs().mean()))
