@@ -53,7 +53,7 @@ _SIGNATURES = {
                                    c_int, c_int, P]),
     "coin_roi_align_bwd": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, P]),
-    "coin_roi_launch_order": (c_int, [P, c_int, P, c_int, P, P]),
+    "coin_roi_launch_order": (c_int, [P, c_int, P, c_int, c_int, P, P]),
     "coin_roi_align_fwd_ord": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_int, P, P, P]),
     "coin_roi_align_bwd_ord": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,

@@ -544,20 +544,22 @@ extern "C" int coin_roi_align_bwd_ord(const coin_level_t* grad_levels_host, int 
 // ------------------------------------------------------------------------------------------------
 // The ROIAlign grids run ~10 waves of CTAs at the reference's batch (1536 RoIs x 4 channel groups on 148 x 4 slots) and a
 // RoI's cost grows with its area, so a large RoI that happens to come last leaves most SMs idle for the length of one CTA.
-// perm = the input order with the `small_pct` % smallest RoIs (by area) moved to the end, both parts in input order
-// (measured on the bench shape: forward 333 -> 321 us, backward 323 -> 298 us; sorting everything by area is slower for
-// the forward, which wants load-heavy and store-heavy CTAs mixed). One CTA: radix-select of the area quantile over
-// shared-memory histograms, then a stable partition by a block scan.
+// perm = the input order with the `small_pct` % smallest RoIs (by area) moved to the end and the `big_pct` % largest to the
+// front, every part in input order (measured on the bench shape: forward 333 -> 321 us, backward 323 -> 298 us with the
+// small ones last; sorting everything by area is slower for the forward, which wants load-heavy and store-heavy CTAs
+// mixed). Largest first is for the rare map-sized RoI, whose CTA runs for hundreds of microseconds: it has to start with
+// the grid, not wherever the proposal list happens to hold it. One CTA: radix-select of the two area quantiles over
+// shared-memory histograms, then a stable three-way partition by a block scan.
 constexpr int kOrderThreads = 1024;
 constexpr int kOrderMax = 8192;
 
 __global__ void __launch_bounds__(kOrderThreads)
-roi_launch_order_kernel(const float* __restrict__ rois, int K_cap, const int32_t* __restrict__ k_dev, int small_pct,
+roi_launch_order_kernel(const float* __restrict__ rois, int K_cap, const int32_t* __restrict__ k_dev, int small_pct, int big_pct,
                         int32_t* __restrict__ perm) {
     extern __shared__ uint32_t okeys[];     // area bits of every live RoI
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_rank;
-    __shared__ int s_big[32], s_small[32];
+    __shared__ int s_cnt[3][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = k_dev ? min(max(__ldg(k_dev), 0), K_cap) : K_cap;
     for (int i = tid; i < K_cap; i += kOrderThreads) {
@@ -569,61 +571,73 @@ roi_launch_order_kernel(const float* __restrict__ rois, int K_cap, const int32_t
             perm[i] = i;
         }
     }
-    const int want = (int)((long long)n * small_pct / 100);
-    if (want <= 0) {
-        for (int i = tid; i < n; i += kOrderThreads) perm[i] = i;
-        return;
-    }
-    if (tid == 0) { s_prefix = 0; s_rank = (uint32_t)(want - 1); }
-    for (int pass = 3; pass >= 0; --pass) {     // the key of rank want-1, one byte per pass
-        const int shift = 8 * pass;
-        if (tid < 256) hist[tid] = 0;
+    // the key of a given rank (0-based, ascending), one byte per pass over shared-memory histograms
+    auto select = [&](int rank_wanted) -> uint32_t {
         __syncthreads();
-        const uint32_t prefix = s_prefix;
-        for (int i = tid; i < n; i += kOrderThreads) {
-            const uint32_t k = okeys[i];
-            if (pass == 3 || (k >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        if (tid == 0) { s_prefix = 0; s_rank = (uint32_t)rank_wanted; }
+        for (int pass = 3; pass >= 0; --pass) {
+            const int shift = 8 * pass;
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            for (int i = tid; i < n; i += kOrderThreads) {
+                const uint32_t k = okeys[i];
+                if (pass == 3 || (k >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t rank = s_rank, b = 0;
+                while (b < 255 && hist[b] <= rank) { rank -= hist[b]; ++b; }
+                s_rank = rank;
+                s_prefix = prefix | (b << shift);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t rank = s_rank, b = 0;
-            while (b < 255 && hist[b] <= rank) { rank -= hist[b]; ++b; }
-            s_rank = rank;
-            s_prefix = prefix | (b << shift);
-        }
-        __syncthreads();
-    }
-    const uint32_t thr = s_prefix;              // RoIs with key <= thr are "small" (ties may add a few)
+        return s_prefix;
+    };
+    const int n_small = (int)((long long)n * small_pct / 100), n_big = (int)((long long)n * big_pct / 100);
+    // RoIs with key <= lo are "small" (launched last), with key >= hi "big" (launched first); ties may add a few
+    const uint32_t lo = n_small > 0 ? select(n_small - 1) : 0u;
+    const bool any_small = n_small > 0;
+    const uint32_t hi = n_big > 0 ? select(n - n_big) : 0xffffffffu;
+    const bool any_big = n_big > 0;
+    auto cls = [&](uint32_t k) { return (any_big && k >= hi && !(any_small && k <= lo)) ? 0 : ((any_small && k <= lo) ? 2 : 1); };
     const int per = (n + kOrderThreads - 1) / kOrderThreads;
     const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
-    int nb = 0, ns = 0;
-    for (int i = i0; i < i1; ++i) { if (okeys[i] <= thr) ++ns; else ++nb; }
-    int pb = nb, ps = ns;                        // inclusive warp scans
+    int cnt[3] = {0, 0, 0};
+    for (int i = i0; i < i1; ++i) ++cnt[cls(okeys[i])];
+    int pre[3] = {cnt[0], cnt[1], cnt[2]};     // inclusive warp scans
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int vb = __shfl_up_sync(0xffffffffu, pb, o), vs = __shfl_up_sync(0xffffffffu, ps, o);
-        if (lane >= o) { pb += vb; ps += vs; }
-    }
-    if (lane == 31) { s_big[warp] = pb; s_small[warp] = ps; }
+    for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int v = __shfl_up_sync(0xffffffffu, pre[c], o);
+            if (lane >= o) pre[c] += v;
+        }
+    if (lane == 31) { s_cnt[0][warp] = pre[0]; s_cnt[1][warp] = pre[1]; s_cnt[2][warp] = pre[2]; }
     __syncthreads();
-    int ob = pb - nb, os = ps - ns, total_big = 0;
-    for (int w = 0; w < kOrderThreads / 32; ++w) {
-        if (w < warp) { ob += s_big[w]; os += s_small[w]; }
-        total_big += s_big[w];
-    }
-    for (int i = i0; i < i1; ++i) {
-        if (okeys[i] <= thr) perm[total_big + os++] = i; else perm[ob++] = i;
-    }
+    int off[3], tot[3] = {0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) off[c] = pre[c] - cnt[c];
+    for (int w = 0; w < kOrderThreads / 32; ++w)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (w < warp) off[c] += s_cnt[c][w];
+            tot[c] += s_cnt[c][w];
+        }
+    off[1] += tot[0];
+    off[2] += tot[0] + tot[1];
+    for (int i = i0; i < i1; ++i) perm[off[cls(okeys[i])]++] = i;
 }
 
-extern "C" int coin_roi_launch_order(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int32_t* perm,
-                                     coin_stream_t stream) {
-    COIN_REQUIRE(K_cap >= 0 && small_pct >= 0 && small_pct <= 100, "roi_launch_order: bad arguments");
+extern "C" int coin_roi_launch_order(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct,
+                                     int32_t* perm, coin_stream_t stream) {
+    COIN_REQUIRE(K_cap >= 0 && small_pct >= 0 && big_pct >= 0 && small_pct + big_pct <= 100, "roi_launch_order: bad arguments");
     if (K_cap == 0) return COIN_OK;
     COIN_REQUIRE(rois && perm, "roi_launch_order: null pointer");
     COIN_REQUIRE(K_cap <= kOrderMax, "roi_launch_order: K=%d exceeds %d (large grids have no tail worth ordering)", K_cap, kOrderMax);
     roi_launch_order_kernel<<<1, kOrderThreads, (size_t)K_cap * sizeof(uint32_t), as_stream(stream)>>>(rois, K_cap, k_dev,
-                                                                                                 small_pct, perm);
+                                                                                                 small_pct, big_pct, perm);
     return check_launch("roi_launch_order_kernel");
 }
 

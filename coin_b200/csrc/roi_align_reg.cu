@@ -50,7 +50,7 @@ static inline void reg_apply_carveout(K kern) {
     if (pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 }
 
-constexpr int kRegTap = 128;    // x / y tap-table entries (PW*grid_w and PH*grid_h must fit)
+constexpr int kRegTap = 256;    // x / y tap-table entries (PW*grid_w and PH*grid_h must fit: RoIs up to 18 cells per bin)
 constexpr int kRegCols = 96;    // feature columns of one RoI handled by the tables
 constexpr int kRegYEnt = 16;    // merged y-table entries per unit
 

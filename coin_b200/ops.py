@@ -111,16 +111,18 @@ ORDER_MAX_ROIS = 8192          # coin_roi_launch_order's limit
 ORDER_MIN_ROIS = 512           # below ~1 wave of CTAs there is no tail to fill
 
 
-def roi_launch_order(rois: torch.Tensor, k_dev: Optional[torch.Tensor] = None, small_pct: int = 20) -> Optional[torch.Tensor]:
+def roi_launch_order(rois: torch.Tensor, k_dev: Optional[torch.Tensor] = None, small_pct: int = 20,
+                     big_pct: int = 5) -> Optional[torch.Tensor]:
     """Launch order for roi_align_forward / roi_align_backward over the same ``rois`` (scheduling only): the smallest
-    ``small_pct`` % of the RoIs go last. Returns None where ordering does not pay (few or very many RoIs)."""
+    ``small_pct`` % of the RoIs go last, the largest ``big_pct`` % first. Returns None where ordering does not pay (few or
+    very many RoIs)."""
     rois = _f32c(rois, "rois")
     k = rois.shape[0]
-    if k < ORDER_MIN_ROIS or k > ORDER_MAX_ROIS or small_pct <= 0:
+    if k < ORDER_MIN_ROIS or k > ORDER_MAX_ROIS or (small_pct <= 0 and big_pct <= 0):
         return None
     perm = torch.empty((k,), dtype=torch.int32, device=rois.device)
     check(lib.coin_roi_launch_order(_ptr(rois), k, _ptr(None if k_dev is None else _count(k_dev)), int(small_pct),
-                                    _ptr(perm), _stream()))
+                                    int(big_pct), _ptr(perm), _stream()))
     return perm
 
 

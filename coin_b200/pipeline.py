@@ -99,9 +99,18 @@ class RoIPathStep:
         # that needs more than ~26 KB of shared memory (sort, knowledge separation) off the SMs until ROIAlign drains.
         self.roi_carveout = int(os.environ.get("COIN_STEP_ROI_CARVEOUT", "-1"))
         self.c_mode = os.environ.get("COIN_STEP_C_MODE", "with_bwd")        # side | between | with_bwd (see _run_static)
-        self.c_reg_mink = int(os.environ.get("COIN_STEP_C_REG_MINK", "0"))  # 0: register-tile kernel for the C boxes
+        # kernel of the private-box forward: RoI counts below this take the separable kernel (one 64-channel slab per CTA, 8
+        # columns of loads in flight), 0 = always the register-tile kernel. Private boxes can span the whole map (a clipped,
+        # mis-regressed detection): a register-tile CTA then walks 256 channels of a 37 x 75 map for ~1 ms. Measured over the
+        # data of the 8 ranks of a node (tools/step_seeds.py, ms per step): register-tile 256 channels 0.90 typical but 1.71 and
+        # 2.43 for the two ranks that drew such boxes; 64 channels + largest-first order 0.93-0.95 / worst 1.07; separable
+        # 0.94-0.95 / worst 0.97 - the scaling figure is the slowest rank, so the separable kernel it is.
+        self.c_reg_mink = int(os.environ.get("COIN_STEP_C_REG_MINK", "1024"))
         # launch order of the two big ROIAlign grids: the smallest p % of the RoIs go last (ops.roi_launch_order), 0: off
         self.roi_tail_pct = int(os.environ.get("COIN_STEP_ROI_TAIL_PCT", "20"))
+        self.c_tail_pct = int(os.environ.get("COIN_STEP_C_TAIL_PCT", "30"))     # the same for the private-box forward
+        self.c_head_pct = int(os.environ.get("COIN_STEP_C_HEAD_PCT", "10"))     # ... whose largest boxes go first
+        self.c_chans = int(os.environ.get("COIN_STEP_C_CHANS", "64"))           # channels per CTA when it is the register-tile kernel
         self.overlap = True         # issue independent stages on side streams (False: everything on the caller's stream)
         self.timeline = None        # tools/step_timeline.py: dict name -> external CUDA event recorded in the graph
         self.kernel_events = None   # bench.py: {"fwd": [], "bwd": []} to time the two dominant kernels live
@@ -424,10 +433,11 @@ class RoIPathStep:
         s_c.wait_event(nhwc_ready)
         if self.c_mode == "with_bwd":      # high-priority stream, but only once the forward is through: shares the
             s_c.wait_event(fwd_done)       # machine with the backward (two latency-bound kernels fill each other's gaps)
-        with torch.cuda.stream(s_c), _lib.options(COIN_ROI_REG_MINK=self.c_reg_mink, COIN_ROI_REG_CHANS_SMALL=256):
+        with torch.cuda.stream(s_c), _lib.options(COIN_ROI_REG_MINK=self.c_reg_mink, COIN_ROI_REG_CHANS_SMALL=self.c_chans):
             c_rois, n_c_rois = ops.concat_rows([seg[:3] for seg in c_segs], width_out=5)
+            c_perm = ops.roi_launch_order(c_rois, n_c_rois, small_pct=self.c_tail_pct, big_pct=self.c_head_pct)   # ~3 waves of CTAs
             out["pooled_c"] = ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32,
-                                                    k_dev=n_c_rois)
+                                                    k_dev=n_c_rois, perm=c_perm)
             slot("c_rois", n_c_rois)
             self._mark("roi.pooled_c_done")
             cat_done = s_c.record_event()

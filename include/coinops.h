@@ -274,11 +274,12 @@ int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float
                    void* ws, size_t ws_bytes, coin_stream_t stream);
 
 /* Launch order of the ROIAlign grids (scheduling only, results are unchanged): perm = 0..K-1 with the `small_pct` %
- * smallest RoIs (by box area) moved to the end, so that the last wave of CTAs holds cheap RoIs instead of whichever
- * came last (d2's ROIPooler hands the kernels the proposals in sampling order, clip_roi_heads.py:172-176).
+ * smallest RoIs (by box area) moved to the end and the `big_pct` % largest to the front (every part in input order), so
+ * that the last wave of CTAs holds cheap RoIs and a map-sized RoI starts with the grid instead of wherever it happens to
+ * stand (d2's ROIPooler hands the kernels the proposals in sampling order, clip_roi_heads.py:172-176).
  * rois: [K_cap,5]; k_dev: optional device live count; perm: int32 [K_cap] (entries beyond the live count = identity).
  * K_cap <= 8192 (larger grids have no tail worth ordering). One single-CTA launch. */
-int coin_roi_launch_order(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int32_t* perm,
+int coin_roi_launch_order(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct, int32_t* perm,
                           coin_stream_t stream);
 /* coin_roi_align_fwd_dev / coin_roi_align_bwd with a launch order from coin_roi_launch_order (perm may be NULL). */
 int coin_roi_align_fwd_ord(const coin_level_t* levels_host, int nlevels, const float* rois,

@@ -186,7 +186,7 @@ def test_roi_align_register_tile_full_size(dev):
 
 @pytest.mark.parametrize("k,live", [(1536, None), (700, 523), (8192, None)])
 def test_roi_launch_order_is_a_permutation_and_changes_nothing(dev, k, live):
-    """coin_roi_launch_order: perm is a permutation of the live RoIs with the smallest 20 % (by area) last, both parts in
+    """coin_roi_launch_order: perm is a permutation of the live RoIs with the smallest 20 % (by area) last and the largest 5 % first, every part in
     input order; entries beyond a device-side live count are the identity; the register-tile kernels launched in that
     order return the same forward bit for bit and the same backward up to the order of the fp32 atomics."""
     g = synth.gen(311 + k)
@@ -195,18 +195,20 @@ def test_roi_launch_order_is_a_permutation_and_changes_nothing(dev, k, live):
     boxes[11, 2] = boxes[11, 0] - 3.0                      # inverted box: counts as the smallest
     rois = torch.cat((torch.randint(0, 2, (k, 1), generator=g).float(), boxes), 1).to(dev)
     kd = None if live is None else torch.tensor([live], dtype=torch.int32, device=dev)
-    perm = ops.roi_launch_order(rois, kd, 20)
+    perm = ops.roi_launch_order(rois, kd, 20, 5)
     n = k if live is None else live
     p = perm.cpu().long()
     assert torch.equal(p[n:], torch.arange(n, k))
     assert torch.equal(p[:n].sort().values, torch.arange(n))
     w, h = boxes[:n, 2] - boxes[:n, 0], boxes[:n, 3] - boxes[:n, 1]
     area = torch.where((w > 0) & (h > 0), w * h, torch.zeros(()))
-    want = n * 20 // 100
-    thr = area.sort().values[want - 1]
-    small = area <= thr
+    srt = area.sort().values
+    small = area <= srt[n * 20 // 100 - 1]
+    big = (area >= srt[n - n * 5 // 100]) & ~small
     idx = torch.arange(n)
-    assert torch.equal(p[:n], torch.cat((idx[~small], idx[small])))
+    assert torch.equal(p[:n], torch.cat((idx[big], idx[~small & ~big], idx[small])))
+    only_small = ops.roi_launch_order(rois, kd, 20, 0).cpu().long()
+    assert torch.equal(only_small[:n], torch.cat((idx[~small], idx[small])))
     if k > 2048:
         return
     x = torch.randn(2, 64, 37, 75, generator=g).to(dev)
