@@ -138,9 +138,10 @@ roi_align_fwd_sep_kernel(const RoiParams p, OutT* __restrict__ out, const int cg
     __shared__ SepChunk chunks[kSepChunks];
     __shared__ int s_nchunks, s_rows, s_mode;      // mode 0: separable, 1: direct, 2: all zero
 
-    const int k = blockIdx.x / cgroups;
-    if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
-    const int cg0 = (blockIdx.x - k * cgroups) * (CC * slabs);
+    const int kk = blockIdx.x / cgroups;
+    if (p.k_dev && kk >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
+    const int k = p.perm ? __ldg(p.perm + kk) : kk;   // launch order / RoI subset (coin_roi_launch_order, coin_roi_split_by_area)
+    const int cg0 = (blockIdx.x - kk * cgroups) * (CC * slabs);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
     const coin_level_t L = p.lv[lvl];
@@ -497,9 +498,10 @@ roi_align_bwd_sep_kernel(const RoiParams p, const GT* __restrict__ go, const int
     __shared__ CEnt cent[kBwdEnt];
     __shared__ int s_mode, s_cmin, s_cmax;         // mode 0: separable, 1: direct
 
-    const int k = blockIdx.x / cgroups;
-    if (p.k_dev && k >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
-    const int cg0 = (blockIdx.x - k * cgroups) * (CC * slabs);
+    const int kk = blockIdx.x / cgroups;
+    if (p.k_dev && kk >= __ldg(p.k_dev)) return;   // capacity launch: RoI beyond the live count
+    const int k = p.perm ? __ldg(p.perm + kk) : kk;   // launch order / RoI subset (coin_roi_launch_order, coin_roi_split_by_area)
+    const int cg0 = (blockIdx.x - kk * cgroups) * (CC * slabs);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int lvl = p.roi_level ? __ldg(p.roi_level + k) : 0;
     const coin_level_t L = p.lv[lvl];

@@ -112,10 +112,11 @@ ORDER_MIN_ROIS = 512           # below ~1 wave of CTAs there is no tail to fill
 
 
 def roi_launch_order(rois: torch.Tensor, k_dev: Optional[torch.Tensor] = None, small_pct: int = 20,
-                     big_pct: int = 5) -> Optional[torch.Tensor]:
+                     big_pct: int = 0) -> Optional[torch.Tensor]:
     """Launch order for roi_align_forward / roi_align_backward over the same ``rois`` (scheduling only): the smallest
-    ``small_pct`` % of the RoIs go last, the largest ``big_pct`` % first. Returns None where ordering does not pay (few or
-    very many RoIs)."""
+    ``small_pct`` % of the RoIs go last, the largest ``big_pct`` % first (default 0: on the bench shape largest-first costs the
+    forward 4 %, which wants load-heavy and store-heavy CTAs mixed; it is for launches of few waves that may hold a map-sized
+    RoI). Returns None where ordering does not pay (few or very many RoIs)."""
     rois = _f32c(rois, "rois")
     k = rois.shape[0]
     if k < ORDER_MIN_ROIS or k > ORDER_MAX_ROIS or (small_pct <= 0 and big_pct <= 0):
@@ -124,6 +125,20 @@ def roi_launch_order(rois: torch.Tensor, k_dev: Optional[torch.Tensor] = None, s
     check(lib.coin_roi_launch_order(_ptr(rois), k, _ptr(None if k_dev is None else _count(k_dev)), int(small_pct),
                                     int(big_pct), _ptr(perm), _stream()))
     return perm
+
+
+def roi_split_by_area(rois: torch.Tensor, k_dev: Optional[torch.Tensor], area_thr: float, side_thr: float = float("inf")):
+    """(perm_small, perm_big, counts): index lists of the "big" RoIs (box area > ``area_thr`` px^2 or a side > ``side_thr``
+    px) and of the rest, with their device lengths counts[0:1] (small), counts[1:2] (big) - for pooling the two subsets
+    with different kernels into one output."""
+    rois = _f32c(rois, "rois")
+    k = rois.shape[0]
+    ps = torch.empty((max(k, 1),), dtype=torch.int32, device=rois.device)
+    pb = torch.empty((max(k, 1),), dtype=torch.int32, device=rois.device)
+    counts = torch.zeros((2,), dtype=torch.int32, device=rois.device)
+    check(lib.coin_roi_split_by_area(_ptr(rois), k, _ptr(None if k_dev is None else _count(k_dev)), float(area_thr), min(float(side_thr), 3.0e38),
+                                     _ptr(ps), _ptr(pb), _ptr(counts), _stream()))
+    return ps, pb, counts
 
 
 def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,

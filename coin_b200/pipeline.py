@@ -110,7 +110,10 @@ class RoIPathStep:
         self.roi_tail_pct = int(os.environ.get("COIN_STEP_ROI_TAIL_PCT", "20"))
         self.c_tail_pct = int(os.environ.get("COIN_STEP_C_TAIL_PCT", "30"))     # the same for the private-box forward
         self.c_head_pct = int(os.environ.get("COIN_STEP_C_HEAD_PCT", "10"))     # ... whose largest boxes go first
-        self.c_chans = int(os.environ.get("COIN_STEP_C_CHANS", "64"))           # channels per CTA when it is the register-tile kernel
+        self.c_chans = int(os.environ.get("COIN_STEP_C_CHANS", "256"))          # channels per CTA when it is the register-tile kernel
+        # private boxes larger than this (px^2; 600 feature cells at stride 16) go to the separable kernel, 0: no split
+        self.c_split_area = float(os.environ.get("COIN_STEP_C_SPLIT_AREA", str(600 * 256)))
+        self.c_split_side = float(os.environ.get("COIN_STEP_C_SPLIT_SIDE", "640"))      # ... or with a side longer than this (px)
         self.overlap = True         # issue independent stages on side streams (False: everything on the caller's stream)
         self.timeline = None        # tools/step_timeline.py: dict name -> external CUDA event recorded in the graph
         self.kernel_events = None   # bench.py: {"fwd": [], "bwd": []} to time the two dominant kernels live
@@ -433,11 +436,25 @@ class RoIPathStep:
         s_c.wait_event(nhwc_ready)
         if self.c_mode == "with_bwd":      # high-priority stream, but only once the forward is through: shares the
             s_c.wait_event(fwd_done)       # machine with the backward (two latency-bound kernels fill each other's gaps)
-        with torch.cuda.stream(s_c), _lib.options(COIN_ROI_REG_MINK=self.c_reg_mink, COIN_ROI_REG_CHANS_SMALL=self.c_chans):
+        with torch.cuda.stream(s_c):
             c_rois, n_c_rois = ops.concat_rows([seg[:3] for seg in c_segs], width_out=5)
-            c_perm = ops.roi_launch_order(c_rois, n_c_rois, small_pct=self.c_tail_pct, big_pct=self.c_head_pct)   # ~3 waves of CTAs
-            out["pooled_c"] = ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32,
-                                                    k_dev=n_c_rois, perm=c_perm)
+            if self.c_split_area > 0:
+                # private boxes can span the whole map (a clipped, mis-regressed detection); one register-tile CTA then
+                # walks 256 channels of a 37 x 75 map for ~1 ms. The few boxes above the area threshold are pooled by the
+                # separable kernel (first: they take longest), everything else by the register-tile kernel, same output.
+                p_small, p_big, c_cnt = ops.roi_split_by_area(c_rois, n_c_rois, self.c_split_area, self.c_split_side)
+                pooled_c = torch.empty((c_rois.shape[0], sh.channels) + size, dtype=torch.float32, device=dev)
+                with _lib.options(COIN_ROI_REG=0):
+                    ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32, k_dev=c_cnt[1:2],
+                                          perm=p_big, out=pooled_c)
+                with _lib.options(COIN_ROI_REG_MINK=0, COIN_ROI_REG_CHANS_SMALL=self.c_chans):
+                    ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32, k_dev=c_cnt[0:1],
+                                          perm=p_small, out=pooled_c)
+                out["pooled_c"] = pooled_c
+            else:
+                with _lib.options(COIN_ROI_REG_MINK=self.c_reg_mink, COIN_ROI_REG_CHANS_SMALL=self.c_chans):
+                    out["pooled_c"] = ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32,
+                                                            k_dev=n_c_rois)
             slot("c_rois", n_c_rois)
             self._mark("roi.pooled_c_done")
             cat_done = s_c.record_event()

@@ -281,7 +281,13 @@ int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float
  * K_cap <= 8192 (larger grids have no tail worth ordering). One single-CTA launch. */
 int coin_roi_launch_order(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct, int32_t* perm,
                           coin_stream_t stream);
-/* coin_roi_align_fwd_dev / coin_roi_align_bwd with a launch order from coin_roi_launch_order (perm may be NULL). */
+/* Two RoI index lists by box size (pixels, input order kept): perm_big = RoIs with area > area_thr or a side > side_thr,
+ * perm_small = the rest; counts = int32 [2] device lengths (small, big). With coin_roi_align_fwd_ord (perm = a list, k_dev = its length, same `out`) a caller
+ * pools the two subsets with different kernels: the step sends the rare map-sized private box to the separable kernel. */
+int coin_roi_split_by_area(const float* rois, int K_cap, const int32_t* k_dev, float area_thr, float side_thr,
+                           int32_t* perm_small, int32_t* perm_big, int32_t* counts, coin_stream_t stream);
+/* coin_roi_align_fwd_dev / coin_roi_align_bwd with a launch order / RoI subset (perm may be NULL): CTA group i works on RoI
+ * perm[i], i < *k_dev. */
 int coin_roi_align_fwd_ord(const coin_level_t* levels_host, int nlevels, const float* rois,
                            const int32_t* roi_level, void* out, int out_dtype, int C, int K_cap, int PH,
                            int PW, int sampling_ratio, int aligned, const int32_t* k_dev, const int32_t* perm,
