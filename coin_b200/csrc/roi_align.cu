@@ -630,16 +630,17 @@ roi_launch_order_kernel(const float* __restrict__ rois, int K_cap, const int32_t
     for (int i = i0; i < i1; ++i) perm[off[cls(okeys[i])]++] = i;
 }
 
-// Two RoI lists by box size (input order kept): "big" = area > area_thr or a side > side_thr, and the rest, with their
+// Two RoI lists by box size (in input order, or in the order of a launch order `order`): "big" = area > area_thr or a side > side_thr, and the rest, with their
 // device-side lengths. The step pools the few map-sized or map-wide private boxes with the separable kernel and the rest
 // with the register-tile kernel (a register-tile CTA walks such a box for 0.2 - 1 ms: tools/c_box_probe.py).
 __global__ void __launch_bounds__(kOrderThreads)
 roi_split_by_area_kernel(const float* __restrict__ rois, int K_cap, const int32_t* __restrict__ k_dev, float area_thr,
-                         float side_thr, int32_t* __restrict__ perm_small, int32_t* __restrict__ perm_big, int32_t* __restrict__ counts) {
+                         float side_thr, int big_cap, const int32_t* __restrict__ order, int32_t* __restrict__ perm_small, int32_t* __restrict__ perm_big, int32_t* __restrict__ counts) {
     __shared__ int s_cnt[2][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = k_dev ? min(max(__ldg(k_dev), 0), K_cap) : K_cap;
-    auto is_big = [&](int i) {
+    auto is_big = [&](int pos) {
+        const int i = order ? order[pos] : pos;
         const float w = __ldg(rois + 5 * i + 3) - __ldg(rois + 5 * i + 1), h = __ldg(rois + 5 * i + 4) - __ldg(rois + 5 * i + 2);
         return w > 0.0f && h > 0.0f && (w * h > area_thr || w > side_thr || h > side_thr);
     };
@@ -647,35 +648,40 @@ roi_split_by_area_kernel(const float* __restrict__ rois, int K_cap, const int32_
     const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
     int nb = 0;
     for (int i = i0; i < i1; ++i) nb += is_big(i);
-    const int ns = (i1 - i0) - nb;
-    int pb = nb, ps = ns;
+    int pb = nb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int vb = __shfl_up_sync(0xffffffffu, pb, o), vs = __shfl_up_sync(0xffffffffu, ps, o);
-        if (lane >= o) { pb += vb; ps += vs; }
+        const int vb = __shfl_up_sync(0xffffffffu, pb, o);
+        if (lane >= o) pb += vb;
     }
-    if (lane == 31) { s_cnt[0][warp] = ps; s_cnt[1][warp] = pb; }
+    if (lane == 31) s_cnt[1][warp] = pb;
     __syncthreads();
-    int os = ps - ns, ob = pb - nb, ts = 0, tbig = 0;
+    int ob = pb - nb, tbig = 0;
     for (int w = 0; w < kOrderThreads / 32; ++w) {
-        if (w < warp) { os += s_cnt[0][w]; ob += s_cnt[1][w]; }
-        ts += s_cnt[0][w];
+        if (w < warp) ob += s_cnt[1][w];
         tbig += s_cnt[1][w];
     }
+    // the big list holds at most big_cap RoIs (its launch is sized for that); big RoIs beyond it stay in the other list
     for (int i = i0; i < i1; ++i) {
-        if (is_big(i)) perm_big[ob++] = i; else perm_small[os++] = i;
+        const int idx = order ? order[i] : i;
+        if (is_big(i)) {
+            if (ob < big_cap) perm_big[ob] = idx; else perm_small[i - big_cap] = idx;
+            ++ob;
+        } else {
+            perm_small[i - min(ob, big_cap)] = idx;
+        }
     }
-    if (tid == 0) { counts[0] = ts; counts[1] = tbig; }
+    if (tid == 0) { counts[1] = min(tbig, big_cap); counts[0] = n - min(tbig, big_cap); }
 }
 
 extern "C" int coin_roi_split_by_area(const float* rois, int K_cap, const int32_t* k_dev, float area_thr, float side_thr,
-                                      int32_t* perm_small,
+                                      int big_cap, const int32_t* order, int32_t* perm_small,
                                       int32_t* perm_big, int32_t* counts, coin_stream_t stream) {
-    COIN_REQUIRE(K_cap >= 0 && counts, "roi_split_by_area: bad arguments");
+    COIN_REQUIRE(K_cap >= 0 && big_cap >= 0 && counts, "roi_split_by_area: bad arguments");
     cudaStream_t s = as_stream(stream);
     if (K_cap == 0) { fill_bytes(counts, 0, 2 * sizeof(int32_t), s); return COIN_OK; }
     COIN_REQUIRE(rois && perm_small && perm_big, "roi_split_by_area: null pointer");
-    roi_split_by_area_kernel<<<1, kOrderThreads, 0, s>>>(rois, K_cap, k_dev, area_thr, side_thr, perm_small, perm_big, counts);
+    roi_split_by_area_kernel<<<1, kOrderThreads, 0, s>>>(rois, K_cap, k_dev, area_thr, side_thr, big_cap, order, perm_small, perm_big, counts);
     return check_launch("roi_split_by_area_kernel");
 }
 

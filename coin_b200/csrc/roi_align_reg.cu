@@ -797,11 +797,10 @@ int launch_roi_align_bwd_reg(const RoiParams& p, const void* grad_out, int grad_
 bool roi_align_fwd_reg_supported(const RoiParams& p, int out_dtype) {
     if (reg_env("COIN_ROI_REG", 1) == 0) return false;
     if ((out_dtype != COIN_F32 && out_dtype != COIN_F16) || p.C % 32 != 0) return false;
-    // few RoIs (the step's private-box call, <= ~150 boxes that can each span the whole map): the grid cannot hide the
-    // load latency of this kernel's long per-warp column walks, and the call runs next to the backward, which owns the
-    // register file; the separable kernel (one 64-channel slab per CTA, 8 columns of loads in flight) finishes it in
-    // time (measured on the step's timeline: 1273 vs 1531 us for the heaviest seed). COIN_ROI_REG_MINK=0: always.
-    if (p.K < reg_env("COIN_ROI_REG_MINK", 1024) && p.k_dev) return false;
+    // COIN_ROI_REG_MINK = n: capacity launches (device-side RoI count) of fewer than n RoIs take the separable kernel. Off by
+    // default: what made such launches slow were map-sized RoIs (one CTA walking 256 channels of the whole map), and callers
+    // now divert those to the separable kernel themselves (ops.roi_align_forward_planned, coin_roi_split_by_area).
+    if (p.K < reg_env("COIN_ROI_REG_MINK", 0) && p.k_dev) return false;
     return (p.PH == 14 && p.PW == 14) || (p.PH == 7 && p.PW == 7);
 }
 

@@ -127,29 +127,73 @@ def roi_launch_order(rois: torch.Tensor, k_dev: Optional[torch.Tensor] = None, s
     return perm
 
 
-def roi_split_by_area(rois: torch.Tensor, k_dev: Optional[torch.Tensor], area_thr: float, side_thr: float = float("inf")):
+BIG_ROI_CELLS = 600            # a RoI covering more feature cells than this, or wider / taller than BIG_ROI_SIDE cells, is "big":
+BIG_ROI_SIDE = 40              # a register-tile CTA walks it for 0.2 - 1 ms (tools/c_box_probe.py); the separable kernel pools it
+BIG_ROI_CAP = 32               # ... up to this many per call (the capacity of that second, normally empty, launch)
+
+
+def roi_split_by_area(rois: torch.Tensor, k_dev: Optional[torch.Tensor], area_thr: float, side_thr: float = float("inf"),
+                      order: Optional[torch.Tensor] = None, big_cap: Optional[int] = None):
     """(perm_small, perm_big, counts): index lists of the "big" RoIs (box area > ``area_thr`` px^2 or a side > ``side_thr``
-    px) and of the rest, with their device lengths counts[0:1] (small), counts[1:2] (big) - for pooling the two subsets
-    with different kernels into one output."""
+    px) and of the rest (in input order, or in the order of ``order``), with their device lengths counts[0:1] (small),
+    counts[1:2] (big) - for pooling the two subsets with different kernels into one output."""
     rois = _f32c(rois, "rois")
     k = rois.shape[0]
+    big_cap = k if big_cap is None else min(int(big_cap), k)
     ps = torch.empty((max(k, 1),), dtype=torch.int32, device=rois.device)
-    pb = torch.empty((max(k, 1),), dtype=torch.int32, device=rois.device)
+    pb = torch.empty((max(big_cap, 1),), dtype=torch.int32, device=rois.device)
     counts = torch.zeros((2,), dtype=torch.int32, device=rois.device)
     check(lib.coin_roi_split_by_area(_ptr(rois), k, _ptr(None if k_dev is None else _count(k_dev)), float(area_thr), min(float(side_thr), 3.0e38),
-                                     _ptr(ps), _ptr(pb), _ptr(counts), _stream()))
+                                     big_cap, _ptr(order), _ptr(ps), _ptr(pb), _ptr(counts), _stream()))
     return ps, pb, counts
+
+
+def roi_align_forward_planned(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
+                              output_size: Tuple[int, int], sampling_ratio: int, aligned: bool, out_dtype: torch.dtype,
+                              order: Optional[torch.Tensor] = None, k_dev: Optional[torch.Tensor] = None,
+                              events: Optional[list] = None, plan=None, big_stream=None) -> torch.Tensor:
+    """Single-level roi_align_forward that is robust to map-sized RoIs: the RoIs are split on the device by size
+    (BIG_ROI_CELLS / BIG_ROI_SIDE feature cells); the big ones are pooled by the separable kernel, the rest by the default
+    (register-tile) kernel in the launch order ``order``; one output. plan: a precomputed roi_split_by_area result.
+    big_stream: optional side stream for the (normally empty) launch of the big RoIs, so that it does not sit in front of the
+    main launch; the current stream waits for it before returning."""
+    if _lib.get_option("COIN_ROI_EXACT", 0) != 0:     # the parity kernels pool every RoI the same way
+        return roi_align_forward(feats_nhwc, scales, rois, None, output_size, sampling_ratio, aligned, out_dtype, events, k_dev)
+    stride = 1.0 / float(scales[0])
+    if plan is None:
+        plan = roi_split_by_area(rois, k_dev, BIG_ROI_CELLS * stride * stride, BIG_ROI_SIDE * stride, order, BIG_ROI_CAP)
+    p_small, p_big, cnt = plan
+    k, c = rois.shape[0], int(feats_nhwc[0].shape[3])
+    out = torch.empty((k, c) + tuple(output_size), dtype=out_dtype, device=rois.device)
+    def pool_big():     # the big list: a launch sized for its capacity (a few CTAs), normally empty
+        with _lib.options(COIN_ROI_REG=0):
+            roi_align_forward(feats_nhwc, scales, rois, None, output_size, sampling_ratio, aligned, out_dtype, k_dev=cnt[1:2],
+                              perm=p_big, out=out, k_launch=int(p_big.shape[0]))
+    big_done = None
+    if big_stream is None:
+        pool_big()
+    else:
+        big_stream.wait_event(torch.cuda.current_stream().record_event())
+        with torch.cuda.stream(big_stream):
+            pool_big()
+            big_done = big_stream.record_event()
+    roi_align_forward(feats_nhwc, scales, rois, None, output_size, sampling_ratio, aligned, out_dtype, events=events,
+                      k_dev=cnt[0:1], perm=p_small, out=out)
+    if big_done is not None:
+        torch.cuda.current_stream().wait_event(big_done)
+    return out
 
 
 def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
                       roi_level: Optional[torch.Tensor], output_size: Tuple[int, int], sampling_ratio: int,
                       aligned: bool, out_dtype: torch.dtype, events: Optional[list] = None,
                       k_dev: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,
-                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, k_launch: Optional[int] = None) -> torch.Tensor:
     """events: optional list; a (start, end) CUDA-event pair bracketing the kernel launch is appended.
     k_dev: optional device int32 live RoI count (<= K): rows of the result beyond it are not written.
     perm: optional launch order from ``roi_launch_order`` (same rois).
-    out: optional preallocated contiguous [K, C, PH, PW] result (e.g. a row range of a larger buffer)."""
+    out: optional preallocated contiguous [K, C, PH, PW] result (e.g. a row range of a larger buffer).
+    k_launch: with perm, the number of RoI slots to launch (<= K; the live count *k_dev must not exceed it)."""
     rois = _f32c(rois, "rois")
     if rois.dim() != 2 or rois.shape[1] != 5:
         raise ValueError(f"coin_b200: rois must have shape [K, 5], got {tuple(rois.shape)}")
@@ -164,7 +208,8 @@ def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float
     pair = _event_pair(events)
     if perm is not None:
         check(lib.coin_roi_align_fwd_ord(_levels(feats_nhwc, scales), len(feats_nhwc), _ptr(rois), _ptr(roi_level),
-                                         _ptr(out), _dtype_code(out_dtype), c, k, ph, pw, int(sampling_ratio),
+                                         _ptr(out), _dtype_code(out_dtype), c, k if k_launch is None else min(int(k_launch), k),
+                                         ph, pw, int(sampling_ratio),
                                          int(bool(aligned)), _ptr(None if k_dev is None else _count(k_dev)),
                                          _ptr(perm), _stream()))
     elif k_dev is None:

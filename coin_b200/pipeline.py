@@ -191,8 +191,8 @@ class RoIPathStep:
             rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
                               for i in range(n_img)])
             perm = ops.roi_launch_order(rois, small_pct=self.roi_tail_pct)
-            out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
-                                                  events=ev["fwd"] if ev else None, perm=perm)
+            out["pooled"] = ops.roi_align_forward_planned([nhwc], scale, rois, size, 0, True, torch.float32, order=perm,
+                                                          events=ev["fwd"] if ev else None)
             if backward:
                 n, c, h, w = d["features"].shape
                 out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
@@ -322,6 +322,9 @@ class RoIPathStep:
             rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
                               for i in range(n_img)])
             perm = ops.roi_launch_order(rois, small_pct=self.roi_tail_pct)   # beside the layout transform below
+            stride = float(sh.stride)      # map-sized RoIs (if any) go to the separable kernel: ops.roi_align_forward_planned
+            plan = ops.roi_split_by_area(rois, None, ops.BIG_ROI_CELLS * stride * stride, ops.BIG_ROI_SIDE * stride, perm,
+                                         ops.BIG_ROI_CAP)
             rois_ready = s_img[2 * n_img].record_event()
         with torch.cuda.stream(s_roi):
             nhwc = ops.to_nhwc_f32(d["features"])
@@ -371,8 +374,9 @@ class RoIPathStep:
         with torch.cuda.stream(s_roi), _lib.options(**roi_opts):
             self._mark("roi.begin_fwd")
             ev = self.kernel_events
-            out["pooled"] = ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32,
-                                                  events=ev["fwd"] if ev else None, perm=perm)
+            out["pooled"] = ops.roi_align_forward_planned([nhwc], scale, rois, size, 0, True, torch.float32, plan=plan,
+                                                          events=ev["fwd"] if ev else None,
+                                                          big_stream=s_img[2 * n_img] if self.overlap else None)
             self._mark("roi.end_fwd")
             fwd_done = s_roi.record_event()
 
@@ -440,17 +444,13 @@ class RoIPathStep:
             c_rois, n_c_rois = ops.concat_rows([seg[:3] for seg in c_segs], width_out=5)
             if self.c_split_area > 0:
                 # private boxes can span the whole map (a clipped, mis-regressed detection); one register-tile CTA then
-                # walks 256 channels of a 37 x 75 map for ~1 ms. The few boxes above the area threshold are pooled by the
+                # walks 256 channels of a 37 x 75 map for ~1 ms. The few boxes above the size thresholds are pooled by the
                 # separable kernel (first: they take longest), everything else by the register-tile kernel, same output.
-                p_small, p_big, c_cnt = ops.roi_split_by_area(c_rois, n_c_rois, self.c_split_area, self.c_split_side)
-                pooled_c = torch.empty((c_rois.shape[0], sh.channels) + size, dtype=torch.float32, device=dev)
-                with _lib.options(COIN_ROI_REG=0):
-                    ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32, k_dev=c_cnt[1:2],
-                                          perm=p_big, out=pooled_c)
-                with _lib.options(COIN_ROI_REG_MINK=0, COIN_ROI_REG_CHANS_SMALL=self.c_chans):
-                    ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32, k_dev=c_cnt[0:1],
-                                          perm=p_small, out=pooled_c)
-                out["pooled_c"] = pooled_c
+                plan_c = ops.roi_split_by_area(c_rois, n_c_rois, self.c_split_area, self.c_split_side, None, ops.BIG_ROI_CAP)
+                with _lib.options(COIN_ROI_REG_CHANS_SMALL=self.c_chans):
+                    out["pooled_c"] = ops.roi_align_forward_planned([nhwc], scale, c_rois, size, 0, True, torch.float32,
+                                                                    plan=plan_c,
+                                                                    big_stream=s_img[2 * n_img + 1] if self.overlap and n_img > 1 else None)
             else:
                 with _lib.options(COIN_ROI_REG_MINK=self.c_reg_mink, COIN_ROI_REG_CHANS_SMALL=self.c_chans):
                     out["pooled_c"] = ops.roi_align_forward([nhwc], scale, c_rois, None, size, 0, True, torch.float32,
@@ -520,7 +520,8 @@ class RoIPathStep:
         perm = ops.roi_launch_order(rois, small_pct=self.roi_tail_pct)     # as in the step (its own small launch)
         for it in range(warmup + iters):
             ev = events if it >= warmup else {"fwd": None, "bwd": None}
-            ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32, events=ev["fwd"], perm=perm)
+            ops.roi_align_forward([nhwc], scale, rois, None, size, 0, True, torch.float32, events=ev["fwd"], perm=perm)   # (the
+            # step's split finds no map-sized RoI among the sampled ones: this IS the launch it makes)
             ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size, 0, True, [torch.float32],
                                    events=ev["bwd"], perm=perm)
 

@@ -281,11 +281,14 @@ int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float
  * K_cap <= 8192 (larger grids have no tail worth ordering). One single-CTA launch. */
 int coin_roi_launch_order(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct, int32_t* perm,
                           coin_stream_t stream);
-/* Two RoI index lists by box size (pixels, input order kept): perm_big = RoIs with area > area_thr or a side > side_thr,
- * perm_small = the rest; counts = int32 [2] device lengths (small, big). With coin_roi_align_fwd_ord (perm = a list, k_dev = its length, same `out`) a caller
+/* Two RoI index lists by box size (pixels): perm_big = RoIs with area > area_thr or a side > side_thr, perm_small = the
+ * rest, both in input order - or in the order of `order` (a coin_roi_launch_order result, may be NULL);
+ * perm_big holds at most big_cap RoIs (the capacity its launch is sized for; further big RoIs stay in perm_small);
+ * counts = int32 [2] device lengths (small, big). With coin_roi_align_fwd_ord (perm = a list, k_dev = its length, same `out`) a caller
  * pools the two subsets with different kernels: the step sends the rare map-sized private box to the separable kernel. */
-int coin_roi_split_by_area(const float* rois, int K_cap, const int32_t* k_dev, float area_thr, float side_thr,
-                           int32_t* perm_small, int32_t* perm_big, int32_t* counts, coin_stream_t stream);
+int coin_roi_split_by_area(const float* rois, int K_cap, const int32_t* k_dev, float area_thr, float side_thr, int big_cap,
+                           const int32_t* order, int32_t* perm_small, int32_t* perm_big, int32_t* counts,
+                           coin_stream_t stream);
 /* coin_roi_align_fwd_dev / coin_roi_align_bwd with a launch order / RoI subset (perm may be NULL): CTA group i works on RoI
  * perm[i], i < *k_dev. */
 int coin_roi_align_fwd_ord(const coin_level_t* levels_host, int nlevels, const float* rois,

@@ -224,6 +224,41 @@ def test_roi_launch_order_is_a_permutation_and_changes_nothing(dev, k, live):
         assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max())
 
 
+def test_roi_align_map_sized_rois_do_not_stall_the_grid(dev):
+    """A clipped, mis-regressed detection is a RoI the size of the map; for the register-tile kernel that is one CTA walking
+    256 channels of 37 x 75 cells for ~1 ms (it turned rank 1 of an 8-GPU run from 0.92 into 2.4 ms per step). The layer
+    splits the RoIs by size on the device and pools the big ones with the separable kernel: same numbers as torchvision,
+    and the call with such RoIs stays within 2x of the call without them."""
+    g = synth.gen(4711)
+    x = torch.randn(1, 1024, 37, 75, generator=g)
+    boxes = synth.random_boxes(g, 600, 600, 1200)
+    big = torch.tensor([[0.0, 0.0, 1200.0, 600.0], [0.0, 431.2, 1200.0, 434.8], [3.0, 0.0, 40.0, 600.0], [0.0, 0.0, 1199.0, 599.0]])
+    layer = coin_b200.ROIAlign(14, 1.0 / 16, 0, True)
+    xd = x.to(dev)
+
+    def rois_of(b):
+        return torch.cat((torch.zeros(len(b), 1), b), 1).to(dev)
+
+    def timed(r):
+        for _ in range(3):
+            layer(xd, r)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            layer(xd, r)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 5
+
+    mixed = torch.cat((boxes[:300], big, boxes[300:]))
+    out = layer(xd, rois_of(mixed))
+    sel = torch.tensor([0, 150, 299, 300, 301, 302, 303, 304, 603])
+    ref = torchvision.ops.roi_align(x[:, :64], rois_of(mixed).cpu()[sel], (14, 14), 1.0 / 16, 0, True)
+    close(out[sel.to(dev), :64], ref, scale=float(x.abs().max()))
+    t_plain, t_mixed = timed(rois_of(boxes)), timed(rois_of(mixed))
+    assert t_mixed < 2.0 * t_plain + 0.05, (t_plain, t_mixed)
+
+
 def test_roi_align_non_finite_features(dev):
     """Inf / NaN cells in the feature map (fp16 overflow under AMP). torchvision multiplies a cell only when it is one of
     the 4 taps of a sample, so only RoIs that sample the cell turn non-finite. Contract of this library:
