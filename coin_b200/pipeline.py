@@ -99,21 +99,18 @@ class RoIPathStep:
         # that needs more than ~26 KB of shared memory (sort, knowledge separation) off the SMs until ROIAlign drains.
         self.roi_carveout = int(os.environ.get("COIN_STEP_ROI_CARVEOUT", "-1"))
         self.c_mode = os.environ.get("COIN_STEP_C_MODE", "with_bwd")        # side | between | with_bwd (see _run_static)
-        # kernel of the private-box forward: RoI counts below this take the separable kernel (one 64-channel slab per CTA, 8
-        # columns of loads in flight), 0 = always the register-tile kernel. Private boxes can span the whole map (a clipped,
-        # mis-regressed detection): a register-tile CTA then walks 256 channels of a 37 x 75 map for ~1 ms. Measured over the
-        # data of the 8 ranks of a node (tools/step_seeds.py, ms per step): register-tile 256 channels 0.90 typical but 1.71 and
-        # 2.43 for the two ranks that drew such boxes; 64 channels + largest-first order 0.93-0.95 / worst 1.07; separable
-        # 0.94-0.95 / worst 0.97 - the scaling figure is the slowest rank, so the separable kernel it is.
-        self.c_reg_mink = int(os.environ.get("COIN_STEP_C_REG_MINK", "1024"))
         # launch order of the two big ROIAlign grids: the smallest p % of the RoIs go last (ops.roi_launch_order), 0: off
         self.roi_tail_pct = int(os.environ.get("COIN_STEP_ROI_TAIL_PCT", "20"))
-        self.c_tail_pct = int(os.environ.get("COIN_STEP_C_TAIL_PCT", "30"))     # the same for the private-box forward
-        self.c_head_pct = int(os.environ.get("COIN_STEP_C_HEAD_PCT", "10"))     # ... whose largest boxes go first
-        self.c_chans = int(os.environ.get("COIN_STEP_C_CHANS", "256"))          # channels per CTA when it is the register-tile kernel
-        # private boxes larger than this (px^2; 600 feature cells at stride 16) go to the separable kernel, 0: no split
+        # The private-box forward. Private boxes can span the whole map (a clipped, mis-regressed detection): a register-tile
+        # CTA then walks 256 channels of a 37 x 75 map for up to ~1 ms, and the step time must not depend on which images a
+        # rank draws. Boxes above the size thresholds (px^2, 600 feature cells at stride 16; or a side in px) go to the
+        # separable kernel, the rest to the register-tile kernel (profiles/r02_step_schedule.md section 3: 0.917-0.933 ms for
+        # the data of all 8 ranks; 0.90 typical / 2.43 worst without the split). c_split_area = 0: no split, and launches of
+        # fewer than c_reg_mink RoIs take the separable kernel entirely (round 1's choice: 0.94-0.97 ms).
         self.c_split_area = float(os.environ.get("COIN_STEP_C_SPLIT_AREA", str(600 * 256)))
-        self.c_split_side = float(os.environ.get("COIN_STEP_C_SPLIT_SIDE", "640"))      # ... or with a side longer than this (px)
+        self.c_split_side = float(os.environ.get("COIN_STEP_C_SPLIT_SIDE", "640"))
+        self.c_reg_mink = int(os.environ.get("COIN_STEP_C_REG_MINK", "1024"))
+        self.c_chans = int(os.environ.get("COIN_STEP_C_CHANS", "256"))          # channels per register-tile CTA of that launch
         self.overlap = True         # issue independent stages on side streams (False: everything on the caller's stream)
         self.timeline = None        # tools/step_timeline.py: dict name -> external CUDA event recorded in the graph
         self.kernel_events = None   # bench.py: {"fwd": [], "bwd": []} to time the two dominant kernels live
