@@ -302,23 +302,34 @@ def main():
     ar_mb = args.allreduce_mb
     if ar_mb is None:
         ar_mb = 200.0 if (args.workload == "bdd_2000" and world > 1) else 0.0
-    buckets, comm_stream = [], None
+    buckets, comm_stream, peer_ar = [], None, None
     if ar_mb > 0 and world > 1:
         n_b = max(int(round(ar_mb / 25.0)), 1)
         buckets = [torch.randn(int(25e6 // 4), device=dev) for _ in range(n_b)]
-        comm_stream = torch.cuda.Stream(device=dev)
+        # HIGH-priority stream: issued from a normal-priority stream the all-reduce does not get onto the SMs while the ROIAlign
+        # grids run and adds its full stand-alone time to the step (tools/ar_overlap.py); from a high-priority one ~70 % of it hides
+        comm_stream = torch.cuda.Stream(device=dev, priority=-1)
+        # the same buckets in a peer-mapped buffer for the NVLink peer-memory all-reduce (coin_b200/p2p.py), measured beside NCCL
+        from coin_b200 import p2p
+        peer_ar = p2p.PeerAllReduce(n_b * int(25e6 // 4), dev)
+        peer_bucket = peer_ar.nelem // n_b // (4 * world) * (4 * world)
+        peer_ar.buffer.normal_()
 
-    def allreduce_buckets():
+    def allreduce_buckets(impl="nccl"):
         comm_stream.wait_stream(torch.cuda.current_stream())
+        if impl == "p2p":
+            for b in range(len(buckets)):
+                peer_ar.all_reduce(b * peer_bucket, peer_bucket, stream=comm_stream)
+            return
         with torch.cuda.stream(comm_stream):
             for b in buckets:
                 dist.all_reduce(b)
 
-    def timed_steps(with_comm):
+    def timed_steps(with_comm, impl="nccl"):
         for _ in range(warmup):
             step.replay()
             if with_comm:
-                allreduce_buckets()
+                allreduce_buckets(impl)
         if with_comm:
             torch.cuda.current_stream().wait_stream(comm_stream)
         barrier()
@@ -327,7 +338,7 @@ def main():
         for _ in range(args.steps):
             step.replay()
             if with_comm:
-                allreduce_buckets()          # bucket k of step n overlaps the graph of step n (and n+1)
+                allreduce_buckets(impl)      # bucket k of step n overlaps the graph of step n + 1
         if with_comm:
             torch.cuda.current_stream().wait_stream(comm_stream)
         t1.record()
@@ -338,27 +349,35 @@ def main():
     sampler.start()
     # ---- device-resident throughput: K graph replays back to back, inputs already in HBM ---------------
     ms_plain = timed_steps(False)
-    ms = timed_steps(True) if buckets else ms_plain
+    ms = timed_steps(True, "nccl") if buckets else ms_plain
     launches = launches_per_step * args.steps
     allreduce = None
     if buckets:
-        # the same buckets alone: bus bandwidth of the all-reduce on this box (2 (N-1)/N x bytes / time)
-        for _ in range(3):
-            allreduce_buckets()
-        torch.cuda.current_stream().wait_stream(comm_stream)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(10):
-            allreduce_buckets()
-        torch.cuda.current_stream().wait_stream(comm_stream)
-        a1.record()
-        barrier()
-        ar_ms = a0.elapsed_time(a1) / 10
+        ms_p2p = timed_steps(True, "p2p")
+
+        def alone(impl):     # the same buckets alone: bus bandwidth of the all-reduce on this box (2 (N-1)/N x bytes / time)
+            for _ in range(3):
+                allreduce_buckets(impl)
+            torch.cuda.current_stream().wait_stream(comm_stream)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(10):
+                allreduce_buckets(impl)
+            torch.cuda.current_stream().wait_stream(comm_stream)
+            a1.record()
+            barrier()
+            return a0.elapsed_time(a1) / 10
+        ar_p2p, ar_nccl = alone("p2p"), alone("nccl")
+        peer_ar.check()
         nbytes = sum(b.numel() * 4 for b in buckets)
+        bus = lambda t: 2 * (world - 1) / world * nbytes / t / 1e6      # noqa: E731
         allreduce = {"bytes_per_step": nbytes, "buckets": len(buckets), "bucket_mb": 25,
-                     "ms_alone": ar_ms, "bus_gbs": 2 * (world - 1) / world * nbytes / ar_ms / 1e6,
-                     "ms_per_step_with": ms / args.steps, "ms_per_step_without": ms_plain / args.steps}
+                     "impl": "NCCL all-reduce per bucket on a high-priority side stream (this is what `value` includes)",
+                     "ms_alone": ar_nccl, "bus_gbs": bus(ar_nccl), "ms_per_step_with": ms / args.steps,
+                     "ms_per_step_without": ms_plain / args.steps,
+                     "peer_memory_kernels": {"impl": "coin_p2p_all_reduce (coin_b200/p2p.py): two-shot over CUDA-IPC-mapped buffers",
+                                             "ms_alone": ar_p2p, "bus_gbs": bus(ar_p2p), "ms_per_step_with": ms_p2p / args.steps}}
 
     # per-replay statistics: >= 200 replays, each bracketed by its own event pair
     n_stat = max(args.steps, 200)

@@ -124,6 +124,8 @@ _SIGNATURES = {
     "coin_argsort_desc": (c_int, [P, c_int64, P, P, c_size_t, P]),
     "coin_voc_match_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "coin_voc_match": (c_int, [P, P, P, c_int64, P, P, P, c_int64, c_double, P, P, P, c_size_t, P]),
+    # peer-memory all-reduce
+    "coin_p2p_all_reduce": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int64, c_int64, ctypes.c_uint32, P, c_int, P]),
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())

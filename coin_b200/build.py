@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcoinops.so")
 SOURCES = ["capi.cu", "roi_align.cu", "roi_align_sep.cu", "roi_align_reg.cu", "box_codec.cu", "iou_match.cu", "nms.cu", "fusion_nms.cu",
-           "det_postprocess.cu", "match_abc.cu", "step_dev.cu", "rpn_proposals.cu", "sampling_loss.cu", "voc_eval.cu"]
+           "det_postprocess.cu", "match_abc.cu", "step_dev.cu", "rpn_proposals.cu", "sampling_loss.cu", "voc_eval.cu", "p2p_allreduce.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xcompiler", "-fPIC",

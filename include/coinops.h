@@ -494,6 +494,19 @@ int coin_voc_match(const int32_t* det_image, const double* det_boxes, const int6
                    const double* gt_boxes, const int32_t* gt_offsets, const uint8_t* gt_difficult, int64_t ng,
                    double ovthresh, double* tp, double* fp, void* ws, size_t ws_bytes, coin_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Gradient all-reduce over NVLink peer memory (BASELINE.json configs[3]; coin/engine/trainer.py:66-72 wraps the model in DDP)
+ * ------------------------------------------------------------------------------------------- */
+
+/* In-place sum over the n ranks of [offset, offset + nelem) fp32 elements of peer-mapped buffers (one process per GPU, n <= 8;
+ * the buffers and the 24-word flag arrays of all ranks are mapped into every process through CUDA IPC by the caller:
+ * coin_b200/p2p.py). data_ptrs / flag_ptrs: HOST arrays of n device pointers as seen from this process. offset, nelem: multiples
+ * of 4 * n. epoch: grows with every call on the group, the same on every rank. err: device int32, non-zero if a peer did not
+ * arrive (the kernels give up instead of hanging). max_ctas: grid size of the two data kernels (0: 4 per SM). Five launches of
+ * 224-thread / one-warp CTAs: sized to run beside the ROIAlign grids, which NCCL's kernels cannot (tools/ar_overlap.py). */
+int coin_p2p_all_reduce(void* const* data_ptrs, void* const* flag_ptrs, int rank, int n, int64_t offset, int64_t nelem,
+                        uint32_t epoch, int32_t* err, int max_ctas, coin_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -1,12 +1,14 @@
 """Can a NCCL all-reduce run BESIDE the ROIAlign grids, or only between them? (torchrun, >= 2 ranks; configs[3] sizes)
 Times 10 x ROIAlign forward+backward (BDD shape) alone, 10 x all-reduce of 200 MB alone, and both issued together in the two
-possible orders, with the NCCL stream at normal / high priority (COIN_BENCH_NCCL_HIPRI).
+possible orders, issued from a NORMAL-priority stream (COIN_BENCH_NCCL_HIPRI only sets the process group's own option).
 
-Measured on 2 x B200 (ms per iteration): roi 2.27, all-reduce 0.56, together 2.81 - 2.82 in either order, at either priority,
-with NCCL_MAX_NCHANNELS=4 (all-reduce 2.40 alone, 4.12 together) and with the ROIAlign grids capped to 3 or 2 CTAs per SM by
-shared-memory padding (3.11 -> 3.54, 5.09 -> 5.54): the sum, every time. The ROIAlign grids hold the register file (4 CTAs x 224
-threads x 72 registers = 64.5 k of 65.5 k per SM) or, capped, the shared memory; a NCCL CTA fits neither and waits for the grid
-to drain, so the gradient all-reduce of configs[3] costs its full stand-alone time on top of this path's step."""
+Measured on 2 x B200 (ms per iteration): roi 2.27, all-reduce 0.56, together 2.81 - 2.82 in either order, with either value of the
+process-group option, with NCCL_MAX_NCHANNELS=4 (all-reduce 2.40 alone, 4.12 together) and with the ROIAlign grids capped to 3 or
+2 CTAs per SM by shared-memory padding (3.11 -> 3.54, 5.09 -> 5.54): the sum, every time. The ROIAlign grids hold the register
+file (4 CTAs x 224 threads x 72 registers = 64.5 k of 65.5 k per SM) and refill every freed slot from their queue of thousands
+of CTAs; a collective issued at the same priority waits for the grid to drain. What changes it is the priority of the stream the
+collective is ISSUED from: tools/p2p_allreduce_check.py and bench.py --workload bdd_2000 issue it from a high-priority stream and
+~70 % of the all-reduce hides under the step (NCCL and the peer-memory kernels of coin_b200/p2p.py alike)."""
 import os
 import sys
 
