@@ -474,6 +474,7 @@ def main():
                    "boundary": "every step: pinned host inputs (fp32 feature map, RoIs, deltas, scores, cloud "
                                "detections, RPN boxes) -> device; graph replay; lengths -> host; detections, "
                                "A/B/C sets, labels, keep lists and the fp32 feature-map gradient -> pinned host. "
+                               "The ~100 variable-length results are packed on the device (coin_pack_rows) and leave in one copy. "
                                "Steps are double buffered (H2D of n+1 and D2H of n-1 overlap the graph of n); "
                                "ms_latency_one_step is the same step with nothing overlapped; link_bound_ms_per_step "
                                "= max(h2d, d2h bytes) / measured bidirectional link GB/s",

@@ -105,6 +105,7 @@ _SIGNATURES = {
                                         c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P, P, P,
                                         c_size_t, P]),
     "coin_concat_rows": (c_int, [POINTER(CoinSeg), c_int, c_int, c_int, P, c_int64, P, P]),
+    "coin_pack_rows": (c_int, [P, c_int, P, P, c_int64, P, P]),
     "coin_abc_pack": (c_int, [POINTER(CoinDets), c_int64, POINTER(CoinDets), c_int64, P, c_int, c_int,
                               P, P, P, P, P, P, P, POINTER(CoinPseudo), POINTER(CoinPseudo), POINTER(CoinPseudo),
                               c_int64, P]),

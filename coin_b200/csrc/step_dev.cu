@@ -126,8 +126,71 @@ __global__ void abc_pack_kernel(const PackArgs a) {
     }
 }
 
+// ---- live prefixes of many result buffers -> one contiguous staging buffer (one D2H copy per step) --------------------
+struct PackItem {               // 32 bytes; the table lives in device memory (built once by the caller)
+    const uint8_t* ptr;
+    int64_t row_bytes;
+    int64_t cap_rows;
+    int32_t count_index;        // index into the step's counts vector, -1: all cap_rows rows are live
+    int32_t pad;
+};
+
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const PackItem* __restrict__ items, int n, const int32_t* __restrict__ counts, uint8_t* __restrict__ packed,
+                 long long cap, long long* __restrict__ offsets) {
+    __shared__ long long s_part[256];
+    auto live_bytes = [&](int j) {
+        const PackItem it = items[j];
+        long long rows = it.cap_rows;
+        if (it.count_index >= 0) rows = min((long long)max(counts[it.count_index], 0), (long long)it.cap_rows);
+        return (rows * it.row_bytes + 15) / 16 * 16;      // every segment starts 16-byte aligned
+    };
+    const int b = blockIdx.x;
+    long long part = 0;
+    for (int j = threadIdx.x; j < b; j += 256) part += live_bytes(j);
+    s_part[threadIdx.x] = part;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_part[threadIdx.x] += s_part[threadIdx.x + o];
+        __syncthreads();
+    }
+    const long long off = s_part[0];
+    const long long mine = live_bytes(b);
+    if (threadIdx.x == 0) {
+        offsets[b] = off;
+        if (b == n - 1) offsets[n] = off + mine;
+    }
+    if (off + mine > cap) return;                         // the caller sized `packed` for the capacities: cannot happen
+    const PackItem it = items[b];
+    long long rows = it.cap_rows;
+    if (it.count_index >= 0) rows = min((long long)max(counts[it.count_index], 0), (long long)it.cap_rows);
+    const long long nbytes = rows * it.row_bytes;
+    uint8_t* dst = packed + off;
+    if ((reinterpret_cast<uintptr_t>(it.ptr) & 15) == 0) {
+        const long long n16 = nbytes / 16;
+        const uint4* s4 = reinterpret_cast<const uint4*>(it.ptr);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (long long i = threadIdx.x; i < n16; i += 256) d4[i] = s4[i];
+        for (long long i = n16 * 16 + threadIdx.x; i < nbytes; i += 256) dst[i] = it.ptr[i];
+    } else {
+        for (long long i = threadIdx.x; i < nbytes; i += 256) dst[i] = it.ptr[i];
+    }
+}
+
 }  // namespace coin
 using namespace coin;
+
+extern "C" int coin_pack_rows(const void* items_dev, int n_items, const int32_t* counts_dev, void* packed, int64_t packed_cap,
+                              int64_t* offsets_dev, coin_stream_t stream) {
+    COIN_REQUIRE(n_items >= 0 && packed_cap >= 0, "pack_rows: bad arguments");
+    if (n_items == 0) return COIN_OK;
+    COIN_REQUIRE(items_dev && packed && offsets_dev, "pack_rows: null pointer");
+    COIN_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "pack_rows: packed must be 16-byte aligned");
+    pack_rows_kernel<<<(unsigned)n_items, 256, 0, as_stream(stream)>>>(static_cast<const PackItem*>(items_dev), n_items, counts_dev,
+                                                                     static_cast<uint8_t*>(packed), (long long)packed_cap,
+                                                                     reinterpret_cast<long long*>(offsets_dev));
+    return check_launch("pack_rows_kernel");
+}
 
 extern "C" int coin_concat_rows(const coin_seg_t* segs_host, int nseg, int width_in, int width_out, float* out,
                                 int64_t out_cap, int32_t* out_count, coin_stream_t stream) {

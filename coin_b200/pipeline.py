@@ -21,11 +21,14 @@ single small D2H copy; the reference has several per image (trainer.py:469, nonz
 Everything else is asynchronous launches of libcoinops kernels on the current stream.
 """
 import os
-from typing import Dict, List
+import ctypes
+import struct
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
 from . import _lib, ops
+from ._lib import check, lib
 from .synth import Shape
 
 ORIG_SCALE = 2048.0 / 1200.0  # Foggy-Cityscapes: 1024x2048 originals, 600x1200 network input
@@ -574,6 +577,27 @@ class RoIPathStep:
 
     # -- results that travel back to the host in the end-to-end measurement ----------------------
     @staticmethod
+    def result_spec(out) -> List[Tuple[torch.Tensor, Optional[int]]]:
+        """The un-narrowed result buffers of a sync-free step in the order of ``result_tensors(finalize(out))`` (without the
+        feature-map gradient), each with the index of its live row count in ``out['counts']`` (None: every row is live)."""
+        sl = out["slots"]
+        spec: List[Tuple[torch.Tensor, Optional[int]]] = []
+        for i, dd in enumerate(out["dets"]):
+            spec += [(v, sl[f"det{i}"]) for v in dd.values()]
+        for i, per_tag in enumerate(out["abc"]):
+            for tag in ("RCNN", "RPN"):
+                o = sl[f"abc{i}.{tag}"]
+                for part, ci in zip(per_tag[tag], (o, o + 1, o + 2)):
+                    if part is not None:
+                        spec += [(v, ci) for v in part.values()]
+        for i, (idx, lab) in enumerate(out["roi_labels"]):
+            spec += [(idx, sl[f"props{i}"]), (lab, sl[f"props{i}"])]
+        for tup in out["rpn_labels"]:
+            spec += [(t, None) for t in tup]
+        spec += [(k, sl[f"rpn{i}"]) for i, k in enumerate(out["rpn_keep"])]
+        return spec
+
+    @staticmethod
     def result_tensors(out) -> List[torch.Tensor]:
         res = []
         for dd in out["dets"]:
@@ -595,7 +619,7 @@ class RoIPathStep:
 
 class PipelinedSteps:
     """End-to-end execution of consecutive steps with double buffering: while the graph of step n runs, the
-    inputs of step n+1 travel host -> device and the results of step n-1 travel device -> host (three
+    inputs of step n+1 travel host -> device and the results of step n-1 travel device -> host (four
     streams, two graph instances). Every step still pays its own H2D copy from pinned host memory, its own
     length read-back and its own D2H copy of the live results; only their latency is overlapped."""
 
@@ -629,13 +653,32 @@ class PipelinedSteps:
             dev_in.append(views)
         for slot, views in zip(self.slots, dev_in):
             slot.capture(views, backward)
-        self.s_in, self.s_c, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.s_in, self.s_c, self.s_out, self.s_p = (torch.cuda.Stream(device=dev) for _ in range(4))
         self.counts_host = [torch.empty(s._graph_out["counts"].shape, dtype=torch.int32).pin_memory() for s in self.slots]
+        # The ~100 variable-length results of a step (detections, A/B/C fields, labels, keep lists) are packed ON THE DEVICE into
+        # one staging buffer (coin_pack_rows: live prefixes only, lengths read on the device) and leave in ONE copy; the host
+        # slices the pinned copy lazily. (Narrowing and packing them in Python cost 0.6 ms per step - more than the link - and
+        # the slot's next graph had to wait for it.)
+        self.specs, self.items_dev, self.packed_dev, self.packed_host, self.offsets_dev, self.offsets_host = [], [], [], [], [], []
+        for slot in self.slots:
+            spec = slot.result_spec(slot._graph_out)
+            table, cap = b"", 0
+            for t, ci in spec:
+                assert t.is_contiguous()
+                rows = int(t.shape[0]) if t.dim() else 1
+                row_bytes = (t.numel() // max(rows, 1)) * t.element_size()
+                table += struct.pack("<QqqiI", t.data_ptr(), row_bytes, rows, -1 if ci is None else int(ci), 0)
+                cap += (rows * row_bytes + 15) // 16 * 16
+            self.specs.append(spec)
+            self.items_dev.append(torch.frombuffer(bytearray(table), dtype=torch.uint8).to(dev))
+            self.packed_dev.append(torch.empty((max(cap, 16),), dtype=torch.uint8, device=dev))
+            self.packed_host.append(torch.empty((max(cap, 16),), dtype=torch.uint8).pin_memory())
+            self.offsets_dev.append(torch.zeros((len(spec) + 1,), dtype=torch.int64, device=dev))
+            self.offsets_host.append(torch.zeros((len(spec) + 1,), dtype=torch.int64).pin_memory())
+        self.grad_host = [None, None]
         self.h2d_done = [None, None]
         self.compute_done = [None, None]
         self.d2h_done = [None, None]
-        self.host_cache = [{}, {}]
-        self.host_views = [None, None]   # per slot: host tensors (views into pinned buffers), order of result_tensors
         self.d2h_bytes = 0
 
     def load_inputs(self, src: Dict[str, torch.Tensor]) -> None:
@@ -661,49 +704,56 @@ class PipelinedSteps:
             if self.d2h_done[s] is not None:
                 self.s_c.wait_event(self.d2h_done[s])           # the results of step n-2 have left these buffers
             out = self.slots[s].replay()
+            graph_done = self.s_c.record_event()
+        with torch.cuda.stream(self.s_p):      # packing and the two tiny read-backs: beside the next step's graph, not before it
+            self.s_p.wait_event(graph_done)
+            check(lib.coin_pack_rows(ctypes.c_void_p(self.items_dev[s].data_ptr()), len(self.specs[s]),
+                                     ctypes.c_void_p(out["counts"].data_ptr()), ctypes.c_void_p(self.packed_dev[s].data_ptr()),
+                                     self.packed_dev[s].numel(), ctypes.c_void_p(self.offsets_dev[s].data_ptr()),
+                                     ctypes.c_void_p(self.s_p.cuda_stream)))
             self.counts_host[s].copy_(out["counts"], non_blocking=True)
-            self.compute_done[s] = self.s_c.record_event()
+            self.offsets_host[s].copy_(self.offsets_dev[s], non_blocking=True)
+            self.compute_done[s] = self.s_p.record_event()
 
     def _d2h(self, n):
         s = n % 2
         self.compute_done[s].synchronize()                      # the lengths of step n are on the host
-        step = self.slots[s]
-        res = step.result_tensors(step.finalize(step._graph_out, counts_host=self.counts_host[s]))
-        cache, nbytes = self.host_cache[s], self.counts_host[s].numel() * 4
-        views = [None] * len(res)
+        total = int(self.offsets_host[s][-1])
+        nbytes = self.counts_host[s].numel() * 4 + self.offsets_host[s].numel() * 8 + total
         with torch.cuda.stream(self.s_out):
-            # the ~100 small result tensors are packed per dtype on the device (one torch.cat each) and leave
-            # in one copy per dtype; large tensors (the feature-map gradient) are copied directly
-            groups: Dict[torch.dtype, list] = {}
-            for i, t in enumerate(res):
-                nbytes += t.numel() * t.element_size()
-                if t.numel() * t.element_size() >= (1 << 20):
-                    h = cache.get(("big", i))
-                    if h is None or h.numel() < t.numel():
-                        h = cache[("big", i)] = torch.empty((t.numel(),), dtype=t.dtype).pin_memory()
-                    h[: t.numel()].copy_(t.reshape(-1), non_blocking=True)
-                    views[i] = h[: t.numel()]
-                else:
-                    groups.setdefault(t.dtype, []).append((i, t.reshape(-1)))
-            for dt, items in groups.items():
-                flat = torch.cat([t for _, t in items]) if len(items) > 1 else items[0][1]
-                h = cache.get(dt)
-                if h is None or h.numel() < flat.numel():
-                    h = cache[dt] = torch.empty((max(2 * flat.numel(), 1),), dtype=dt).pin_memory()
-                h[: flat.numel()].copy_(flat, non_blocking=True)
-                off = 0
-                for i, t in items:
-                    views[i] = h[off: off + t.numel()]
-                    off += t.numel()
+            self.s_out.wait_event(self.compute_done[s])
+            self.packed_host[s][:total].copy_(self.packed_dev[s][:total], non_blocking=True)
+            g = self.slots[s]._graph_out.get("grad_features")
+            if g is not None:                                   # the feature-map gradient: fixed size, copied directly
+                if self.grad_host[s] is None:
+                    self.grad_host[s] = torch.empty((g.numel(),), dtype=g.dtype).pin_memory()
+                self.grad_host[s].copy_(g.reshape(-1), non_blocking=True)
+                nbytes += g.numel() * g.element_size()
             self.d2h_done[s] = self.s_out.record_event()
-        self.host_views[s] = views
         self.d2h_bytes = nbytes
+
+    @property
+    def host_views(self) -> List[List[torch.Tensor]]:
+        """Per slot: the host copies of the last step's results (views into the pinned staging buffers, flattened), in the
+        order of ``RoIPathStep.result_tensors(finalize(...))``. Call after run()."""
+        out = []
+        for s, slot in enumerate(self.slots):
+            cnt, offs, views = self.counts_host[s].tolist(), self.offsets_host[s].tolist(), []
+            for j, (t, ci) in enumerate(self.specs[s]):
+                rows = int(t.shape[0]) if t.dim() else 1
+                live = rows if ci is None else min(max(cnt[ci], 0), rows)
+                nbytes = live * (t.numel() // max(rows, 1)) * t.element_size()
+                views.append(self.packed_host[s][offs[j]: offs[j] + nbytes].view(t.dtype))
+            if self.grad_host[s] is not None:
+                views.append(self.grad_host[s])
+            out.append(views)
+        return out
 
     def run(self, pinned, steps: int) -> None:
         """`steps` end-to-end steps; returns when every result is on the host. pinned: a dict of host tensors that
         is written into the pinned staging buffers before every H2D copy, or None to send the staging buffers
         as they are (filled beforehand with load_inputs)."""
-        for st in (self.s_in, self.s_c, self.s_out):
+        for st in (self.s_in, self.s_c, self.s_out, self.s_p):
             st.wait_stream(torch.cuda.current_stream())
         self._h2d(0, pinned)
         for n in range(steps):
@@ -714,5 +764,5 @@ class PipelinedSteps:
                 self._d2h(n - 1)
         self._d2h(steps - 1)
         self.s_out.synchronize()
-        for st in (self.s_in, self.s_c, self.s_out):
+        for st in (self.s_in, self.s_c, self.s_out, self.s_p):
             torch.cuda.current_stream().wait_stream(st)

@@ -476,6 +476,14 @@ int coin_kl_distill_rpn_fwd(const float* logits, const int8_t* distillation_labe
 int coin_kl_distill_rpn_bwd(const float* logits, const int8_t* distillation_labels, const float* teacher_probs, int64_t n,
                             const int32_t* n_valid, const float* grad_loss, float* grad_logits, coin_stream_t stream);
 
+/* Packs the live prefixes of many result buffers into one contiguous staging buffer, so that a step's ~100 variable-length
+ * results (detections, A/B/C fields, labels, keep lists: trainer.py:393-459 hands them on one by one) leave the device in ONE
+ * copy. items_dev: DEVICE array of n_items records {const void* ptr; int64 row_bytes; int64 cap_rows; int32 count_index;
+ * int32 pad} (32 bytes each; count_index = index into counts_dev of the live row count, -1 = all rows). Segment i starts at
+ * offsets_dev[i] (16-byte aligned); offsets_dev[n_items] = total bytes. packed_cap >= the sum of the padded capacities. */
+int coin_pack_rows(const void* items_dev, int n_items, const int32_t* counts_dev, void* packed, int64_t packed_cap,
+                   int64_t* offsets_dev, coin_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Evaluation
  * ------------------------------------------------------------------------------------------- */
