@@ -58,7 +58,7 @@ _SIGNATURES = {
     "coin_roi_align_fwd_ord": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_int, P, P, P]),
     "coin_roi_align_bwd_ord": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
-                                       c_int, c_int, P, P]),
+                                       c_int, c_int, P, P, P]),
     "coin_roi_pooler_levels": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P]),
     "coin_apply_deltas": (c_int, [P, P, P, c_int64, c_int, c_float, c_float, c_float, c_float, c_float,
                                   c_int, c_float, c_float, P]),

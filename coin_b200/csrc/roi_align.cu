@@ -506,13 +506,15 @@ extern "C" int coin_roi_align_fwd_ord(const coin_level_t* levels_host, int nleve
 
 static int roi_align_bwd_impl(const coin_level_t* grad_levels_host, int nlevels, const float* rois,
                               const int32_t* roi_level, const void* grad_out, int grad_dtype, int C, int K,
-                              int PH, int PW, int sampling_ratio, int aligned, const int32_t* perm, coin_stream_t stream) {
+                              int PH, int PW, int sampling_ratio, int aligned, const int32_t* k_dev, const int32_t* perm,
+                              coin_stream_t stream) {
     RoiParams p;
     if (int rc = fill_params(p, grad_levels_host, nlevels, rois, roi_level, C, K, PH, PW, sampling_ratio, aligned)) return rc;
     COIN_REQUIRE(grad_dtype == COIN_F32 || grad_dtype == COIN_F16, "roi_align_bwd: bad grad_dtype %d", grad_dtype);
     if (K == 0) return COIN_OK;
     COIN_REQUIRE(grad_out, "roi_align_bwd: grad_out is null");
     p.perm = perm;
+    p.k_dev = k_dev;
     // COIN_ROI_BWD_SEP: 1 (default) the register-tile / separable kernels; 0 the per-sample kernel below
     if (env_int("COIN_ROI_BWD_SEP", 1) != 0 && roi_align_bwd_reg_supported(p, grad_dtype))
         return launch_roi_align_bwd_reg(p, grad_out, grad_dtype, as_stream(stream));
@@ -528,15 +530,15 @@ extern "C" int coin_roi_align_bwd(const coin_level_t* grad_levels_host, int nlev
                                   const int32_t* roi_level, const void* grad_out, int grad_dtype, int C, int K,
                                   int PH, int PW, int sampling_ratio, int aligned, coin_stream_t stream) {
     return roi_align_bwd_impl(grad_levels_host, nlevels, rois, roi_level, grad_out, grad_dtype, C, K, PH, PW, sampling_ratio,
-                              aligned, nullptr, stream);
+                              aligned, nullptr, nullptr, stream);
 }
 
 extern "C" int coin_roi_align_bwd_ord(const coin_level_t* grad_levels_host, int nlevels, const float* rois,
                                       const int32_t* roi_level, const void* grad_out, int grad_dtype, int C, int K,
-                                      int PH, int PW, int sampling_ratio, int aligned, const int32_t* perm,
-                                      coin_stream_t stream) {
+                                      int PH, int PW, int sampling_ratio, int aligned, const int32_t* k_dev,
+                                      const int32_t* perm, coin_stream_t stream) {
     return roi_align_bwd_impl(grad_levels_host, nlevels, rois, roi_level, grad_out, grad_dtype, C, K, PH, PW, sampling_ratio,
-                              aligned, perm, stream);
+                              aligned, k_dev, perm, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -33,8 +33,10 @@ def _tv_roi_align(input, rois, spatial_scale, pooled_height, pooled_width, sampl
     if rois.size(0) == 0:
         return torch.zeros((0, input.size(1), ph, pw), dtype=input.dtype, device=input.device)
     nhwc = ops.to_nhwc_f32(input)
-    return ops.roi_align_forward([nhwc], (float(spatial_scale),), rois.to(torch.float32), None, (ph, pw),
-                                 int(sampling_ratio), bool(aligned), input.dtype)
+    rois = rois.to(torch.float32)
+    # (launch order + size split: a map-sized RoI must not become a 1-ms CTA of the register-tile kernel)
+    return ops.roi_align_forward_planned([nhwc], (float(spatial_scale),), rois, (ph, pw), int(sampling_ratio), bool(aligned),
+                                         input.dtype, order=ops.roi_launch_order(rois))
 
 
 def _tv_roi_align_backward(grad, rois, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width,

@@ -35,24 +35,26 @@ class _ROIAlignFn(torch.autograd.Function):
         if levels is None:
             # one level (COIN's C4 heads): nothing bounds a RoI's size in feature cells, and a map-sized RoI is a 1-ms CTA for
             # the register-tile kernel - the planned forward pools those few with the separable kernel
-            out = ops.roi_align_forward_planned(nhwc, scales, rois, output_size, sampling_ratio, aligned, feats[0].dtype,
-                                                order=perm)
+            out, plan = ops.roi_align_forward_planned(nhwc, scales, rois, output_size, sampling_ratio, aligned, feats[0].dtype,
+                                                      order=perm, return_plan=True)
         else:   # ROIPooler assigns large boxes to coarse levels: at most ~28 x 28 cells per RoI by construction
+            plan = None
             out = ops.roi_align_forward(nhwc, scales, rois, levels, output_size, sampling_ratio, aligned, feats[0].dtype,
                                         perm=perm)
         ctx.save_for_backward(rois, levels if levels is not None else torch.empty(0),
-                              perm if perm is not None else torch.empty(0))
-        ctx.has_levels, ctx.has_perm = levels is not None, perm is not None
+                              perm if perm is not None else torch.empty(0), *(plan if plan is not None else ()))
+        ctx.has_levels, ctx.has_perm, ctx.has_plan = levels is not None, perm is not None, plan is not None
         ctx.meta = (output_size, tuple(scales), sampling_ratio, aligned, [tuple(f.shape) for f in feats],
                     [f.dtype for f in feats])
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        rois, levels, perm = ctx.saved_tensors
+        rois, levels, perm = ctx.saved_tensors[:3]
+        plan = tuple(ctx.saved_tensors[3:6]) if ctx.has_plan else None
         output_size, scales, sampling_ratio, aligned, shapes, dtypes = ctx.meta
         grads = ops.roi_align_backward(grad_out, shapes, scales, rois, levels if ctx.has_levels else None, output_size,
-                                       sampling_ratio, aligned, dtypes, perm=perm if ctx.has_perm else None)
+                                       sampling_ratio, aligned, dtypes, perm=perm if ctx.has_perm else None, plan=plan)
         return (None, None, None, None, None, None, *grads)
 
 

@@ -151,14 +151,15 @@ def roi_split_by_area(rois: torch.Tensor, k_dev: Optional[torch.Tensor], area_th
 def roi_align_forward_planned(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
                               output_size: Tuple[int, int], sampling_ratio: int, aligned: bool, out_dtype: torch.dtype,
                               order: Optional[torch.Tensor] = None, k_dev: Optional[torch.Tensor] = None,
-                              events: Optional[list] = None, plan=None, big_stream=None) -> torch.Tensor:
+                              events: Optional[list] = None, plan=None, big_stream=None, return_plan: bool = False):
     """Single-level roi_align_forward that is robust to map-sized RoIs: the RoIs are split on the device by size
     (BIG_ROI_CELLS / BIG_ROI_SIDE feature cells); the big ones are pooled by the separable kernel, the rest by the default
     (register-tile) kernel in the launch order ``order``; one output. plan: a precomputed roi_split_by_area result.
     big_stream: optional side stream for the (normally empty) launch of the big RoIs, so that it does not sit in front of the
     main launch; the current stream waits for it before returning."""
     if _lib.get_option("COIN_ROI_EXACT", 0) != 0:     # the parity kernels pool every RoI the same way
-        return roi_align_forward(feats_nhwc, scales, rois, None, output_size, sampling_ratio, aligned, out_dtype, events, k_dev)
+        out = roi_align_forward(feats_nhwc, scales, rois, None, output_size, sampling_ratio, aligned, out_dtype, events, k_dev)
+        return (out, None) if return_plan else out
     stride = 1.0 / float(scales[0])
     if plan is None:
         plan = roi_split_by_area(rois, k_dev, BIG_ROI_CELLS * stride * stride, BIG_ROI_SIDE * stride, order, BIG_ROI_CAP)
@@ -181,7 +182,7 @@ def roi_align_forward_planned(feats_nhwc: Sequence[torch.Tensor], scales: Sequen
                       k_dev=cnt[0:1], perm=p_small, out=out)
     if big_done is not None:
         torch.cuda.current_stream().wait_event(big_done)
-    return out
+    return (out, plan) if return_plan else out
 
 
 def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float], rois: torch.Tensor,
@@ -227,8 +228,11 @@ def roi_align_forward(feats_nhwc: Sequence[torch.Tensor], scales: Sequence[float
 def roi_align_backward(grad_out: torch.Tensor, shapes: Sequence[Tuple[int, int, int, int]], scales: Sequence[float],
                        rois: torch.Tensor, roi_level: Optional[torch.Tensor], output_size: Tuple[int, int],
                        sampling_ratio: int, aligned: bool, out_dtypes: Sequence[torch.dtype],
-                       events: Optional[list] = None, perm: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
-    """Returns one NCHW gradient per level (shape ``shapes[i]`` = (N,C,H,W), dtype ``out_dtypes[i]``)."""
+                       events: Optional[list] = None, perm: Optional[torch.Tensor] = None, plan=None,
+                       big_stream=None) -> List[torch.Tensor]:
+    """Returns one NCHW gradient per level (shape ``shapes[i]`` = (N,C,H,W), dtype ``out_dtypes[i]``).
+    perm: launch order (roi_launch_order). plan: a roi_split_by_area result of the forward (single level): the map-sized
+    RoIs' gradients are scattered by the separable kernel (on ``big_stream`` if given), the rest by the default kernel."""
     grad_out = _cuda(grad_out, "grad_out").contiguous()
     rois = _f32c(rois, "rois")
     k, c = rois.shape[0], shapes[0][1]
@@ -236,11 +240,32 @@ def roi_align_backward(grad_out: torch.Tensor, shapes: Sequence[Tuple[int, int, 
     bufs = [torch.zeros((n, h, w, cc), dtype=torch.float32, device=grad_out.device) for (n, cc, h, w) in shapes]
     if roi_level is not None:
         roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
-    pair = _event_pair(events)
-    check(lib.coin_roi_align_bwd_ord(_levels(bufs, scales), len(bufs), _ptr(rois), _ptr(roi_level), _ptr(grad_out),
-                                     _dtype_code(grad_out.dtype), c, k, ph, pw, int(sampling_ratio), int(bool(aligned)),
-                                     _ptr(perm), _stream()))
+    def launch(k_launch, k_dev, order):
+        check(lib.coin_roi_align_bwd_ord(_levels(bufs, scales), len(bufs), _ptr(rois), _ptr(roi_level), _ptr(grad_out),
+                                         _dtype_code(grad_out.dtype), c, k_launch, ph, pw, int(sampling_ratio),
+                                         int(bool(aligned)), _ptr(k_dev), _ptr(order), _stream()))
+    big_done = None
+    if plan is not None and _lib.get_option("COIN_ROI_EXACT", 0) == 0:
+        p_small, p_big, cnt = plan
+
+        def scatter_big():
+            with _lib.options(COIN_ROI_REG=0):
+                launch(int(p_big.shape[0]), cnt[1:2], p_big)
+        if big_stream is None:
+            scatter_big()
+        else:
+            big_stream.wait_event(torch.cuda.current_stream().record_event())      # (the zero-filled buffers exist)
+            with torch.cuda.stream(big_stream):
+                scatter_big()
+                big_done = big_stream.record_event()
+        pair = _event_pair(events)
+        launch(k, cnt[0:1], p_small)
+    else:
+        pair = _event_pair(events)
+        launch(k, None, perm)
     _event_close(pair)
+    if big_done is not None:
+        torch.cuda.current_stream().wait_event(big_done)
     outs = []
     for buf, (n, cc, h, w), dt in zip(bufs, shapes, out_dtypes):
         g = torch.empty((n, cc, h, w), dtype=dt, device=buf.device)

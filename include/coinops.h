@@ -297,7 +297,7 @@ int coin_roi_align_fwd_ord(const coin_level_t* levels_host, int nlevels, const f
                            coin_stream_t stream);
 int coin_roi_align_bwd_ord(const coin_level_t* grad_levels_host, int nlevels, const float* rois,
                            const int32_t* roi_level, const void* grad_out, int grad_dtype, int C, int K,
-                           int PH, int PW, int sampling_ratio, int aligned, const int32_t* perm,
+                           int PH, int PW, int sampling_ratio, int aligned, const int32_t* k_dev, const int32_t* perm,
                            coin_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -257,6 +257,13 @@ def test_roi_align_map_sized_rois_do_not_stall_the_grid(dev):
     close(out[sel.to(dev), :64], ref, scale=float(x.abs().max()))
     t_plain, t_mixed = timed(rois_of(boxes)), timed(rois_of(mixed))
     assert t_mixed < 2.0 * t_plain + 0.05, (t_plain, t_mixed)
+    # the backward takes the same split (the plan travels through autograd): gradient against torchvision on 64 channels
+    xs = x[:, :64].clone().to(dev).requires_grad_(True)
+    go = torch.randn(len(mixed), 64, 14, 14, generator=g)
+    layer(xs, rois_of(mixed)).backward(go.to(dev))
+    xr = x[:, :64].clone().requires_grad_(True)
+    torchvision.ops.roi_align(xr, rois_of(mixed).cpu(), (14, 14), 1.0 / 16, 0, True).backward(go)
+    close(xs.grad, xr.grad, scale=float(xr.grad.abs().max()))
 
 
 def test_roi_align_non_finite_features(dev):

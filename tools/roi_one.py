@@ -19,7 +19,7 @@ lv = ops._levels([buf], (1 / 16,))
 perm = ops.roi_launch_order(rois)      # as in the step: the smallest 20 % of the RoIs are launched last
 for _ in range(int(os.environ.get("ITERS", "2"))):
     out = ops.roi_align_forward([nhwc], (1 / 16,), rois, None, (pooled, pooled), 0, True, torch.float32, perm=perm)
-    check(lib.coin_roi_align_bwd_ord(lv, 1, ops._ptr(rois), ops._ptr(None), ops._ptr(go), 0, c, k, pooled, pooled, 0, 1, ops._ptr(perm),
+    check(lib.coin_roi_align_bwd_ord(lv, 1, ops._ptr(rois), ops._ptr(None), ops._ptr(go), 0, c, k, pooled, pooled, 0, 1, ops._ptr(None), ops._ptr(perm),
                                      ops._stream()))
 torch.cuda.synchronize()
 print("ok", float(out.abs().mean()))
