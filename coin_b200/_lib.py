@@ -54,6 +54,7 @@ _SIGNATURES = {
     "coin_roi_align_bwd": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, P]),
     "coin_roi_launch_order": (c_int, [P, c_int, P, c_int, c_int, P, P]),
+    "coin_roi_launch_plan": (c_int, [P, c_int, P, c_int, c_int, c_float, c_float, c_int, P, P, P, P]),
     "coin_roi_split_by_area": (c_int, [P, c_int, P, c_float, c_float, c_int, P, P, P, P, P]),
     "coin_roi_align_fwd_ord": (c_int, [POINTER(CoinLevel), c_int, P, P, P, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_int, P, P, P]),

@@ -557,22 +557,40 @@ constexpr int kOrderMax = 8192;
 
 __global__ void __launch_bounds__(kOrderThreads)
 roi_launch_order_kernel(const float* __restrict__ rois, int K_cap, const int32_t* __restrict__ k_dev, int small_pct, int big_pct,
-                        int32_t* __restrict__ perm) {
-    extern __shared__ uint32_t okeys[];     // area bits of every live RoI
+                        int32_t* __restrict__ perm, float area_thr, float side_thr, int divert_cap,
+                        int32_t* __restrict__ perm_divert, int32_t* __restrict__ counts) {
+    extern __shared__ uint32_t okeys[];     // area bits of every live RoI; bit 0 borrowed: the RoI exceeds the size thresholds
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_rank;
-    __shared__ int s_cnt[3][32];
+    __shared__ int s_cnt[4][32];
+    __shared__ int s_div;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = k_dev ? min(max(__ldg(k_dev), 0), K_cap) : K_cap;
     for (int i = tid; i < K_cap; i += kOrderThreads) {
         if (i < n) {
             const float w = __ldg(rois + 5 * i + 3) - __ldg(rois + 5 * i + 1), h = __ldg(rois + 5 * i + 4) - __ldg(rois + 5 * i + 2);
             const float a = (w > 0.0f && h > 0.0f) ? w * h : 0.0f;     // NaN / inverted: smallest
-            okeys[i] = __float_as_uint(a);                              // non-negative floats order like their bits
+            const bool div = perm_divert && w > 0.0f && h > 0.0f && (a > area_thr || w > side_thr || h > side_thr);
+            // non-negative floats order like their bits (plan mode gives the lowest mantissa bit to the flag)
+            okeys[i] = perm_divert ? ((__float_as_uint(a) & ~1u) | (div ? 1u : 0u)) : __float_as_uint(a);
         } else {
             perm[i] = i;
         }
     }
+    // RoIs above the size thresholds are DIVERTED: they go to the very end of perm (behind the live count the caller's main
+    // launch gets in counts[0]) and into perm_divert, for a launch of their own on the separable kernel - unless there are
+    // more of them than that launch's capacity, then nothing is diverted (correct, slow)
+    if (tid == 0) s_div = 0;
+    __syncthreads();
+    if (perm_divert) {
+        int nd = 0;
+        for (int i = tid; i < n; i += kOrderThreads) nd += okeys[i] & 1u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, o);
+        if (lane == 0 && nd) atomicAdd(&s_div, nd);
+    }
+    __syncthreads();
+    const bool divert_on = perm_divert && s_div > 0 && s_div <= divert_cap;
     // the key of a given rank (0-based, ascending), one byte per pass over shared-memory histograms
     auto select = [&](int rank_wanted) -> uint32_t {
         __syncthreads();
@@ -603,33 +621,44 @@ roi_launch_order_kernel(const float* __restrict__ rois, int K_cap, const int32_t
     const bool any_small = n_small > 0;
     const uint32_t hi = n_big > 0 ? select(n - n_big) : 0xffffffffu;
     const bool any_big = n_big > 0;
-    auto cls = [&](uint32_t k) { return (any_big && k >= hi && !(any_small && k <= lo)) ? 0 : ((any_small && k <= lo) ? 2 : 1); };
+    auto cls = [&](uint32_t k) {
+        if (divert_on && (k & 1u)) return 3;      // (divert_on implies plan mode: bit 0 is the flag)
+        return (any_big && k >= hi && !(any_small && k <= lo)) ? 0 : ((any_small && k <= lo) ? 2 : 1);
+    };
     const int per = (n + kOrderThreads - 1) / kOrderThreads;
     const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
-    int cnt[3] = {0, 0, 0};
+    int cnt[4] = {0, 0, 0, 0};
     for (int i = i0; i < i1; ++i) ++cnt[cls(okeys[i])];
-    int pre[3] = {cnt[0], cnt[1], cnt[2]};     // inclusive warp scans
+    int pre[4] = {cnt[0], cnt[1], cnt[2], cnt[3]};     // inclusive warp scans
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < 4; ++c) {
             const int v = __shfl_up_sync(0xffffffffu, pre[c], o);
             if (lane >= o) pre[c] += v;
         }
-    if (lane == 31) { s_cnt[0][warp] = pre[0]; s_cnt[1][warp] = pre[1]; s_cnt[2][warp] = pre[2]; }
+    if (lane == 31) { s_cnt[0][warp] = pre[0]; s_cnt[1][warp] = pre[1]; s_cnt[2][warp] = pre[2]; s_cnt[3][warp] = pre[3]; }
     __syncthreads();
-    int off[3], tot[3] = {0, 0, 0};
+    int off[4], tot[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) off[c] = pre[c] - cnt[c];
+    for (int c = 0; c < 4; ++c) off[c] = pre[c] - cnt[c];
     for (int w = 0; w < kOrderThreads / 32; ++w)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < 4; ++c) {
             if (w < warp) off[c] += s_cnt[c][w];
             tot[c] += s_cnt[c][w];
         }
+    const int nd0 = off[3];                   // this thread's first index in the diverted list
     off[1] += tot[0];
     off[2] += tot[0] + tot[1];
-    for (int i = i0; i < i1; ++i) perm[off[cls(okeys[i])]++] = i;
+    off[3] += tot[0] + tot[1] + tot[2];
+    int jd = nd0;
+    for (int i = i0; i < i1; ++i) {
+        const int c = cls(okeys[i]);
+        perm[off[c]++] = i;
+        if (c == 3) perm_divert[jd++] = i;
+    }
+    if (tid == 0 && counts) { counts[0] = n - tot[3]; counts[1] = tot[3]; }
 }
 
 // Two RoI lists by box size (in input order, or in the order of a launch order `order`): "big" = area > area_thr or a side > side_thr, and the rest, with their
@@ -687,15 +716,32 @@ extern "C" int coin_roi_split_by_area(const float* rois, int K_cap, const int32_
     return check_launch("roi_split_by_area_kernel");
 }
 
-extern "C" int coin_roi_launch_order(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct,
-                                     int32_t* perm, coin_stream_t stream) {
+static int roi_launch_order_impl(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct, int32_t* perm,
+                                 float area_thr, float side_thr, int divert_cap, int32_t* perm_divert, int32_t* counts,
+                                 coin_stream_t stream) {
     COIN_REQUIRE(K_cap >= 0 && small_pct >= 0 && big_pct >= 0 && small_pct + big_pct <= 100, "roi_launch_order: bad arguments");
-    if (K_cap == 0) return COIN_OK;
+    if (K_cap == 0) {
+        if (counts) fill_bytes(counts, 0, 2 * sizeof(int32_t), as_stream(stream));
+        return COIN_OK;
+    }
     COIN_REQUIRE(rois && perm, "roi_launch_order: null pointer");
     COIN_REQUIRE(K_cap <= kOrderMax, "roi_launch_order: K=%d exceeds %d (large grids have no tail worth ordering)", K_cap, kOrderMax);
-    roi_launch_order_kernel<<<1, kOrderThreads, (size_t)K_cap * sizeof(uint32_t), as_stream(stream)>>>(rois, K_cap, k_dev,
-                                                                                                 small_pct, big_pct, perm);
+    roi_launch_order_kernel<<<1, kOrderThreads, (size_t)K_cap * sizeof(uint32_t), as_stream(stream)>>>(
+        rois, K_cap, k_dev, small_pct, big_pct, perm, area_thr, side_thr, divert_cap, perm_divert, counts);
     return check_launch("roi_launch_order_kernel");
+}
+
+extern "C" int coin_roi_launch_order(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct,
+                                     int32_t* perm, coin_stream_t stream) {
+    return roi_launch_order_impl(rois, K_cap, k_dev, small_pct, big_pct, perm, 0.0f, 0.0f, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int coin_roi_launch_plan(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct,
+                                    float area_thr, float side_thr, int divert_cap, int32_t* perm, int32_t* perm_divert,
+                                    int32_t* counts, coin_stream_t stream) {
+    COIN_REQUIRE(perm_divert && counts && divert_cap >= 0, "roi_launch_plan: null pointer");
+    return roi_launch_order_impl(rois, K_cap, k_dev, small_pct, big_pct, perm, area_thr, side_thr, divert_cap, perm_divert,
+                                 counts, stream);
 }
 
 extern "C" int coin_nchw_to_nhwc_f32(const void* in, int in_dtype, float* out, int N, int C, int H, int W,

@@ -36,7 +36,7 @@ def _tv_roi_align(input, rois, spatial_scale, pooled_height, pooled_width, sampl
     rois = rois.to(torch.float32)
     # (launch order + size split: a map-sized RoI must not become a 1-ms CTA of the register-tile kernel)
     return ops.roi_align_forward_planned([nhwc], (float(spatial_scale),), rois, (ph, pw), int(sampling_ratio), bool(aligned),
-                                         input.dtype, order=ops.roi_launch_order(rois))
+                                         input.dtype, plan=ops.roi_launch_plan(rois, float(spatial_scale))[1])
 
 
 def _tv_roi_align_backward(grad, rois, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width,

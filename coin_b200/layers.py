@@ -31,14 +31,15 @@ class _ROIAlignFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rois, levels, output_size, scales, sampling_ratio, aligned, *feats):
         nhwc = [ops.to_nhwc_f32(f) for f in feats]
-        perm = ops.roi_launch_order(rois)     # scheduling only: the smallest RoIs are launched last
         if levels is None:
             # one level (COIN's C4 heads): nothing bounds a RoI's size in feature cells, and a map-sized RoI is a 1-ms CTA for
-            # the register-tile kernel - the planned forward pools those few with the separable kernel
-            out, plan = ops.roi_align_forward_planned(nhwc, scales, rois, output_size, sampling_ratio, aligned, feats[0].dtype,
-                                                      order=perm, return_plan=True)
+            # the register-tile kernel - the planned forward pools those few with the separable kernel. One launch computes
+            # the launch order (the smallest RoIs go last: scheduling only) and the split.
+            perm, plan = ops.roi_launch_plan(rois, scales[0])
+            out = ops.roi_align_forward_planned(nhwc, scales, rois, output_size, sampling_ratio, aligned, feats[0].dtype,
+                                                plan=plan)
         else:   # ROIPooler assigns large boxes to coarse levels: at most ~28 x 28 cells per RoI by construction
-            plan = None
+            perm, plan = ops.roi_launch_order(rois), None
             out = ops.roi_align_forward(nhwc, scales, rois, levels, output_size, sampling_ratio, aligned, feats[0].dtype,
                                         perm=perm)
         ctx.save_for_backward(rois, levels if levels is not None else torch.empty(0),

@@ -127,8 +127,31 @@ def roi_launch_order(rois: torch.Tensor, k_dev: Optional[torch.Tensor] = None, s
     return perm
 
 
-BIG_ROI_CELLS = 600            # a RoI covering more feature cells than this, or wider / taller than BIG_ROI_SIDE cells, is "big":
-BIG_ROI_SIDE = 40              # a register-tile CTA walks it for 0.2 - 1 ms (tools/c_box_probe.py); the separable kernel pools it
+def roi_launch_plan(rois: torch.Tensor, scale: float, k_dev: Optional[torch.Tensor] = None, small_pct: int = 20,
+                    big_pct: int = 0):
+    """Launch order + size split in ONE launch (coin_roi_launch_plan): returns (perm, plan) where perm is the launch order over
+    all live RoIs (for the backward) and plan = (perm, perm_divert, counts) is what roi_align_forward_planned takes: the main
+    kernel pools perm[:counts[0]], the separable kernel the map-sized RoIs perm_divert[:counts[1]]. None, None beyond 8192 RoIs."""
+    rois = _f32c(rois, "rois")
+    k = rois.shape[0]
+    if k > ORDER_MAX_ROIS or k == 0:
+        return None, None
+    stride = 1.0 / float(scale)
+    perm = torch.empty((k,), dtype=torch.int32, device=rois.device)
+    cap = min(BIG_ROI_CAP, k)
+    pd = torch.empty((cap,), dtype=torch.int32, device=rois.device)
+    counts = torch.zeros((2,), dtype=torch.int32, device=rois.device)
+    if k < ORDER_MIN_ROIS:
+        small_pct = big_pct = 0              # below ~1 wave of CTAs there is no tail to fill: only the split
+    check(lib.coin_roi_launch_plan(_ptr(rois), k, _ptr(None if k_dev is None else _count(k_dev)), int(small_pct), int(big_pct),
+                                   BIG_ROI_CELLS * stride * stride, BIG_ROI_SIDE * stride, cap, _ptr(perm), _ptr(pd),
+                                   _ptr(counts), _stream()))
+    return perm, (perm, pd, counts)
+
+
+BIG_ROI_CELLS = 1000           # a RoI covering more feature cells than this, or wider / taller than BIG_ROI_SIDE cells, is "big":
+BIG_ROI_SIDE = 40              # a register-tile CTA walks it for 0.2 - 1 ms (tools/c_box_probe.py); the separable kernel pools it.
+#                                (500 x 500 px at stride 16 - the largest box of the Foggy size law, 47 us - stays below both.)
 BIG_ROI_CAP = 32               # ... up to this many per call (the capacity of that second, normally empty, launch)
 
 

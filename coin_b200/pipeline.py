@@ -190,8 +190,8 @@ class RoIPathStep:
             nhwc = ops.to_nhwc_f32(d["features"])
             rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
                               for i in range(n_img)])
-            perm = ops.roi_launch_order(rois, small_pct=self.roi_tail_pct)
-            out["pooled"] = ops.roi_align_forward_planned([nhwc], scale, rois, size, 0, True, torch.float32, order=perm,
+            perm, plan = ops.roi_launch_plan(rois, scale[0], small_pct=self.roi_tail_pct)
+            out["pooled"] = ops.roi_align_forward_planned([nhwc], scale, rois, size, 0, True, torch.float32, plan=plan,
                                                           events=ev["fwd"] if ev else None)
             if backward:
                 n, c, h, w = d["features"].shape
@@ -321,10 +321,9 @@ class RoIPathStep:
         with torch.cuda.stream(s_img[2 * n_img]):     # (this stream's chain starts only after knowledge separation)
             rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
                               for i in range(n_img)])
-            perm = ops.roi_launch_order(rois, small_pct=self.roi_tail_pct)   # beside the layout transform below
-            stride = float(sh.stride)      # map-sized RoIs (if any) go to the separable kernel: ops.roi_align_forward_planned
-            plan = ops.roi_split_by_area(rois, None, ops.BIG_ROI_CELLS * stride * stride, ops.BIG_ROI_SIDE * stride, perm,
-                                         ops.BIG_ROI_CAP)
+            # launch order (smallest RoIs last) + size split (map-sized RoIs, if any, go to the separable kernel:
+            # ops.roi_align_forward_planned) in one launch, beside the layout transform below
+            perm, plan = ops.roi_launch_plan(rois, scale[0], small_pct=self.roi_tail_pct)
             rois_ready = s_img[2 * n_img].record_event()
         with torch.cuda.stream(s_roi):
             nhwc = ops.to_nhwc_f32(d["features"])

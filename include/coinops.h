@@ -281,6 +281,14 @@ int coin_match_abc(const float* on_boxes, const int64_t* on_classes, const float
  * K_cap <= 8192 (larger grids have no tail worth ordering). One single-CTA launch. */
 int coin_roi_launch_order(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct, int32_t* perm,
                           coin_stream_t stream);
+/* coin_roi_launch_order and the size split below in ONE launch: perm = [largest big_pct % | rest | smallest small_pct % | diverted],
+ * where "diverted" are the RoIs with area > area_thr or a side > side_thr (pixels) - at most divert_cap of them, otherwise
+ * none is diverted; perm_divert = the diverted RoIs alone; counts = int32 [2] = {K_live - diverted, diverted}. A caller
+ * launches its main kernel over perm with the live count counts[0] and the separable kernel over perm_divert with counts[1]
+ * (ops.roi_align_forward_planned); perm as a whole stays a permutation of the live RoIs (for the backward). */
+int coin_roi_launch_plan(const float* rois, int K_cap, const int32_t* k_dev, int small_pct, int big_pct, float area_thr,
+                         float side_thr, int divert_cap, int32_t* perm, int32_t* perm_divert, int32_t* counts,
+                         coin_stream_t stream);
 /* Two RoI index lists by box size (pixels): perm_big = RoIs with area > area_thr or a side > side_thr, perm_small = the
  * rest, both in input order - or in the order of `order` (a coin_roi_launch_order result, may be NULL);
  * perm_big holds at most big_cap RoIs (the capacity its launch is sized for; further big RoIs stay in perm_small);

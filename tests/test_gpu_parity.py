@@ -224,6 +224,35 @@ def test_roi_launch_order_is_a_permutation_and_changes_nothing(dev, k, live):
         assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max())
 
 
+@pytest.mark.parametrize("n_big", [0, 3, 40])
+def test_roi_launch_plan_orders_and_diverts(dev, n_big):
+    """coin_roi_launch_plan = launch order + size split in one launch: perm is a permutation of the RoIs whose tail holds the
+    diverted (map-sized) RoIs, perm_divert lists them, counts = (rest, diverted); more than the capacity (32): none diverted."""
+    g = synth.gen(99 + n_big)
+    k = 900
+    boxes = synth.random_boxes(g, k, 600, 1200)                    # <= 500 px a side: none exceeds the thresholds
+    where = torch.randperm(k, generator=g)[:n_big]
+    boxes[where] = torch.tensor([0.0, 0.0, 1200.0, 600.0])
+    if n_big:
+        boxes[where[0]] = torch.tensor([0.0, 431.2, 1200.0, 434.8])   # wide and flat: caught by the side threshold
+    rois = torch.cat((torch.zeros(k, 1), boxes), 1).to(dev)
+    perm, plan = ops.roi_launch_plan(rois, 1.0 / 16)
+    p, pd, cnt = perm.cpu().long(), plan[1].cpu().long(), plan[2].tolist()
+    assert torch.equal(p.sort().values, torch.arange(k))
+    diverted = n_big if n_big <= ops.BIG_ROI_CAP else 0
+    assert cnt == [k - diverted, diverted]
+    assert sorted(pd[:diverted].tolist()) == sorted(where.tolist()[:diverted] if diverted else [])
+    assert sorted(p[k - diverted:].tolist()) == sorted(pd[:diverted].tolist())
+    x = torch.randn(1, 64, 37, 75, generator=g).to(dev)
+    nhwc = ops.to_nhwc_f32(x)
+    a = ops.roi_align_forward([nhwc], (1 / 16,), rois, None, (14, 14), 0, True, torch.float32)
+    b = ops.roi_align_forward_planned([nhwc], (1 / 16,), rois, (14, 14), 0, True, torch.float32, plan=plan)
+    close(b, a, scale=float(x.abs().max()))                        # (the diverted rows come from the separable kernel)
+    keep = torch.ones(k, dtype=torch.bool)
+    keep[pd[:diverted]] = False
+    assert torch.equal(a[keep.to(dev)], b[keep.to(dev)])
+
+
 def test_roi_align_map_sized_rois_do_not_stall_the_grid(dev):
     """A clipped, mis-regressed detection is a RoI the size of the map; for the register-tile kernel that is one CTA walking
     256 channels of 37 x 75 cells for ~1 ms (it turned rank 1 of an 8-GPU run from 0.92 into 2.4 ms per step). The layer
