@@ -207,12 +207,18 @@ def subsample_anchor_labels(label: torch.Tensor, batch_size_per_image: int, posi
 
 def label_and_sample_proposals(proposals: list, targets, matcher: Matcher, num_classes: int, batch_size_per_image: int,
                                positive_fraction: float, proposal_append_gt: bool = True, bg_train: bool = True,
-                               generator="torch", seed: int = 0, offset: int = 0) -> list:
-    """``OpenVocabularyRes5ROIHeads.label_and_sample_proposals`` for the 'step_one' / 'step_two' branches
-    (clip_roi_heads.py:342-399). ``proposals``: one Instances(proposal_boxes, ...) per image; ``targets`` = (A, B, C) lists
+                               generator="torch", seed: int = 0, offset: int = 0, branch: str = "step_two") -> list:
+    """``OpenVocabularyRes5ROIHeads.label_and_sample_proposals`` (clip_roi_heads.py:283-399). 'step_one' / 'step_two'
+    (:342-399): ``proposals`` = one Instances(proposal_boxes, ...) per image; ``targets`` = (A, B, C) lists
     of pseudo-label Instances as ``match_dual_teacher`` returns them. Returns one (proposals_a, proposals_b, proposals_bg)
     triple per image with the reference's fields: the fused IoU + Matcher + private-box rule (A6-A8), the class assignment
-    and the subsample run in kernels; the per-group field gathers are index selections."""
+    and the subsample run in kernels; the per-group field gathers are index selections. 'pre_train' (:286-340): see
+    ``label_and_sample_proposals_pretrain``."""
+    if branch == "pre_train":
+        return label_and_sample_proposals_pretrain(proposals, targets, matcher, num_classes, batch_size_per_image,
+                                                   positive_fraction, proposal_append_gt, generator, seed, offset)
+    if branch not in ("step_one", "step_two"):
+        raise ValueError(branch)
     a_targets, b_targets, c_targets = targets
     out = []
     for i, (p, a, b, c) in enumerate(zip(proposals, a_targets, b_targets, c_targets)):
@@ -252,6 +258,49 @@ def label_and_sample_proposals(proposals: list, targets, matcher: Matcher, num_c
     return out
 
 
+def label_and_sample_proposals_pretrain(proposals: list, targets: list, matcher: Matcher, num_classes: int,
+                                        batch_size_per_image: int, positive_fraction: float, proposal_append_gt: bool = True,
+                                        generator="torch", seed: int = 0, offset: int = 0) -> list:
+    """The 'pre_train' branch of ``label_and_sample_proposals`` (clip_roi_heads.py:286-340): ``targets`` = one Instances per
+    image with ``gt_boxes``, ``gt_classes_offline`` (+ any other gt_* field) and, optionally on ALL of them, ``no_thresh_boxes``
+    - boxes that are matched like ground truth but must be neither foreground nor sampled as such (:300-309: label -1 unless
+    the Matcher said background, index reset to 0). Returns one (proposals_fg, proposals_bg) pair per image. Unlike the
+    reference (:289-291) the targets are not modified: ``no_thresh_boxes`` stays on them."""
+    with_nt = len(targets) > 0 and all(t.has("no_thresh_boxes") for t in targets)
+    out = []
+    for i, (p, t) in enumerate(zip(proposals, targets)):
+        boxes = p.proposal_boxes
+        logits = p.objectness_logits if p.has("objectness_logits") else None
+        gt = t.gt_boxes
+        if proposal_append_gt:
+            boxes = Boxes.cat([boxes, gt])
+            if logits is not None:
+                gt_logit = math.log((1.0 - 1e-10) / (1 - (1.0 - 1e-10)))
+                logits = torch.cat([logits, torch.full((len(gt),), gt_logit, dtype=logits.dtype, device=logits.device)])
+        if with_nt:
+            nt = t.get("no_thresh_boxes")
+            idx, lab = matcher.match_boxes(Boxes.cat([gt, nt]), boxes)
+            lab, idx, _, _ = ops.relabel_rpn_(idx, lab, len(gt), len(nt))      # the same rule as the RPN's C boxes
+        else:
+            idx, lab = matcher.match_boxes(gt, boxes)
+        sampled, temp = sample_proposals(idx, lab, t.gt_classes_offline, num_classes, batch_size_per_image, positive_fraction,
+                                         generator, seed, offset + i)
+        m = idx[sampled]
+        bg = temp == num_classes
+        fg = ~bg
+        size = p.image_size
+        pf, pbg = Instances(size), Instances(size)
+        pf.proposal_boxes, pbg.proposal_boxes = Boxes(boxes.tensor[sampled[fg]]), Boxes(boxes.tensor[sampled[bg]])
+        if logits is not None:
+            pf.objectness_logits, pbg.objectness_logits = logits[sampled[fg]], logits[sampled[bg]]
+        pbg.gt_classes = temp[bg]
+        for name, val in t.get_fields().items():
+            if name.startswith("gt_"):
+                pf.set(name, val[m[fg]])
+        out.append((pf, pbg))
+    return out
+
+
 def label_anchors(matcher: Matcher, a_boxes: Boxes, c_boxes: Boxes, anchors: Boxes):
     """rpn.py:209-228: returns (gt_labels, matched_idxs, distillation_idxs, distillation_labels)."""
     gt = Boxes.cat([a_boxes, c_boxes])
@@ -276,6 +325,19 @@ def label_and_sample_anchors(matcher: Matcher, a_boxes: Boxes, c_boxes: Boxes, a
     else:
         matched_gt_boxes = a_boxes.tensor[idx]
     return lab, matched_gt_boxes, didx, dlab
+
+
+def label_and_sample_anchors_pretrain(matcher: Matcher, gt_boxes: Boxes, no_thresh_boxes: Optional[Boxes], anchors: Boxes,
+                                      batch_size_per_image: int, positive_fraction: float, generator="torch", seed: int = 0,
+                                      offset: int = 0):
+    """``DualTeacherRPN.label_and_sample_anchors`` for one image of the 'pre_train' branch (rpn.py:139-197,
+    anchor_boundary_thresh < 0): returns (gt_labels, matched_gt_boxes). ``no_thresh_boxes`` (may be None) are treated exactly
+    like the private (C) boxes of the later branches - label -1 unless background, index reset to 0, and without any gt box
+    only the anchors that matched one of them as background keep a label (:183-190)."""
+    nt = no_thresh_boxes if no_thresh_boxes is not None else Boxes(gt_boxes.tensor.new_zeros((0, 4)))
+    lab, mgb, _, _ = label_and_sample_anchors(matcher, gt_boxes, nt, anchors, batch_size_per_image, positive_fraction,
+                                              generator, seed, offset)
+    return lab, mgb
 
 
 class AnchorGrid(tuple):

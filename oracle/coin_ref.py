@@ -290,6 +290,17 @@ def relabel_rpn(matched_idxs, labels, len_a, len_c):
     return lab, idx, dist_idx, dist_lab
 
 
+def relabel_pretrain(matched_idxs, labels, n_gt, n_no_thresh):
+    """The 'pre_train' branches (clip_roi_heads.py:305-309, rpn.py:161-165): a match on a `no_thresh_boxes` row is
+    neither foreground nor (unless the Matcher already said background) kept: label -1, and its index is reset to 0.
+    Returns (labels, matched_idxs)."""
+    idx, lab = matched_idxs.clone(), labels.clone()
+    in_nt = (idx >= n_gt) & (idx < n_gt + n_no_thresh)
+    lab[in_nt & ~(lab == 0)] = -1
+    idx[in_nt] = 0
+    return lab, idx
+
+
 # ------------------------------------------------------------------------------------------------
 # A9  knowledge separation: coin/utils/util.py:434-507 + coin/engine/trainer.py:338-485
 # ------------------------------------------------------------------------------------------------

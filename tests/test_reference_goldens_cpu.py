@@ -170,6 +170,74 @@ def test_anchor_labelling_equals_reference():
             assert torch.equal(mgb.double().sum(0), c["matched_gt_boxes_colsum"])
 
 
+PRETRAIN = load_golden("labels_pretrain_ref.pt")
+
+
+def test_pretrain_roi_labelling_equals_reference():
+    """The 'pre_train' branch of label_and_sample_proposals (clip_roi_heads.py:286-317), without and with
+    `no_thresh_boxes`: the (matched_idxs, matched_labels) the reference hands to _sample_proposals, and the sampled
+    (fg, bg) sets replayed with the same torch seed."""
+    for c in PRETRAIN["roi"]:
+        what = (c["label"], c["with_no_thresh"])
+        gt, nt = c["gt_boxes"], c["no_thresh_boxes"]
+        props = torch.cat((c["proposals"], gt))                    # PROPOSAL_APPEND_GT: only the gt rows join
+        rows = torch.cat((gt, nt)) if c["with_no_thresh"] else gt
+        idx, lab = d2_ref.Matcher([0.5], [0, 1], False)(d2_ref.pairwise_iou(rows, props))
+        if c["with_no_thresh"]:
+            lab, idx = coin_ref.relabel_pretrain(idx, lab, len(gt), len(nt))
+        assert torch.equal(idx, c["matched_idxs"]), what
+        assert torch.equal(lab, c["matched_labels"]), what
+        torch.manual_seed(c["torch_seed"])
+        k = c["num_classes"]
+        pre = c["gt_classes_offline"][idx].clone() if len(gt) else torch.zeros_like(idx) + k
+        if len(gt):
+            pre[lab == 0], pre[lab == -1] = k, -1
+        perms = (torch.randperm(int(((pre != -1) & (pre != k)).sum())), torch.randperm(int((pre == k).sum())))
+        sampled, cls = d2_ref.sample_proposals(idx, lab, c["gt_classes_offline"], k, c["batch_size_per_image"],
+                                               c["positive_fraction"], perms)
+        bg = cls == c["num_classes"]
+        assert torch.equal(props[sampled[~bg]], c["sampled"]["fg"]["proposal_boxes"]), what
+        assert torch.equal(props[sampled[bg]], c["sampled"]["bg"]["proposal_boxes"]), what
+        assert torch.equal(cls[bg], c["sampled"]["bg"]["gt_classes"]), what
+        m = idx[sampled][~bg]
+        assert torch.equal(gt[m], c["sampled"]["fg"]["gt_boxes"]), what
+        assert torch.equal(c["gt_classes_offline"][m], c["sampled"]["fg"]["gt_classes_offline"]), what
+        assert torch.equal(c["gt_probs"][m], c["sampled"]["fg"]["gt_probs"]), what
+
+
+def test_pretrain_anchor_labelling_equals_reference():
+    """The 'pre_train' branch of label_and_sample_anchors (rpn.py:139-197): labels before _subsample_labels, labels after
+    it and the no-gt epilogue (rpn.py:183-190), matched gt boxes."""
+    for c in PRETRAIN["rpn"]:
+        what = (c["label"], c["with_no_thresh"])
+        hf, wf = c["anchors_hw"]
+        anchors = d2_ref.grid_anchors(hf, wf, 16, d2_ref.cell_anchors())
+        gt, nt = c["gt_boxes"], c["no_thresh_boxes"]
+        rows = torch.cat((gt, nt)) if c["with_no_thresh"] else gt
+        idx, lab = d2_ref.Matcher([0.3, 0.7], [0, -1, 1], True)(d2_ref.pairwise_iou(rows, anchors))
+        bg_nt = None
+        if c["with_no_thresh"]:
+            bg_nt = (idx >= len(gt)) & (idx < len(gt) + len(nt)) & (lab == 0)
+            lab, idx = coin_ref.relabel_pretrain(idx, lab, len(gt), len(nt))
+        assert torch.equal(lab, c["labels_before_sampling"]), what
+        torch.manual_seed(c["torch_seed"])
+        perms = (torch.randperm(int((lab == 1).sum())), torch.randperm(int((lab == 0).sum())))
+        pos, neg = d2_ref.subsample_labels(lab, c["batch_size_per_image"], c["positive_fraction"], 0, perms)
+        out = torch.full_like(lab, -1)
+        out[pos], out[neg] = 1, 0
+        if len(gt) == 0:
+            if bg_nt is None:
+                out[:] = -1
+            else:
+                out[~bg_nt] = -1
+            mgb = torch.zeros_like(anchors)
+        else:
+            mgb = gt[idx]
+        assert torch.equal(out, c["gt_labels"]), what
+        assert torch.equal(mgb[:256], c["matched_gt_boxes_head"]), what
+        assert torch.equal(mgb.double().sum(0), c["matched_gt_boxes_colsum"]), what
+
+
 def test_rpn_distillation_loss_equals_reference():
     by_label = {c["label"]: c for c in LABELS["rpn"]}
     finite = 0

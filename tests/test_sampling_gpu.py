@@ -91,6 +91,55 @@ def test_label_and_sample_anchors_equals_reference_outputs(dev):
         assert torch.equal(mgb.double().sum(0).cpu(), r["matched_gt_boxes_colsum"]), r["label"]
 
 
+PRETRAIN = load_golden("labels_pretrain_ref.pt")
+
+
+@pytest.mark.parametrize("via_branch", [False, True])
+def test_pretrain_label_and_sample_proposals_equals_reference_outputs(dev, via_branch):
+    """clip_roi_heads.py:286-340 ('pre_train', PROPOSAL_APPEND_GT, without / with no_thresh_boxes, also without any gt box)
+    run unmodified with torch.manual_seed(2024) -> tests/golden/labels_pretrain_ref.pt; every field of the (fg, bg) pair."""
+    m = layers.Matcher([0.5], [0, 1], allow_low_quality_matches=False)
+    for c in PRETRAIN["roi"]:
+        size = tuple(c["image_size"])
+        p = Instances(size)
+        p.proposal_boxes = Boxes(c["proposals"].to(dev))
+        p.objectness_logits = c["objectness_logits"].to(dev)
+        t = Instances(size)
+        t.gt_boxes = Boxes(c["gt_boxes"].to(dev))
+        t.gt_classes_offline = c["gt_classes_offline"].to(dev)
+        t.gt_probs = c["gt_probs"].to(dev)
+        if c["with_no_thresh"]:
+            t._fields["no_thresh_boxes"] = Boxes(c["no_thresh_boxes"].to(dev))    # (its length is its own)
+        torch.manual_seed(c["torch_seed"])
+        args = ([p], [t], m, c["num_classes"], c["batch_size_per_image"], c["positive_fraction"])
+        res = (integration.label_and_sample_proposals(*args, branch="pre_train") if via_branch
+               else integration.label_and_sample_proposals_pretrain(*args))
+        assert t.has("no_thresh_boxes") == c["with_no_thresh"]
+        for got, name in zip(res[0], ("fg", "bg")):
+            want = c["sampled"][name]
+            assert set(got.get_fields()) == set(want), (c["label"], name)
+            for k, v in want.items():
+                gv = got.get(k)
+                gv = gv.tensor if isinstance(gv, Boxes) else gv
+                assert torch.equal(gv.cpu(), v), (c["label"], c["with_no_thresh"], name, k)
+
+
+def test_pretrain_label_and_sample_anchors_equals_reference_outputs(dev):
+    """rpn.py:139-197 ('pre_train') run unmodified with torch.manual_seed(2024), replayed with the same seed."""
+    m = layers.Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=True)
+    for r in PRETRAIN["rpn"]:
+        hf, wf = r["anchors_hw"]
+        anchors = Boxes(d2_ref.grid_anchors(hf, wf, 16, d2_ref.cell_anchors()).to(dev))
+        nt = Boxes(r["no_thresh_boxes"].to(dev)) if r["with_no_thresh"] else None
+        torch.manual_seed(r["torch_seed"])
+        lab, mgb = integration.label_and_sample_anchors_pretrain(m, Boxes(r["gt_boxes"].to(dev)), nt, anchors,
+                                                                 r["batch_size_per_image"], r["positive_fraction"])
+        what = (r["label"], r["with_no_thresh"])
+        assert torch.equal(lab.cpu(), r["gt_labels"]), what
+        assert torch.equal(mgb[:256].cpu(), r["matched_gt_boxes_head"]), what
+        assert torch.equal(mgb.double().sum(0).cpu(), r["matched_gt_boxes_colsum"]), what
+
+
 def test_rpn_distillation_loss_and_gradient(dev):
     by_label = {c["label"]: c for c in LABELS["rpn"]}
     for c in LABELS["rpn_loss"]:
