@@ -68,20 +68,29 @@ def resize_boxes(boxes: torch.Tensor, size: Tuple[int, int], clip: bool = False)
     return ops.boxes_cxcywh_to_xyxy(boxes, size, clip)
 
 
-def gdino_collect(ori: Instances, nms_module, rcnn_thresh: float, rpn_thresh: float, nms_thresh: float) -> dict:
-    """GDINO_PROCESSOR.post_process without ZOOM / AUG (gdino_processor.py:287-293) + GDINO_PROCESSOR.nms (:164-182):
-    the two score thresholds, then ``mynms.nms`` (coin_b200.layers.MyNMS) per tag."""
-    out = {}
-    for tag, thr in (("RCNN", rcnn_thresh), ("RPN", rpn_thresh)):
-        sub = ori[ori.scores >= thr]
-        _, boxes, scores, probs, labels = nms_module.nms(sub.pred_boxes.tensor, sub.scores, sub.probs, sub.pred_classes,
-                                                         nms_thresh)
+def gdino_collect(ori: Instances, nms_module, rcnn_thresh: float, rpn_thresh: float, nms_thresh: float,
+                  aug: Optional[Instances] = None) -> dict:
+    """GDINO_PROCESSOR.post_process without ZOOM (gdino_processor.py:287-298) + GDINO_PROCESSOR.nms (:164-182):
+    the two score thresholds, then ``mynms.nms`` (coin_b200.layers.MyNMS) per tag. ``aug`` = the detections of the augmented
+    view (cfg.INPUT.TEACHER_CLOUD.COLLECT_AUG): adds 'RPN_AUG' = the NMS of the NMS'ed RPN set followed by them (:295-297),
+    which ``preprocess_results`` then uses in place of 'RPN'."""
+    def nms(boxes, scores, probs, classes):
+        _, boxes, scores, probs, labels = nms_module.nms(boxes, scores, probs, classes, nms_thresh)
         inst = Instances(ori.image_size)
         inst.pred_boxes = Boxes(boxes)
         inst.scores = scores
         inst.pred_classes = labels
         inst.probs = probs
-        out[tag] = {"instances": inst}
+        return {"instances": inst}
+
+    out = {}
+    for tag, thr in (("RCNN", rcnn_thresh), ("RPN", rpn_thresh)):
+        sub = ori[ori.scores >= thr]
+        out[tag] = nms(sub.pred_boxes.tensor, sub.scores, sub.probs, sub.pred_classes)
+    if aug is not None:
+        rpn = out["RPN"]["instances"]
+        out["RPN_AUG"] = nms(torch.cat((rpn.pred_boxes.tensor, aug.pred_boxes.tensor)), torch.cat((rpn.scores, aug.scores)),
+                             torch.cat((rpn.probs, aug.probs)), torch.cat((rpn.pred_classes, aug.pred_classes)))
     return out
 
 

@@ -108,15 +108,21 @@ def resize_boxes(boxes: torch.Tensor, size) -> torch.Tensor:
     return torch.cat((xy, b[:, 2:] + xy), dim=1)
 
 
-def gdino_collect(ori: DetSet, method: str, rcnn_thresh: float, rpn_thresh: float, nms_thresh: float):
-    """GDINO_PROCESSOR.post_process without ZOOM/AUG (gdino_processor.py:287-293) + .nms (:164-182): score
-    thresholds for the two tags, then MyNMS(method).nms per tag."""
+def gdino_collect(ori: DetSet, method: str, rcnn_thresh: float, rpn_thresh: float, nms_thresh: float,
+                  aug: Optional[DetSet] = None):
+    """GDINO_PROCESSOR.post_process without ZOOM (gdino_processor.py:287-298) + .nms (:164-182): score
+    thresholds for the two tags, then MyNMS(method).nms per tag; with an AUG set, 'RPN_AUG' = the NMS of the NMS'ed
+    RPN set followed by the AUG detections (:295-297)."""
     out = {}
     for tag, thr in (("RCNN", rcnn_thresh), ("RPN", rpn_thresh)):
         keep = ori["scores"] >= thr
         sub = {k: v[keep] for k, v in ori.items()}
         _, b, s, p, l = mynms(method, sub["pred_boxes"], sub["scores"], sub["probs"], sub["pred_classes"], nms_thresh)
         out[tag] = {"pred_boxes": b, "scores": s, "pred_classes": l, "probs": p}
+    if aug is not None:
+        both = {k: torch.cat((out["RPN"][k], aug[k])) for k in ("pred_boxes", "scores", "pred_classes", "probs")}
+        _, b, s, p, l = mynms(method, both["pred_boxes"], both["scores"], both["probs"], both["pred_classes"], nms_thresh)
+        out["RPN_AUG"] = {"pred_boxes": b, "scores": s, "pred_classes": l, "probs": p}
     return out
 
 

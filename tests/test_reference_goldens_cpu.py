@@ -289,6 +289,16 @@ def test_gdino_collect_equals_reference():
                 assert torch.equal(got[tag][k], v), (c["method"], tag, k)
 
 
+def test_gdino_collect_with_aug_equals_reference():
+    """post_process with an 'AUG' set (gdino_processor.py:295-297): RPN_AUG = nms(cat(nms(RPN), AUG)); also an empty ORI set."""
+    g = load_golden("gdino_aug_ref.pt")
+    for c in g["cases"]:
+        got = coin_ref.gdino_collect(c["in"], c["method"], c["rcnn_thresh"], c["rpn_thresh"], c["nms_thresh"], aug=c["aug"])
+        for tag in ("RCNN", "RPN", "RPN_AUG"):
+            for k, v in c["out"][tag].items():
+                assert torch.equal(got[tag][k], v), (c["method"], tag, k)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/coin"), reason="the reference tree exists in the build container only")
 def test_reference_modules_load_unmodified_under_the_stub_finder():
     """oracle/ref_loader.py: every module is the reference's file (by path), not a copy."""

@@ -158,6 +158,21 @@ def test_gdino_collection_nms_equals_reference_outputs(dev):
             torch.testing.assert_close(got.probs.cpu(), want["probs"], rtol=1e-5, atol=1e-6)
 
 
+def test_gdino_collection_with_aug_equals_reference_outputs(dev):
+    """gdino_processor.py:287-298 with an 'AUG' set (and an empty ORI set): the three tags."""
+    g = load_golden("gdino_aug_ref.pt")
+    for c in g["cases"]:
+        out = integration.gdino_collect(_inst(c["in"], dev, (1024, 2048)), layers.MyNMS(c["method"]), c["rcnn_thresh"],
+                                        c["rpn_thresh"], c["nms_thresh"], aug=_inst(c["aug"], dev, (1024, 2048)))
+        for tag in ("RCNN", "RPN", "RPN_AUG"):
+            want = c["out"][tag]
+            got = out[tag]["instances"]
+            assert torch.equal(got.pred_classes.cpu(), want["pred_classes"]), (c["method"], tag)
+            torch.testing.assert_close(got.pred_boxes.tensor.cpu(), want["pred_boxes"], rtol=1e-5, atol=PIX_ATOL)
+            torch.testing.assert_close(got.scores.cpu(), want["scores"], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(got.probs.cpu(), want["probs"], rtol=1e-5, atol=1e-6)
+
+
 def test_unmodified_reference_nms_module_runs_on_this_library(dev):
     """Drop-in proof for coin/layers/nms.py: the fixture outputs came from the reference's MyNMS calling
     detectron2.layers.batched_nms; coin_b200.batched_nms is that symbol's replacement - same keep list on the
