@@ -140,7 +140,7 @@ def roi_launch_plan(rois: torch.Tensor, scale: float, k_dev: Optional[torch.Tens
     perm = torch.empty((k,), dtype=torch.int32, device=rois.device)
     cap = min(BIG_ROI_CAP, k)
     pd = torch.empty((cap,), dtype=torch.int32, device=rois.device)
-    counts = torch.zeros((2,), dtype=torch.int32, device=rois.device)
+    counts = torch.empty((2,), dtype=torch.int32, device=rois.device)     # (written by the kernel: no fill launch)
     if k < ORDER_MIN_ROIS:
         small_pct = big_pct = 0              # below ~1 wave of CTAs there is no tail to fill: only the split
     check(lib.coin_roi_launch_plan(_ptr(rois), k, _ptr(None if k_dev is None else _count(k_dev)), int(small_pct), int(big_pct),
@@ -642,7 +642,7 @@ def concat_rows(segments, width_out: Optional[int] = None, out_cap: Optional[int
     cap = worst if out_cap is None else int(out_cap)
     dev = keep[0].device
     out = torch.empty((max(cap, 1), width_out), dtype=torch.float32, device=dev)
-    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)       # (written by the kernel: no fill launch)
     check(lib.coin_concat_rows(arr, n, width_in, width_out, _ptr(out), cap, _ptr(count), _stream()))
     return out, count
 

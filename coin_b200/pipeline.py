@@ -188,8 +188,7 @@ class RoIPathStep:
         # ---- ROIAlign forward (S4) and backward (S5) over the sampled RoIs: own stream, needs only the map
         with torch.cuda.stream(s_roi):
             nhwc = ops.to_nhwc_f32(d["features"])
-            rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
-                              for i in range(n_img)])
+            rois = self._batched_rois(d, n_img)
             perm, plan = ops.roi_launch_plan(rois, scale[0], small_pct=self.roi_tail_pct)
             out["pooled"] = ops.roi_align_forward_planned([nhwc], scale, rois, size, 0, True, torch.float32, plan=plan,
                                                           events=ev["fwd"] if ev else None)
@@ -295,6 +294,13 @@ class RoIPathStep:
                 main.wait_stream(st)
         return out
 
+    @staticmethod
+    def _batched_rois(d, n_img: int) -> torch.Tensor:
+        """[batch index | box] rows of every image's sampled RoIs (convert_boxes_to_pooler_format) in ONE launch: the ROIAlign
+        forward waits for this list and its launch plan, so the seven torch fill / cat kernels it used to take were ~25 us
+        of lead-in at the start of every step."""
+        return ops.concat_rows([(d[f"{i}.rois"], None, float(i)) for i in range(n_img)], width_out=5)[0]
+
     def _mark(self, name: str) -> None:
         """Named timestamp on the current stream (only when a timeline is being collected)."""
         if self.timeline is not None:
@@ -319,8 +325,7 @@ class RoIPathStep:
 
         self._mark("start")
         with torch.cuda.stream(s_img[2 * n_img]):     # (this stream's chain starts only after knowledge separation)
-            rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
-                              for i in range(n_img)])
+            rois = self._batched_rois(d, n_img)
             # launch order (smallest RoIs last) + size split (map-sized RoIs, if any, go to the separable kernel:
             # ops.roi_align_forward_planned) in one launch, beside the layout transform below
             perm, plan = ops.roi_launch_plan(rois, scale[0], small_pct=self.roi_tail_pct)
@@ -512,8 +517,7 @@ class RoIPathStep:
         on the current stream, `iters` times, appending a CUDA-event pair per launch to events['fwd'/'bwd']."""
         sh, dev = self.shape, self.device
         nhwc = ops.to_nhwc_f32(d["features"])
-        rois = torch.cat([torch.cat((torch.full((sh.rois, 1), float(i), device=dev), d[f"{i}.rois"]), dim=1)
-                          for i in range(sh.images)])
+        rois = self._batched_rois(d, sh.images)
         n, c, h, w = d["features"].shape
         size, scale = (sh.pooled, sh.pooled), (1.0 / sh.stride,)
         perm = ops.roi_launch_order(rois, small_pct=self.roi_tail_pct)     # as in the step (its own small launch)
