@@ -366,6 +366,61 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, OutT* __restri
     }
 }
 
+// The same transforms with 128 (hw) x 32 (c) tiles and every load of a thread issued before the barrier: 16 independent
+// loads per thread instead of 4, a quarter of the CTAs (the 32 x 32 version leaves the copy at ~3.2 TB/s on a 68 MB round trip).
+constexpr int kLtHw = 128;
+template <typename InT>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_v2_kernel(const InT* __restrict__ in, float* __restrict__ out, int C, int HW) {
+    __shared__ float t[32][kLtHw + 1];
+    const size_t img = (size_t)blockIdx.z * C * HW;
+    const int hw0 = blockIdx.x * kLtHw, cb = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;      // (32, 8)
+    float v[4][kLtHw / 32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < kLtHw / 32; ++j) {
+            const int c = cb + ty + 8 * i, hw = hw0 + tx + 32 * j;
+            v[i][j] = (c < C && hw < HW) ? to_f32(in[img + (size_t)c * HW + hw]) : 0.0f;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < kLtHw / 32; ++j) t[ty + 8 * i][tx + 32 * j] = v[i][j];
+    __syncthreads();
+    const int c = cb + tx;
+#pragma unroll 4
+    for (int r = ty; r < kLtHw; r += 8) {
+        const int hw = hw0 + r;
+        if (c < C && hw < HW) out[img + (size_t)hw * C + c] = t[tx][r];
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_v2_kernel(const float* __restrict__ in, OutT* __restrict__ out, int C, int HW) {
+    __shared__ float t[kLtHw][33];
+    const size_t img = (size_t)blockIdx.z * C * HW;
+    const int hw0 = blockIdx.x * kLtHw, cb = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int c = cb + tx;
+    float v[kLtHw / 8];
+#pragma unroll
+    for (int i = 0; i < kLtHw / 8; ++i) {
+        const int hw = hw0 + ty + 8 * i;
+        v[i] = (c < C && hw < HW) ? in[img + (size_t)hw * C + c] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < kLtHw / 8; ++i) t[ty + 8 * i][tx] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < kLtHw / 32; ++j) {
+            const int cc = cb + ty + 8 * i, hw = hw0 + tx + 32 * j;
+            if (cc < C && hw < HW) out[img + (size_t)cc * HW + hw] = from_f32<OutT>(t[tx + 32 * j][ty + 8 * i]);
+        }
+}
+
 __global__ void pooler_levels_kernel(const float* __restrict__ boxes, int64_t n, int min_level, int max_level,
                                      float canonical_size, float canonical_level, int32_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -752,6 +807,14 @@ extern "C" int coin_nchw_to_nhwc_f32(const void* in, int in_dtype, float* out, i
     COIN_REQUIRE(in && out, "nchw_to_nhwc: null pointer");
     const int HW = H * W;
     dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N), block(32, 8);
+    if (env_int("COIN_LAYOUT_V2", 1)) {
+        dim3 g2((unsigned)ceil_div(HW, kLtHw), (unsigned)ceil_div(C, 32), (unsigned)N);
+        if (in_dtype == COIN_F32)
+            nchw_to_nhwc_v2_kernel<float><<<g2, block, 0, as_stream(stream)>>>(static_cast<const float*>(in), out, C, HW);
+        else
+            nchw_to_nhwc_v2_kernel<__half><<<g2, block, 0, as_stream(stream)>>>(static_cast<const __half*>(in), out, C, HW);
+        return check_launch("nchw_to_nhwc_v2_kernel");
+    }
     if (in_dtype == COIN_F32)
         nchw_to_nhwc_kernel<float><<<grid, block, 0, as_stream(stream)>>>(static_cast<const float*>(in), out, C, HW);
     else
@@ -767,6 +830,14 @@ extern "C" int coin_nhwc_f32_to_nchw(const float* in, void* out, int out_dtype, 
     COIN_REQUIRE(in && out, "nhwc_to_nchw: null pointer");
     const int HW = H * W;
     dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N), block(32, 8);
+    if (env_int("COIN_LAYOUT_V2", 1)) {
+        dim3 g2((unsigned)ceil_div(HW, kLtHw), (unsigned)ceil_div(C, 32), (unsigned)N);
+        if (out_dtype == COIN_F32)
+            nhwc_to_nchw_v2_kernel<float><<<g2, block, 0, as_stream(stream)>>>(in, static_cast<float*>(out), C, HW);
+        else
+            nhwc_to_nchw_v2_kernel<__half><<<g2, block, 0, as_stream(stream)>>>(in, static_cast<__half*>(out), C, HW);
+        return check_launch("nhwc_to_nchw_v2_kernel");
+    }
     if (out_dtype == COIN_F32)
         nhwc_to_nchw_kernel<float><<<grid, block, 0, as_stream(stream)>>>(in, static_cast<float*>(out), C, HW);
     else

@@ -252,15 +252,25 @@ def roi_align_backward(grad_out: torch.Tensor, shapes: Sequence[Tuple[int, int, 
                        rois: torch.Tensor, roi_level: Optional[torch.Tensor], output_size: Tuple[int, int],
                        sampling_ratio: int, aligned: bool, out_dtypes: Sequence[torch.dtype],
                        events: Optional[list] = None, perm: Optional[torch.Tensor] = None, plan=None,
-                       big_stream=None) -> List[torch.Tensor]:
+                       big_stream=None, zeroed: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
     """Returns one NCHW gradient per level (shape ``shapes[i]`` = (N,C,H,W), dtype ``out_dtypes[i]``).
     perm: launch order (roi_launch_order). plan: a roi_split_by_area result of the forward (single level): the map-sized
-    RoIs' gradients are scattered by the separable kernel (on ``big_stream`` if given), the rest by the default kernel."""
+    RoIs' gradients are scattered by the separable kernel (on ``big_stream`` if given), the rest by the default kernel.
+    zeroed: one ZERO-FILLED fp32 [N,H,W,C] accumulation buffer per level, ready on the current stream (a caller that zeroes
+    them ahead of time, beside other work, takes the fill off the path between forward and backward); consumed."""
     grad_out = _cuda(grad_out, "grad_out").contiguous()
     rois = _f32c(rois, "rois")
     k, c = rois.shape[0], shapes[0][1]
     ph, pw = output_size
-    bufs = [torch.zeros((n, h, w, cc), dtype=torch.float32, device=grad_out.device) for (n, cc, h, w) in shapes]
+    if zeroed is not None:
+        bufs = list(zeroed)
+        for buf, (n, cc, h, w) in zip(bufs, shapes):
+            if tuple(buf.shape) != (n, h, w, cc) or buf.dtype != torch.float32 or not buf.is_contiguous():
+                raise ValueError("coin_b200: zeroed buffers must be contiguous fp32 [N,H,W,C] per level")
+        if len(bufs) != len(shapes):
+            raise ValueError("coin_b200: one zeroed buffer per level")
+    else:
+        bufs = [torch.zeros((n, h, w, cc), dtype=torch.float32, device=grad_out.device) for (n, cc, h, w) in shapes]
     if roi_level is not None:
         roi_level = _cuda(roi_level, "roi_level").to(torch.int32).contiguous()
     def launch(k_launch, k_dev, order):

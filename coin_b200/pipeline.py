@@ -330,6 +330,11 @@ class RoIPathStep:
             # ops.roi_align_forward_planned) in one launch, beside the layout transform below
             perm, plan = ops.roi_launch_plan(rois, scale[0], small_pct=self.roi_tail_pct)
             rois_ready = s_img[2 * n_img].record_event()
+            gbuf = gbuf_ready = None
+            if backward:      # the backward's accumulation buffer is zeroed here, beside the forward, not between the two
+                n, c, h, w = d["features"].shape
+                gbuf = torch.zeros((n, h, w, c), dtype=torch.float32, device=dev)
+                gbuf_ready = s_img[2 * n_img].record_event()
         with torch.cuda.stream(s_roi):
             nhwc = ops.to_nhwc_f32(d["features"])
             nhwc_ready = s_roi.record_event()
@@ -366,7 +371,7 @@ class RoIPathStep:
             slot(f"rpn{i}", nkeep)
         if self.roi_gate in ("det", "det+rpn"):
             gate += det_done
-        out["_keepalive"] = (clouds, clips)   # read by other streams: must outlive this function's locals
+        out["_keepalive"] = (clouds, clips, gbuf)   # read by other streams: must outlive this function's locals
 
         # ---- ROIAlign forward (S4) and backward (S5) over the sampled RoIs: needs only the map. roi_gate
         #      optionally holds it back until the short, resource-hungry kernels of the chains above (sorts,
@@ -385,11 +390,12 @@ class RoIPathStep:
             fwd_done = s_roi.record_event()
 
         def run_backward():
+            s_roi.wait_event(gbuf_ready)
             with torch.cuda.stream(s_roi), _lib.options(**roi_opts):
                 n, c, h, w = d["features"].shape
                 out["grad_features"] = ops.roi_align_backward(self.head_grad, [(n, c, h, w)], scale, rois, None, size,
                                                               0, True, [self.io_dtype],
-                                                              events=ev["bwd"] if ev else None, perm=perm)[0]
+                                                              events=ev["bwd"] if ev else None, perm=perm, zeroed=[gbuf])[0]
                 self._mark("roi.end_bwd")
         if backward and self.c_mode != "between":
             run_backward()

@@ -224,6 +224,24 @@ def test_roi_launch_order_is_a_permutation_and_changes_nothing(dev, k, live):
         assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max())
 
 
+@pytest.mark.parametrize("v2", [0, 1])
+@pytest.mark.parametrize("shape", [(3, 1024, 37, 75), (2, 40, 5, 7), (1, 33, 1, 130), (1, 64, 16, 16)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_layout_transforms_are_exact_permutations(dev, v2, shape, dtype):
+    """coin_nchw_to_nhwc_f32 / coin_nhwc_f32_to_nchw (the [N,C,H,W] <-> [N,H,W,C] copies either side of the ROIAlign
+    kernels): bit-exact permutations for both tile shapes, ragged C and H*W, fp32 and fp16 boundaries."""
+    from coin_b200._lib import lib, check
+    n, c, h, w = shape
+    x = torch.randn(shape, generator=synth.gen(7)).to(dtype).to(dev)
+    with _lib.options(COIN_LAYOUT_V2=v2):
+        nhwc = ops.to_nhwc_f32(x)
+        assert torch.equal(nhwc, x.float().permute(0, 2, 3, 1).contiguous())
+        back = torch.empty(shape, dtype=dtype, device=dev)
+        check(lib.coin_nhwc_f32_to_nchw(ops._ptr(nhwc), ops._ptr(back), 0 if dtype == torch.float32 else 1, n, c, h, w,
+                                        ops._stream()))
+        assert torch.equal(back, x)
+
+
 @pytest.mark.parametrize("n_big", [0, 3, 40])
 def test_roi_launch_plan_orders_and_diverts(dev, n_big):
     """coin_roi_launch_plan = launch order + size split in one launch: perm is a permutation of the RoIs whose tail holds the
